@@ -1,0 +1,138 @@
+/*
+ * b200sr.h -- C ABI of the B200-native super-resolution forward path.
+ *
+ * The reference (zhuzhui-2000/mobilesuperresolution) is pure Python/PyTorch and defines NO FFI:
+ * its boundary for this path is the nn.Module surface.  These entry points are what
+ * a binding for that surface calls; each cites the reference interface it stands behind
+ * (paths relative to /root/reference).  The Python mirror of the nn.Module surface lives in
+ * mobilesuperresolution_b200/ and reaches this library through ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - Pointers named *_dev are CUDA device pointers, *_host are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Device entry points
+ *     never synchronise and never allocate: the caller passes a workspace.  They are CUDA-graph
+ *     capturable.
+ *   - Return value: 0 = ok, <0 = invalid argument (B200SR_E_*), >0 = cudaError_t.
+ *     b200sr_last_error() returns a thread-local message for the last non-zero return.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef B200SR_H_
+#define B200SR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SR_VERSION 1
+
+#if defined(__GNUC__)
+#define B200SR_API __attribute__((visibility("default")))
+#else
+#define B200SR_API
+#endif
+
+/* element types of activation tensors, and arithmetic precisions */
+#define B200SR_F32 0  /* float32 storage; true-fp32 FMA arithmetic                                  */
+#define B200SR_BF16 1 /* bfloat16 storage; bf16 tensor-core operands, fp32 accumulate/bias/residual */
+
+/* flow_warp padding modes (models/spynet_arch.py:98 `padding_mode`) */
+#define B200SR_PAD_ZEROS 0
+#define B200SR_PAD_BORDER 1
+
+/* activations for b200sr_conv2d_nhwc */
+#define B200SR_ACT_NONE 0
+#define B200SR_ACT_RELU 1
+#define B200SR_ACT_LRELU01 2 /* LeakyReLU(0.1), models/basicvsr_arch_origin.py:40 */
+
+#define B200SR_E_INVAL (-1)
+#define B200SR_E_STATE (-2)
+#define B200SR_E_WORKSPACE (-3)
+#define B200SR_E_UNSUPPORTED (-4)
+
+B200SR_API int b200sr_version(void);
+B200SR_API const char *b200sr_last_error(void);
+/* number of CUDA devices visible; <=0 means the library cannot compute */
+B200SR_API int b200sr_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * WDSR-B image path.
+ *   BASIC_MODEL.__init__/forward   models/basic_wdsr_b.py:16-93
+ *   Block                          models/basic_wdsr_b.py:96-144 == models/wdsr_b.py:253-319
+ *   pruned Model                   export_onnx.py:6-88  (per-block (IN,M1,M2), no "+ image_mean")
+ *   BinaryConv2d masks / depth gate are resolved by the host into (IN,M1,M2) and kept-block lists
+ *   before a plan is created (models/ops.py:7-43, models/wdsr_b.py:358-365).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200sr_wdsr b200sr_wdsr_t;
+
+typedef struct {
+    int32_t scale;       /* PixelShuffle factor s (2, 3 or 4); output channels = 3*s*s          */
+    int32_t num_blocks;  /* kept residual blocks (>= 0)                                         */
+    int32_t c_trunk;     /* trunk width IN (num_residual_units; 24 dense, 8..24 pruned)         */
+    int32_t add_mean;    /* 1: "+ image_mean" after the shuffle (BASIC_MODEL/NAS_MODEL), 0: export_onnx.Model */
+    float image_mean;    /* params.image_mean (0.5)                                             */
+    const int32_t *m1;   /* [num_blocks] expand widths  (144 dense)                             */
+    const int32_t *m2;   /* [num_blocks] reduce widths  (20 dense)                              */
+} b200sr_wdsr_desc;
+
+B200SR_API int b200sr_wdsr_create(const b200sr_wdsr_desc *desc, b200sr_wdsr_t **out);
+B200SR_API void b200sr_wdsr_destroy(b200sr_wdsr_t *plan);
+
+/* Weight-norm-FOLDED float32 filters in PyTorch OIHW order, host pointers; copied by the call.
+ *   head  w[IN][3][3][3]            b[IN]                  models/basic_wdsr_b.py:32-42
+ *   block w1[M1][IN] b1[M1]  w2[M2][M1] b2[M2]  w3[IN][M2][3][3] b3[IN]      :108-138
+ *   tail  wt[3ss][IN][3][3] bt[3ss]   skip ws[3ss][3][5][5] bs[3ss]           :55-78        */
+B200SR_API int b200sr_wdsr_set_head(b200sr_wdsr_t *plan, const float *w_host, const float *b_host);
+B200SR_API int b200sr_wdsr_set_block(b200sr_wdsr_t *plan, int block, const float *w1_host, const float *b1_host,
+                          const float *w2_host, const float *b2_host, const float *w3_host, const float *b3_host);
+B200SR_API int b200sr_wdsr_set_tail(b200sr_wdsr_t *plan, const float *wt_host, const float *bt_host, const float *ws_host,
+                         const float *bs_host);
+/* Pack (pad to tile multiples, round to bf16 once) and upload to the current device.  Synchronous. */
+B200SR_API int b200sr_wdsr_commit(b200sr_wdsr_t *plan);
+
+/* bytes of device workspace b200sr_wdsr_forward needs for an N x 3 x H x W input */
+B200SR_API size_t b200sr_wdsr_workspace_bytes(const b200sr_wdsr_t *plan, int n, int h, int w, int precision);
+
+/* y[N,3,sH,sW] = model(x[N,3,H,W]); x and y are contiguous NCHW (the reference's tensors,
+ * models/basic_wdsr_b.py:85-93).  x_dtype / y_dtype: element type of x / y; precision: arithmetic. */
+B200SR_API int b200sr_wdsr_forward(const b200sr_wdsr_t *plan, const void *x_dev, int x_dtype, void *y_dev, int y_dtype, int n,
+                        int h, int w, int precision, void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Same call with HOST buffers (pinned recommended): H2D copy, forward, D2H copy, all enqueued on
+ * `stream`; x_stage_dev / y_stage_dev are caller-provided device staging buffers of the tensors' sizes. */
+B200SR_API int b200sr_wdsr_forward_host(const b200sr_wdsr_t *plan, const void *x_host, int x_dtype, void *y_host, int y_dtype,
+                             int n, int h, int w, int precision, void *x_stage_dev, void *y_stage_dev,
+                             void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Stage-level entry points (parity tests).  Trunk tensors are NHWC with b200sr_wdsr_trunk_channels()
+ * channels (IN padded up to a multiple of 8; padding channels are zero), element type = precision. */
+B200SR_API int b200sr_wdsr_trunk_channels(const b200sr_wdsr_t *plan);
+B200SR_API int b200sr_wdsr_head(const b200sr_wdsr_t *plan, const void *x_dev, int x_dtype, void *trunk_dev, int n, int h, int w,
+                     int precision, void *stream);
+B200SR_API int b200sr_wdsr_block(const b200sr_wdsr_t *plan, int block, const void *trunk_in_dev, void *trunk_out_dev, int n,
+                      int h, int w, int precision, void *stream);
+B200SR_API int b200sr_wdsr_tail(const b200sr_wdsr_t *plan, const void *trunk_dev, const void *x_dev, int x_dtype, void *y_dev,
+                     int y_dtype, int n, int h, int w, int precision, void *stream);
+/* kernels launched by the last b200sr_wdsr_forward* call on this plan (bench "gpu_launches") */
+B200SR_API int b200sr_wdsr_launches_per_forward(const b200sr_wdsr_t *plan);
+
+/* ------------------------------------------------------------------------------------------------
+ * flow_warp(x, flow, 'bilinear', padding_mode, align_corners=True)   models/spynet_arch.py:98-129
+ * (mmedit twin used at models/basicvsr_arch.py:74,85; basicvsr_arch_origin.py:68,79).
+ * x, y: (n,c,h,w) NCHW float32 contiguous.  flow: float32, logical shape (n,h,w,2), addressed with
+ * ELEMENT strides so the caller's `.permute(0,2,3,1)` view of an (n,2,h,w) tensor is consumed as is.
+ * ---------------------------------------------------------------------------------------------- */
+B200SR_API int b200sr_flow_warp_nchw(const float *x_dev, const float *flow_dev, int64_t fs_n, int64_t fs_h, int64_t fs_w,
+                          int64_t fs_c, float *y_dev, int n, int c, int h, int w, int padding_mode, void *stream);
+/* NHWC variant used inside the video path: x,y (n,h,w,c) of `dtype`, c % 8 == 0 for bf16 / % 4 for f32;
+ * flow (n,2,h,w) float32 planar. */
+B200SR_API int b200sr_flow_warp_nhwc(const void *x_dev, const float *flow_nchw_dev, void *y_dev, int n, int c, int h, int w,
+                          int padding_mode, int dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SR_H_ */

@@ -1,0 +1,382 @@
+// b200sr.cu -- C ABI (include/b200sr.h): plan objects, host-side weight packing, forward orchestration.
+//
+// No CPU fallback lives here: every compute entry point launches the sm_100a kernels or fails.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200sr.h"
+#include "common.cuh"
+#include "launch.h"
+#include "wdsr_bf16.cuh"
+#include "wdsr_f32.cuh"
+
+using namespace b200sr;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    return fail((int)e, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+#define CU(call)                                        \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+uint16_t f2bf(float f) {  // round-to-nearest-even, same as __float2bfloat16_rn for finite values
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+size_t esize(int dtype) { return dtype == B200SR_F32 ? 4 : 2; }
+
+struct BlockW {
+    std::vector<float> w1, b1, w2, b2, w3, b3;
+    bool set = false;
+};
+
+}  // namespace
+
+struct b200sr_wdsr {
+    int scale = 0, nb = 0, cin = 0, cp = 0, add_mean = 1;
+    float mean = 0.5f;
+    int no = 0;  // 3*s*s
+    std::vector<int> m1, m2, m1p, m2p_f32, m2p_bf16;
+    std::vector<float> head_w, head_b, tail_w, tail_b, skip_w, skip_b;
+    bool head_set = false, tail_set = false, committed = false;
+    std::vector<BlockW> blocks;
+    int device = -1;
+    // device images
+    float *d_head = nullptr;
+    std::vector<float *> d_blk_f32;
+    std::vector<uint8_t *> d_blk_bf16;
+    float *d_tail_f32 = nullptr;
+    uint8_t *d_tail_bf16 = nullptr;
+    mutable int launches = 0;
+
+    void free_device() {
+        if (d_head) cudaFree(d_head), d_head = nullptr;
+        for (auto p : d_blk_f32) cudaFree(p);
+        for (auto p : d_blk_bf16) cudaFree(p);
+        d_blk_f32.clear(), d_blk_bf16.clear();
+        if (d_tail_f32) cudaFree(d_tail_f32), d_tail_f32 = nullptr;
+        if (d_tail_bf16) cudaFree(d_tail_bf16), d_tail_bf16 = nullptr;
+    }
+};
+
+extern "C" {
+
+int b200sr_version(void) { return B200SR_VERSION; }
+const char *b200sr_last_error(void) { return g_err.c_str(); }
+int b200sr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int b200sr_wdsr_create(const b200sr_wdsr_desc *d, b200sr_wdsr_t **out) {
+    if (!d || !out) return fail(B200SR_E_INVAL, "wdsr_create: null argument");
+    if (d->scale < 2 || d->scale > 4) return fail(B200SR_E_UNSUPPORTED, "wdsr_create: scale %d not in {2,3,4}", d->scale);
+    if (d->c_trunk < 1 || d->c_trunk > 24)
+        return fail(B200SR_E_UNSUPPORTED, "wdsr_create: trunk width %d not in [1,24]", d->c_trunk);
+    if (d->num_blocks < 0 || (d->num_blocks > 0 && (!d->m1 || !d->m2))) return fail(B200SR_E_INVAL, "wdsr_create: bad block list");
+    b200sr_wdsr *p = new (std::nothrow) b200sr_wdsr();
+    if (!p) return fail(B200SR_E_INVAL, "wdsr_create: out of memory");
+    p->scale = d->scale, p->nb = d->num_blocks, p->cin = d->c_trunk, p->cp = round_up(d->c_trunk, 8);
+    p->add_mean = d->add_mean, p->mean = d->image_mean, p->no = 3 * d->scale * d->scale;
+    for (int i = 0; i < p->nb; ++i) {
+        const int m1 = d->m1[i], m2 = d->m2[i];
+        if (m1 < 1 || m1 > 160 || m2 < 1 || m2 > 24) {
+            delete p;
+            return fail(B200SR_E_UNSUPPORTED, "wdsr_create: block %d widths (M1=%d, M2=%d) outside [1,160]x[1,24]", i, m1, m2);
+        }
+        p->m1.push_back(m1), p->m2.push_back(m2);
+        p->m1p.push_back(round_up(m1, 16));
+        p->m2p_f32.push_back(round_up(m2, 4) < 8 ? 8 : round_up(m2, 4));
+        p->m2p_bf16.push_back(round_up(m2, 8));
+    }
+    p->blocks.resize(p->nb);
+    *out = p;
+    return 0;
+}
+
+void b200sr_wdsr_destroy(b200sr_wdsr_t *p) {
+    if (!p) return;
+    p->free_device();
+    delete p;
+}
+
+int b200sr_wdsr_set_head(b200sr_wdsr_t *p, const float *w, const float *b) {
+    if (!p || !w || !b) return fail(B200SR_E_INVAL, "set_head: null argument");
+    p->head_w.assign(w, w + (size_t)p->cin * 27);
+    p->head_b.assign(b, b + p->cin);
+    p->head_set = true, p->committed = false;
+    return 0;
+}
+
+int b200sr_wdsr_set_block(b200sr_wdsr_t *p, int i, const float *w1, const float *b1, const float *w2, const float *b2,
+                          const float *w3, const float *b3) {
+    if (!p || !w1 || !b1 || !w2 || !b2 || !w3 || !b3) return fail(B200SR_E_INVAL, "set_block: null argument");
+    if (i < 0 || i >= p->nb) return fail(B200SR_E_INVAL, "set_block: block %d out of range [0,%d)", i, p->nb);
+    BlockW &k = p->blocks[i];
+    const int m1 = p->m1[i], m2 = p->m2[i], c = p->cin;
+    k.w1.assign(w1, w1 + (size_t)m1 * c), k.b1.assign(b1, b1 + m1);
+    k.w2.assign(w2, w2 + (size_t)m2 * m1), k.b2.assign(b2, b2 + m2);
+    k.w3.assign(w3, w3 + (size_t)c * m2 * 9), k.b3.assign(b3, b3 + c);
+    k.set = true, p->committed = false;
+    return 0;
+}
+
+int b200sr_wdsr_set_tail(b200sr_wdsr_t *p, const float *wt, const float *bt, const float *ws, const float *bs) {
+    if (!p || !wt || !bt || !ws || !bs) return fail(B200SR_E_INVAL, "set_tail: null argument");
+    p->tail_w.assign(wt, wt + (size_t)p->no * p->cin * 9), p->tail_b.assign(bt, bt + p->no);
+    p->skip_w.assign(ws, ws + (size_t)p->no * 75), p->skip_b.assign(bs, bs + p->no);
+    p->tail_set = true, p->committed = false;
+    return 0;
+}
+
+static int upload(const void *host, size_t bytes, void **dev) {
+    CU(cudaMalloc(dev, bytes));
+    CU(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
+    if (!p) return fail(B200SR_E_INVAL, "commit: null plan");
+    if (!p->head_set || !p->tail_set) return fail(B200SR_E_STATE, "commit: head/tail weights not set");
+    for (int i = 0; i < p->nb; ++i)
+        if (!p->blocks[i].set) return fail(B200SR_E_STATE, "commit: block %d weights not set", i);
+    if (b200sr_device_count() <= 0) return fail(B200SR_E_STATE, "commit: no CUDA device (this library has no CPU fallback)");
+    CU(cudaGetDevice(&p->device));
+    p->free_device();
+    const int C = p->cin, CP = p->cp;
+    int rc;
+    {   // head: [27][CP] (k = c*9+ky*3+kx) + bias[CP]
+        std::vector<float> h((size_t)27 * CP + CP, 0.f);
+        for (int o = 0; o < C; ++o) {
+            for (int k = 0; k < 27; ++k) h[(size_t)k * CP + o] = p->head_w[(size_t)o * 27 + k];
+            h[(size_t)27 * CP + o] = p->head_b[o];
+        }
+        if ((rc = upload(h.data(), h.size() * 4, (void **)&p->d_head))) return rc;
+    }
+    for (int i = 0; i < p->nb; ++i) {
+        const BlockW &k = p->blocks[i];
+        const int M1 = p->m1[i], M2 = p->m2[i], M1P = p->m1p[i];
+        {   // fp32 image
+            const int M2P = p->m2p_f32[i];
+            BlockF32Layout L(CP, M1P, M2P);
+            std::vector<float> f((size_t)L.total, 0.f);
+            for (int m = 0; m < M1; ++m) {
+                for (int c = 0; c < C; ++c) f[L.w1 + (size_t)m * CP + c] = k.w1[(size_t)m * C + c];
+                f[L.b1 + m] = k.b1[m];
+                for (int j = 0; j < M2; ++j) f[L.w2 + (size_t)m * M2P + j] = k.w2[(size_t)j * M1 + m];
+            }
+            for (int j = 0; j < M2; ++j) f[L.b2 + j] = k.b2[j];
+            for (int o = 0; o < C; ++o) {
+                for (int j = 0; j < M2; ++j)
+                    for (int tap = 0; tap < 9; ++tap)
+                        f[L.w3 + ((size_t)tap * M2P + j) * CP + o] = k.w3[((size_t)o * M2 + j) * 9 + tap];
+                f[L.b3 + o] = k.b3[o];
+            }
+            float *d = nullptr;
+            if ((rc = upload(f.data(), f.size() * 4, (void **)&d))) return rc;
+            p->d_blk_f32.push_back(d);
+        }
+        {   // bf16 image (verbatim shared-memory layout)
+            const int M2P = p->m2p_bf16[i];
+            BlockBf16Layout L(CP, M1P, M2P);
+            std::vector<uint8_t> img((size_t)L.total, 0);
+            uint16_t *w1 = (uint16_t *)(img.data() + L.w1), *w2 = (uint16_t *)(img.data() + L.w2),
+                     *w3 = (uint16_t *)(img.data() + L.w3);
+            float *b1 = (float *)(img.data() + L.b1), *b2 = (float *)(img.data() + L.b2), *b3 = (float *)(img.data() + L.b3);
+            for (int m = 0; m < M1; ++m) {
+                for (int c = 0; c < C; ++c) w1[(size_t)m * L.s1 + c] = f2bf(k.w1[(size_t)m * C + c]);
+                b1[m] = k.b1[m];
+            }
+            for (int j = 0; j < M2; ++j) {
+                for (int m = 0; m < M1; ++m) w2[(size_t)j * L.s2 + m] = f2bf(k.w2[(size_t)j * M1 + m]);
+                b2[j] = k.b2[j];
+            }
+            for (int o = 0; o < C; ++o) {
+                for (int j = 0; j < M2; ++j)
+                    for (int tap = 0; tap < 9; ++tap)
+                        w3[((size_t)tap * CP + o) * L.s3 + j] = f2bf(k.w3[((size_t)o * M2 + j) * 9 + tap]);
+                b3[o] = k.b3[o];
+            }
+            uint8_t *d = nullptr;
+            if ((rc = upload(img.data(), img.size(), (void **)&d))) return rc;
+            p->d_blk_bf16.push_back(d);
+        }
+    }
+    const int NO = p->no;
+    {   // tail fp32: Wt[9][CP][NOP4] | Ws[75][NOP4] | bias[NOP4]
+        const int NOP = round_up(NO, 4);
+        std::vector<float> f((size_t)9 * CP * NOP + 75 * NOP + NOP, 0.f);
+        float *wt = f.data(), *ws = wt + (size_t)9 * CP * NOP, *bias = ws + (size_t)75 * NOP;
+        for (int o = 0; o < NO; ++o) {
+            for (int c = 0; c < C; ++c)
+                for (int tap = 0; tap < 9; ++tap) wt[((size_t)tap * CP + c) * NOP + o] = p->tail_w[((size_t)o * C + c) * 9 + tap];
+            for (int k = 0; k < 75; ++k) ws[(size_t)k * NOP + o] = p->skip_w[(size_t)o * 75 + k];
+            bias[o] = p->tail_b[o] + p->skip_b[o];
+        }
+        if ((rc = upload(f.data(), f.size() * 4, (void **)&p->d_tail_f32))) return rc;
+    }
+    {   // tail bf16: Wt[9][NOP8][st] | Ws[NOP8][120] (k = ky*24 + dx*4 + c) | bias[NOP8]
+        const int NOP = round_up(NO, 8);
+        TailBf16Layout L(CP, NOP);
+        std::vector<uint8_t> img((size_t)L.total, 0);
+        uint16_t *wt = (uint16_t *)(img.data() + L.wt), *ws = (uint16_t *)(img.data() + L.ws);
+        float *bias = (float *)(img.data() + L.bias);
+        for (int o = 0; o < NO; ++o) {
+            for (int c = 0; c < C; ++c)
+                for (int tap = 0; tap < 9; ++tap)
+                    wt[((size_t)tap * NOP + o) * L.st + c] = f2bf(p->tail_w[((size_t)o * C + c) * 9 + tap]);
+            for (int c = 0; c < 3; ++c)
+                for (int ky = 0; ky < 5; ++ky)
+                    for (int kx = 0; kx < 5; ++kx)
+                        ws[(size_t)o * 120 + ky * 24 + kx * 4 + c] = f2bf(p->skip_w[(size_t)o * 75 + c * 25 + ky * 5 + kx]);
+            bias[o] = p->tail_b[o] + p->skip_b[o];
+        }
+        if ((rc = upload(img.data(), img.size(), (void **)&p->d_tail_bf16))) return rc;
+    }
+    p->committed = true;
+    return 0;
+}
+
+int b200sr_wdsr_trunk_channels(const b200sr_wdsr_t *p) { return p ? p->cp : 0; }
+int b200sr_wdsr_launches_per_forward(const b200sr_wdsr_t *p) { return p ? p->launches : 0; }
+
+size_t b200sr_wdsr_workspace_bytes(const b200sr_wdsr_t *p, int n, int h, int w, int precision) {
+    if (!p || n <= 0 || h <= 0 || w <= 0) return 0;
+    const size_t trunk = round_up((int)(((size_t)n * h * w * p->cp * esize(precision) + 255) / 256), 1) * (size_t)256;
+    return 2 * trunk;
+}
+
+static int check_common(const b200sr_wdsr_t *p, int n, int h, int w, int precision, const char *who) {
+    if (!p) return fail(B200SR_E_INVAL, "%s: null plan", who);
+    if (!p->committed) return fail(B200SR_E_STATE, "%s: weights not committed", who);
+    if (n <= 0 || h <= 0 || w <= 0) return fail(B200SR_E_INVAL, "%s: bad shape n=%d h=%d w=%d", who, n, h, w);
+    if (precision != B200SR_F32 && precision != B200SR_BF16) return fail(B200SR_E_INVAL, "%s: bad precision %d", who, precision);
+    if ((long long)n * h * w * p->scale * p->scale * 3 >= (1ll << 40)) return fail(B200SR_E_INVAL, "%s: tensor too large", who);
+    return 0;
+}
+
+int b200sr_wdsr_head(const b200sr_wdsr_t *p, const void *x, int x_dtype, void *trunk, int n, int h, int w, int precision,
+                     void *stream) {
+    int rc = check_common(p, n, h, w, precision, "wdsr_head");
+    if (rc) return rc;
+    if (!x || !trunk) return fail(B200SR_E_INVAL, "wdsr_head: null tensor");
+    CU(launch_head(p->cp, x_dtype, precision, x, trunk, p->d_head, n, h, w, p->mean, (cudaStream_t)stream));
+    return 0;
+}
+
+int b200sr_wdsr_block(const b200sr_wdsr_t *p, int i, const void *tin, void *tout, int n, int h, int w, int precision,
+                      void *stream) {
+    int rc = check_common(p, n, h, w, precision, "wdsr_block");
+    if (rc) return rc;
+    if (i < 0 || i >= p->nb) return fail(B200SR_E_INVAL, "wdsr_block: block %d out of range", i);
+    if (!tin || !tout || tin == tout) return fail(B200SR_E_INVAL, "wdsr_block: in/out must be distinct non-null buffers");
+    if (precision == B200SR_F32)
+        CU(launch_block_f32(p->cp, p->m2p_f32[i], (const float *)tin, (float *)tout, p->d_blk_f32[i], p->m1p[i], n, h, w,
+                            (cudaStream_t)stream));
+    else
+        CU(launch_block_bf16(p->cp, p->m2p_bf16[i], tin, tout, p->d_blk_bf16[i], p->m1p[i], n, h, w, (cudaStream_t)stream));
+    return 0;
+}
+
+int b200sr_wdsr_tail(const b200sr_wdsr_t *p, const void *trunk, const void *x, int x_dtype, void *y, int y_dtype, int n,
+                     int h, int w, int precision, void *stream) {
+    int rc = check_common(p, n, h, w, precision, "wdsr_tail");
+    if (rc) return rc;
+    if (!trunk || !x || !y) return fail(B200SR_E_INVAL, "wdsr_tail: null tensor");
+    const float out_add = p->add_mean ? p->mean : 0.f;
+    if (precision == B200SR_F32)
+        CU(launch_tail_f32(p->cp, p->scale, x_dtype, y_dtype, (const float *)trunk, x, y, p->d_tail_f32, n, h, w, p->mean,
+                           out_add, (cudaStream_t)stream));
+    else
+        CU(launch_tail_bf16(p->cp, p->scale, x_dtype, y_dtype, trunk, x, y, p->d_tail_bf16, n, h, w, p->mean, out_add,
+                            (cudaStream_t)stream));
+    return 0;
+}
+
+int b200sr_wdsr_forward(const b200sr_wdsr_t *p, const void *x, int x_dtype, void *y, int y_dtype, int n, int h, int w,
+                        int precision, void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_common(p, n, h, w, precision, "wdsr_forward");
+    if (rc) return rc;
+    if (!x || !y || !ws) return fail(B200SR_E_INVAL, "wdsr_forward: null tensor/workspace");
+    const size_t need = b200sr_wdsr_workspace_bytes(p, n, h, w, precision);
+    if (ws_bytes < need) return fail(B200SR_E_WORKSPACE, "wdsr_forward: workspace %zu < %zu bytes", ws_bytes, need);
+    uint8_t *a = (uint8_t *)ws, *b = a + need / 2;
+    int launches = 0;
+    if ((rc = b200sr_wdsr_head(p, x, x_dtype, a, n, h, w, precision, stream))) return rc;
+    ++launches;
+    for (int i = 0; i < p->nb; ++i) {
+        if ((rc = b200sr_wdsr_block(p, i, a, b, n, h, w, precision, stream))) return rc;
+        ++launches;
+        uint8_t *t = a;
+        a = b, b = t;
+    }
+    if ((rc = b200sr_wdsr_tail(p, a, x, x_dtype, y, y_dtype, n, h, w, precision, stream))) return rc;
+    p->launches = launches + 1;
+    return 0;
+}
+
+int b200sr_wdsr_forward_host(const b200sr_wdsr_t *p, const void *xh, int x_dtype, void *yh, int y_dtype, int n, int h, int w,
+                             int precision, void *xd, void *yd, void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_common(p, n, h, w, precision, "wdsr_forward_host");
+    if (rc) return rc;
+    if (!xh || !yh || !xd || !yd) return fail(B200SR_E_INVAL, "wdsr_forward_host: null buffer");
+    const size_t xb = (size_t)n * 3 * h * w * esize(x_dtype);
+    const size_t yb = (size_t)n * 3 * h * w * p->scale * p->scale * esize(y_dtype);
+    CU(cudaMemcpyAsync(xd, xh, xb, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    if ((rc = b200sr_wdsr_forward(p, xd, x_dtype, yd, y_dtype, n, h, w, precision, ws, ws_bytes, stream))) return rc;
+    CU(cudaMemcpyAsync(yh, yd, yb, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+
+int b200sr_flow_warp_nchw(const float *x, const float *flow, int64_t fs_n, int64_t fs_h, int64_t fs_w, int64_t fs_c, float *y,
+                          int n, int c, int h, int w, int padding_mode, void *stream) {
+    if (!x || !flow || !y) return fail(B200SR_E_INVAL, "flow_warp: null tensor");
+    if (n < 0 || c < 0 || h <= 0 || w <= 0) return fail(B200SR_E_INVAL, "flow_warp: bad shape");
+    if (padding_mode != B200SR_PAD_ZEROS && padding_mode != B200SR_PAD_BORDER)
+        return fail(B200SR_E_UNSUPPORTED, "flow_warp: padding_mode %d (only zeros/border)", padding_mode);
+    CU(launch_flow_warp_nchw(x, flow, fs_n, fs_h, fs_w, fs_c, y, n, c, h, w, padding_mode == B200SR_PAD_BORDER,
+                             (cudaStream_t)stream));
+    return 0;
+}
+
+int b200sr_flow_warp_nhwc(const void *x, const float *flow, void *y, int n, int c, int h, int w, int padding_mode, int dtype,
+                          void *stream) {
+    if (!x || !flow || !y) return fail(B200SR_E_INVAL, "flow_warp_nhwc: null tensor");
+    if (padding_mode != B200SR_PAD_ZEROS && padding_mode != B200SR_PAD_BORDER)
+        return fail(B200SR_E_UNSUPPORTED, "flow_warp_nhwc: padding_mode %d", padding_mode);
+    cudaError_t e = launch_flow_warp_nhwc(x, flow, y, n, c, h, w, padding_mode == B200SR_PAD_BORDER, dtype, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "flow_warp_nhwc (c must be a multiple of 8 (bf16) / 4 (f32), c*esize/16 in {1,2,3,4,6,8,16})");
+    return 0;
+}
+
+}  // extern "C"

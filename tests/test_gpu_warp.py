@@ -1,0 +1,84 @@
+"""GPU parity: flow_warp kernels against the golden vectors / oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def V():
+    from mobilesuperresolution_b200 import video
+    assert torch.cuda.is_available()
+    return video
+
+
+@pytest.mark.parametrize("mode", ["zeros", "border"])
+def test_flow_warp_golden(V, mode):
+    from oracle import synth
+    meta, arrs = load_golden("flow_warp_small")
+    x = torch.from_numpy(synth.synth_input(meta["xshape"], meta["xseed"], meta["xlo"], meta["xhi"])).cuda()
+    fl = torch.from_numpy(synth.synth_input(meta["fshape"], meta["fseed"], meta["flo"], meta["fhi"])).cuda()
+    y = V.flow_warp(x, fl, padding_mode=mode).cpu().numpy()
+    assert np.abs(y - arrs[mode]).max() <= 1e-5
+
+
+def test_flow_warp_kat4(V, kat):
+    g = torch.Generator().manual_seed(9)
+    feat = torch.rand(1, 8, 45, 80, generator=g)
+    fl = (torch.rand(1, 45, 80, 2, generator=g) - 0.5) * 20
+    wz = V.flow_warp(feat.cuda(), fl.cuda()).cpu()
+    wb = V.flow_warp(feat.cuda(), fl.cuda(), padding_mode="border").cpu()
+    assert abs(float(wz.double().sum()) - kat["KAT4"]["zeros_sum"]) < 5e-2
+    assert abs(float(wb.double().sum()) - kat["KAT4"]["border_sum"]) < 5e-2
+    assert float(wz[0, 0, 0, 0]) == 0.0 and abs(float(wz[0, 3, 22, 40]) - kat["KAT4"]["w[0,3,22,40]"]) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["zeros", "border"])
+def test_flow_warp_permuted_view_and_oob(V, mode):
+    """The callers pass flow.permute(0,2,3,1) of an (n,2,h,w) tensor (basicvsr_arch_origin.py:68): consumed as a view.
+    Flows of +-40 px on a 31x50 image push most samples out of the image."""
+    from oracle import port
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 7, 31, 50, generator=g)
+    fl = (torch.rand(2, 2, 31, 50, generator=g) - 0.5) * 80
+    ref = port.flow_warp(x, fl.permute(0, 2, 3, 1), padding_mode=mode)
+    y = V.flow_warp(x.cuda(), fl.cuda().permute(0, 2, 3, 1), padding_mode=mode).cpu()
+    assert float((y - ref).abs().max()) <= 1e-5
+
+
+def test_flow_warp_asserts_like_reference(V):
+    with pytest.raises(AssertionError):
+        V.flow_warp(torch.zeros(1, 2, 4, 4).cuda(), torch.zeros(1, 5, 4, 2).cuda())
+    with pytest.raises(RuntimeError):
+        V.flow_warp(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4, 2))          # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("dtype,c", [(torch.float32, 64), (torch.bfloat16, 64), (torch.bfloat16, 24), (torch.float32, 8)])
+@pytest.mark.parametrize("mode", ["zeros", "border"])
+def test_flow_warp_nhwc(V, dtype, c, mode):
+    from oracle import port
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, c, 45, 77, generator=g)
+    fl = (torch.rand(2, 2, 45, 77, generator=g) - 0.5) * 30
+    xq = x.to(dtype).float()
+    ref = port.flow_warp(xq, fl.permute(0, 2, 3, 1), padding_mode=mode)
+    y = V.flow_warp_nhwc(xq.permute(0, 2, 3, 1).contiguous().to(dtype).cuda(), fl.cuda(), padding_mode=mode)
+    y = y.float().cpu().permute(0, 3, 1, 2)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert float((y - ref).abs().max()) <= tol
+
+
+def test_flow_warp_full_size_identity_and_shift(V):
+    """cfg4 size (64ch, 180x320): zero flow is the identity and an integer flow a pure shift -- up to the ~1e-6
+    bilinear leakage of the reference's own fp32 normalise/un-normalise round trip, which the kernel replays."""
+    x = torch.randn(1, 64, 180, 320, generator=torch.Generator().manual_seed(8)).cuda()
+    z = torch.zeros(1, 180, 320, 2, device="cuda")
+    assert float((V.flow_warp(x, z) - x).abs().max()) <= 2e-5
+    s = z.clone()
+    s[..., 0], s[..., 1] = 3.0, -2.0
+    y = V.flow_warp(x, s)
+    assert float((y[:, :, 2:, :-3] - x[:, :, :-2, 3:]).abs().max()) <= 2e-5
+    assert float(y[:, :, :1].abs().max()) <= 2e-5 and float(y[:, :, :, -2:].abs().max()) <= 2e-5
