@@ -35,7 +35,7 @@ class BinaryConv2d(nn.Conv2d):
         init.constant_(self.weight, value)
 
     def keep_indices(self) -> torch.Tensor:
-        keep = rounding(self.weight.detach(), self.least_channel).view(-1)
+        keep = rounding(self.weight.detach().float().cpu(), self.least_channel).view(-1)
         return torch.nonzero(keep > 0, as_tuple=False).view(-1)
 
     def forward(self, x, y=None):

@@ -436,7 +436,7 @@ class NAS_MODEL(_WdsrNet):
     @torch.no_grad()
     def get_width_from_block_idx(self, remain_block_idx) -> List[List[int]]:
         """(IN, M1, M2) per kept block -- the ``block_index.txt`` triple ``export_onnx.Model`` consumes."""
-        n_in = int(rounding(self.mask.weight).sum()) if self.width_search else self.num_residual_units
+        n_in = int(rounding(self.mask.weight.detach().cpu()).sum()) if self.width_search else self.num_residual_units
         out = []
         for i, m in enumerate(self.body):
             if i in remain_block_idx:
@@ -456,7 +456,7 @@ class NAS_MODEL(_WdsrNet):
 
     @torch.no_grad()
     def speed_accu(self) -> torch.Tensor:
-        c0 = float(rounding(self.mask.weight).sum()) if self.width_search else float(self.num_residual_units)
+        c0 = float(rounding(self.mask.weight.detach().cpu()).sum()) if self.width_search else float(self.num_residual_units)
         total = torch.zeros(1)
         for m in self.body:
             f = m.pruned_filters()

@@ -72,13 +72,23 @@ def test_flow_warp_nhwc(V, dtype, c, mode):
 
 
 def test_flow_warp_full_size_identity_and_shift(V):
-    """cfg4 size (64ch, 180x320): zero flow is the identity and an integer flow a pure shift -- up to the ~1e-6
-    bilinear leakage of the reference's own fp32 normalise/un-normalise round trip, which the kernel replays."""
-    x = torch.randn(1, 64, 180, 320, generator=torch.Generator().manual_seed(8)).cuda()
+    """cfg4 size (64ch, 180x320) against the oracle, plus two size-independent properties: zero flow is the identity
+    and an integer flow a pure shift -- both only up to the bilinear leakage of the reference's own fp32
+    normalise/un-normalise round trip (position error ~2e-5 px at x~300 times the local gradient), which the kernel
+    replays rather than "fixes"."""
+    from oracle import port
+    xc = torch.randn(1, 64, 180, 320, generator=torch.Generator().manual_seed(8))
+    x = xc.cuda()
     z = torch.zeros(1, 180, 320, 2, device="cuda")
-    assert float((V.flow_warp(x, z) - x).abs().max()) <= 2e-5
+    y0 = V.flow_warp(x, z)
+    assert float((y0 - x).abs().max()) <= 5e-4
+    assert float((y0.cpu() - port.flow_warp(xc, z.cpu())).abs().max()) <= 2e-5
     s = z.clone()
     s[..., 0], s[..., 1] = 3.0, -2.0
     y = V.flow_warp(x, s)
-    assert float((y[:, :, 2:, :-3] - x[:, :, :-2, 3:]).abs().max()) <= 2e-5
-    assert float(y[:, :, :1].abs().max()) <= 2e-5 and float(y[:, :, :, -2:].abs().max()) <= 2e-5
+    assert float((y[:, :, 2:, :-3] - x[:, :, :-2, 3:]).abs().max()) <= 5e-4
+    assert float(y[:, :, :1].abs().max()) <= 5e-4 and float(y[:, :, :, -2:].abs().max()) <= 5e-4
+    fl = (torch.rand(1, 180, 320, 2, generator=torch.Generator().manual_seed(9)) - 0.5) * 30
+    for mode in ("zeros", "border"):
+        ref = port.flow_warp(xc, fl, padding_mode=mode)
+        assert float((V.flow_warp(x, fl.cuda(), padding_mode=mode).cpu() - ref).abs().max()) <= 2e-5
