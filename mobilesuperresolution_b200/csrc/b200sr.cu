@@ -16,6 +16,9 @@
 #include "launch.h"
 #include "wdsr_bf16.cuh"
 #include "wdsr_f32.cuh"
+#include "wdsr_tc5_layout.cuh"
+
+#include <cstdlib>
 
 using namespace b200sr;
 
@@ -71,6 +74,8 @@ struct b200sr_wdsr {
     float *d_head = nullptr;
     std::vector<float *> d_blk_f32;
     std::vector<uint8_t *> d_blk_bf16;
+    std::vector<uint8_t *> d_blk_tc5;  // tcgen05 operand images (nullptr where the block is not eligible)
+    int block_impl = 0;                // 0 = mma.sync kernel, 1 = tcgen05 sequential form, 2 = tcgen05 pipelined form
     float *d_tail_f32 = nullptr;
     uint8_t *d_tail_bf16 = nullptr;
     mutable int launches = 0;
@@ -79,7 +84,9 @@ struct b200sr_wdsr {
         if (d_head) cudaFree(d_head), d_head = nullptr;
         for (auto p : d_blk_f32) cudaFree(p);
         for (auto p : d_blk_bf16) cudaFree(p);
-        d_blk_f32.clear(), d_blk_bf16.clear();
+        for (auto p : d_blk_tc5)
+            if (p) cudaFree(p);
+        d_blk_f32.clear(), d_blk_bf16.clear(), d_blk_tc5.clear();
         if (d_tail_f32) cudaFree(d_tail_f32), d_tail_f32 = nullptr;
         if (d_tail_bf16) cudaFree(d_tail_bf16), d_tail_bf16 = nullptr;
     }
@@ -231,6 +238,42 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
             if ((rc = upload(img.data(), img.size(), (void **)&d))) return rc;
             p->d_blk_bf16.push_back(d);
         }
+        if (CP == 24 && M2 <= 24) {   // tcgen05 operand image (interleaved K-major core matrices, see wdsr_tc5.cuh)
+            BlockTc5Layout L(M1P);
+            std::vector<uint8_t> img((size_t)L.total, 0);
+            auto at = [&](int off) { return (uint16_t *)(img.data() + off); };
+            for (int n = 0; n < M1; ++n) {
+                for (int c = 0; c < C; ++c) at(L.w1 + (n / 8) * 512 + (c / 8) * 128 + (n % 8) * 16)[c % 8] = f2bf(k.w1[(size_t)n * C + c]);
+                const uint16_t hi = f2bf(k.b1[n]);
+                uint32_t hu = (uint32_t)hi << 16;
+                float hf;
+                memcpy(&hf, &hu, 4);
+                uint16_t *bc = at(L.w1 + (n / 8) * 512 + 3 * 128 + (n % 8) * 16);
+                bc[0] = hi, bc[1] = f2bf(k.b1[n] - hf);          // b1 = hi + lo against the two constant-one channels
+            }
+            for (int j = 0; j < M2; ++j)
+                for (int m = 0; m < M1; ++m)
+                    at(L.w2 + (j / 8) * L.sbo2 + (m / 8) * 128 + (j % 8) * 16)[m % 8] = f2bf(k.w2[(size_t)j * M1 + m]);
+            for (int o = 0; o < C; ++o)
+                for (int j = 0; j < M2; ++j)
+                    for (int dy = 0; dy < 3; ++dy)
+                        for (int dx = 0; dx < 3; ++dx) {
+                            const int q = (dx * 3 + dy) * 3 + j / 8;
+                            at(L.w3 + (o / 8) * (28 * 128) + q * 128 + (o % 8) * 16)[j % 8] = f2bf(k.w3[((size_t)o * M2 + j) * 9 + dy * 3 + dx]);
+                        }
+            float *b2 = (float *)(img.data() + L.b2), *b3 = (float *)(img.data() + L.b3);
+            for (int j = 0; j < M2; ++j) b2[j] = k.b2[j];
+            for (int o = 0; o < C; ++o) b3[o] = k.b3[o];
+            uint8_t *d = nullptr;
+            if ((rc = upload(img.data(), img.size(), (void **)&d))) return rc;
+            p->d_blk_tc5.push_back(d);
+        } else {
+            p->d_blk_tc5.push_back(nullptr);
+        }
+    }
+    {
+        const char *e = getenv("B200SR_BLOCK_IMPL");   // developer switch: mma | tc5seq | tc5
+        p->block_impl = !e ? 0 : !strcmp(e, "tc5seq") ? 1 : !strcmp(e, "tc5") ? 2 : 0;
     }
     const int NO = p->no;
     {   // tail fp32: Wt[9][CP][NOP4] | Ws[75][NOP4] | bias[NOP4]
@@ -303,6 +346,8 @@ int b200sr_wdsr_block(const b200sr_wdsr_t *p, int i, const void *tin, void *tout
     if (precision == B200SR_F32)
         CU(launch_block_f32(p->cp, p->m2p_f32[i], (const float *)tin, (float *)tout, p->d_blk_f32[i], p->m1p[i], n, h, w,
                             (cudaStream_t)stream));
+    else if (p->block_impl && p->d_blk_tc5[i])
+        CU(launch_block_tc5(p->block_impl - 1, tin, tout, p->d_blk_tc5[i], p->m1p[i], n, h, w, (cudaStream_t)stream));
     else
         CU(launch_block_bf16(p->cp, p->m2p_bf16[i], tin, tout, p->d_blk_bf16[i], p->m1p[i], n, h, w, (cudaStream_t)stream));
     return 0;
