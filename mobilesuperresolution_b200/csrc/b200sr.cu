@@ -272,8 +272,10 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
         }
     }
     {
-        const char *e = getenv("B200SR_BLOCK_IMPL");   // developer switch: mma | tc5seq | tc5
-        p->block_impl = !e ? 0 : !strcmp(e, "tc5seq") ? 1 : !strcmp(e, "tc5") ? 2 : 0;
+        // default: the tcgen05 kernel wherever a block is eligible (trunk padded to 24, M2 <= 24), the mma.sync kernel
+        // elsewhere.  B200SR_BLOCK_IMPL = mma | tc5seq | tc5 is a developer switch (A/B timing, reference form).
+        const char *e = getenv("B200SR_BLOCK_IMPL");
+        p->block_impl = !e ? 2 : !strcmp(e, "mma") ? 0 : !strcmp(e, "tc5seq") ? 1 : 2;
     }
     const int NO = p->no;
     {   // tail fp32: Wt[9][CP][NOP4] | Ws[75][NOP4] | bias[NOP4]

@@ -23,6 +23,16 @@
 #include "tc5.cuh"
 #include "wdsr_tc5_layout.cuh"
 
+// Optional phase timers for tools/tc5_probe.cu (compiled out of the library).
+#ifdef B200SR_TC5_PROF
+__device__ unsigned long long g_tc5_prof[64];
+#define TC5_T0() const long long prof_t0__ = clock64()
+#define TC5_ADD(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_tc5_prof[i] += (unsigned long long)(clock64() - prof_t0__); } while (0)
+#else
+#define TC5_T0() do {} while (0)
+#define TC5_ADD(i) do {} while (0)
+#endif
+
 namespace b200sr {
 
 __global__ void __launch_bounds__(128, 1)
@@ -70,6 +80,7 @@ wdsr_block_tc5_seq_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, c
         const int x0 = tx * TW - 1, y0 = ty * TH - 1;
 
         // ---- stage the trunk tile + halo in the interleaved operand layout
+        { TC5_T0();
         for (int i = tid; i < HP * 3; i += 128) {
             const int p = i / 3, q = i - 3 * p;
             const int gy = y0 + p / HW_, gx = x0 + p % HW_;
@@ -81,8 +92,10 @@ wdsr_block_tc5_seq_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, c
         cp_async_wait<0>();
         tc5::fence_proxy_async();
         __syncthreads();
+        TC5_ADD(0); }
 
         for (int m = 0; m < NMT; ++m) {
+            { TC5_T0();
             if (tid == 0) {  // G1
                 tc5::fence_after_sync();
                 const uint32_t a = xs_u + m * 16 * XS_GROUP;
@@ -94,6 +107,8 @@ wdsr_block_tc5_seq_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, c
             tc5::mbar_wait(bar, phase);
             phase ^= 1;
             tc5::fence_after_sync();
+            TC5_ADD(1); }
+            { TC5_T0();
             // E1: relu -> bf16, in place
             for (int k = 0; k < M1P / 16; ++k) {
                 uint32_t v[16], pk[8];
@@ -107,6 +122,8 @@ wdsr_block_tc5_seq_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, c
             tc5::tmem_wait_st();
             tc5::fence_before_sync();
             __syncthreads();
+            TC5_ADD(2); }
+            { TC5_T0();
             if (tid == 0) {  // G2: A from TMEM
                 tc5::fence_after_sync();
                 for (int j = 0; j < M1P / 16; ++j)
@@ -117,6 +134,8 @@ wdsr_block_tc5_seq_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, c
             tc5::mbar_wait(bar, phase);
             phase ^= 1;
             tc5::fence_after_sync();
+            TC5_ADD(3); }
+            { TC5_T0();
             {   // E2
                 uint32_t v[32];
                 tc5::tmem_ld16(tmem + lane_base + D2_COL, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
@@ -146,11 +165,13 @@ wdsr_block_tc5_seq_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, c
             }
             tc5::fence_before_sync();
             __syncthreads();
+            TC5_ADD(4); }
         }
         tc5::fence_proxy_async();
         __syncthreads();
 
         for (int m3 = 0; m3 < TH / 4; ++m3) {
+            { TC5_T0();
             if (tid == 0) {  // G3
                 tc5::fence_after_sync();
                 const uint32_t abase = t2_u + m3 * 4 * T2_ROW;
@@ -167,6 +188,8 @@ wdsr_block_tc5_seq_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, c
             tc5::mbar_wait(bar, phase);
             phase ^= 1;
             tc5::fence_after_sync();
+            TC5_ADD(5); }
+            { TC5_T0();
             {   // E3
                 uint32_t v[32];
                 tc5::tmem_ld16(tmem + lane_base + D3_COL, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
@@ -196,6 +219,7 @@ wdsr_block_tc5_seq_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, c
             }
             tc5::fence_before_sync();
             __syncthreads();
+            TC5_ADD(6); }
         }
     }
     __syncthreads();
@@ -206,5 +230,7 @@ inline size_t wdsr_block_tc5_seq_smem(int M1P) {
     using namespace tc5cfg;
     return (size_t)CTRL_BYTES + XS_BYTES + T2_BYTES + BlockTc5Layout(M1P).total + 1024;  // + slack for 1024-B alignment
 }
+
+
 
 }  // namespace b200sr

@@ -1,0 +1,437 @@
+// wdsr_tc5p.cuh -- production form of the tcgen05 fused WDSR-B residual block (see wdsr_tc5.cuh for the algebra and the
+// sequential reference form that validated the descriptor / TMEM protocol).
+//
+//   warp 0      TMA producer   3 x cp.async.bulk.tensor.5d per tile (one per 8-channel plane) into a double-buffered,
+//                              chunk-planar trunk tile; out-of-image halo is zero-filled by the TMA unit
+//   warp 1      MMA issuer A   one elected lane issues the G1 / G2 stream (software-pipelined over M-tiles)
+//   warp 18     MMA issuer B   one elected lane issues the 3x3 (G3) stream; two issuers so that neither stream's barrier
+//                              wait blocks the other -- the tensor pipe interleaves them
+//   warps 2-5   WG-A   E1 (relu -> bf16 A operand) of even M-tiles
+//   warps 6-9   WG-B   E1 of odd M-tiles
+//   warps 10-13 WG-C   E2 (t2 -> shared) of even M-tiles, E3 (bias + residual + store) of 3x3 M-tile 3
+//   warps 14-17 WG-D   E2 of odd M-tiles, E3 of 3x3 M-tiles 0,1,2
+// (a warp can only touch TMEM lanes 32*(warp%4)..+31, so every warpgroup is 4 consecutive warps.)
+//
+// Shared-memory operand layout (SWIZZLE_NONE, K-major): chunk-planar  XS[plane c][pixel p][16 B]  for the trunk tile
+// (planes 0..2 = channels 8c..8c+7, plane 3 = the constant-one channel that carries b1), so one TMA box lands as one
+// contiguous plane and a K=16 MMA pairs two planes through LBO = plane stride, SBO = 128 B.
+// TMEM (512 columns): D1[2] x 144 (relu(t1) is written back in place as the bf16 A operand of G2), D2[2] x 32, D3[4] x 32.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc5.cuh"
+#include "wdsr_tc5_layout.cuh"
+
+#ifdef B200SR_TC5_PROF
+__device__ unsigned long long g_tc5p_prof[64];
+__device__ unsigned long long g_tc5p_cta[1024][3];
+__device__ __forceinline__ unsigned long long gtimer__() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid__() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
+// timers accumulate in registers (prof__[slot & 7]); each warp's lane 0 of CTA 0 flushes them once at kernel end
+#define V3_WAIT(slot, b, par) do { const long long w0__ = clock64(); tc5::mbar_wait(b, par); prof__[(slot) & 7] += (unsigned long long)(clock64() - w0__); } while (0)
+#define V3_T0() const long long v3t0__ = clock64()
+#define V3_ADD(slot) do { prof__[(slot) & 7] += (unsigned long long)(clock64() - v3t0__); } while (0)
+#define V3_DECL() unsigned long long prof__[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define V3_FLUSH(base) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) for (int i__ = 0; i__ < 8; ++i__) g_tc5p_prof[(base) + i__] = prof__[i__]; } while (0)
+#else
+#define V3_WAIT(slot, b, par) tc5::mbar_wait(b, par)
+#define V3_T0() do {} while (0)
+#define V3_ADD(slot) do {} while (0)
+#define V3_DECL() do {} while (0)
+#define V3_FLUSH(base) do {} while (0)
+#endif
+
+namespace b200sr {
+namespace tc5v3 {
+using namespace tc5cfg;
+constexpr int NTHREADS = 608;
+constexpr int TMEM_COLS = 512;
+constexpr int XS_PLANE = NMT * 128 * 16;       // 10,240 B: 640 pixels x 16 B
+constexpr int XS_NBUF = 3;                    // TMA runs two tiles ahead of the MMA stream
+constexpr int XS_BUF = 3 * XS_PLANE;           // 30,720 B of tile data per buffer; the constant-one plane is shared
+constexpr int XS_ONE = XS_NBUF * XS_BUF;       // byte offset of the constant-one plane
+constexpr int XS_BYTES_ALL = XS_ONE + XS_PLANE;
+constexpr int TMA_BYTES = 3 * HP * 16;         // 29,376 B per tile
+__host__ __device__ constexpr int d1_col(int e) { return e * 144; }
+__host__ __device__ constexpr int d2_col(int e) { return 288 + e * 32; }
+__host__ __device__ constexpr int d3_col(int k) { return 352 + k * 32; }
+// The MMA issuer is one thread and an mbarrier wait costs it ~100 clk even when already complete, so everything a group of
+// MMAs needs is folded into ONE barrier:
+//   G2_READY[e] (256) = E1 of this M-tile wrote A2 into D1[e]  +  E2 of the previous M-tile on this buffer drained D2[e]
+//   G3_READY[k] (384) = E2 of M-tiles k and k+1 wrote their t2 rows  +  E3 of the previous tile drained D3[k]
+enum Bar { XS_FULL = 0 /*3*/, XS_EMPTY = 3 /*3*/, D1_FULL = 6, G2_READY = 8, D2_FULL = 10, G3_READY = 12 /*4*/, T2R_FREE = 16 /*4*/,
+           D3_FULL = 20 /*4*/, NBARS = 24 };
+constexpr int CTRL_BYTES = 256;  // 22 mbarriers (176 B) + tmem base pointer at byte 240
+constexpr size_t smem_bytes(int M1P) { return (size_t)tc5v3::CTRL_BYTES + XS_BYTES_ALL + T2_BYTES + (size_t)BlockTc5Layout(M1P).total; }
+}  // namespace tc5v3
+
+__global__ void __launch_bounds__(tc5v3::NTHREADS, 1)
+wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *__restrict__ in, bf16 *__restrict__ out,
+                       const uint8_t *__restrict__ wimg, int M1P, int N, int H, int W, int tiles_x, int tiles_y, int ntiles) {
+    using namespace tc5v3;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const BlockTc5Layout L(M1P);
+    uint8_t *ctrl = smem_raw;
+    uint8_t *xs = smem_raw + tc5v3::CTRL_BYTES;  // XS_NBUF x XS_BUF + constant-one plane
+    uint8_t *t2 = xs + XS_BYTES_ALL;      // T2_BYTES
+    uint8_t *wsm = t2 + T2_BYTES;         // L.total
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bars = smem_u32(ctrl);
+    auto bar = [&](int b) { return bars + 8u * (uint32_t)b; };
+    const uint32_t xs_u = smem_u32(xs), t2_u = smem_u32(t2), w_u = smem_u32(wsm);
+    V3_DECL();
+#ifdef B200SR_TC5_PROF
+    const long long kstart__ = clock64();
+    if (threadIdx.x == 0) { g_tc5p_cta[blockIdx.x][0] = gtimer__(); g_tc5p_cta[blockIdx.x][2] = smid__(); }
+#endif
+
+    // ---- one-time setup
+    if (tid == 0) {
+        for (int b = 0; b < XS_NBUF; ++b) {
+            tc5::mbar_init(bar(XS_FULL + b), 1);
+            tc5::mbar_init(bar(XS_EMPTY + b), 257);  // commit after the last G1 + the 256 threads of WG-C/D after their E3
+        }
+        for (int e = 0; e < 2; ++e) {
+            tc5::mbar_init(bar(D1_FULL + e), 1);
+            tc5::mbar_init(bar(G2_READY + e), 256);
+            tc5::mbar_init(bar(D2_FULL + e), 1);
+        }
+        for (int k = 0; k < 4; ++k) {
+            tc5::mbar_init(bar(G3_READY + k), 384);
+            tc5::mbar_init(bar(T2R_FREE + k), 1);
+            tc5::mbar_init(bar(D3_FULL + k), 1);
+        }
+        tc5::mbar_init_fence();
+        tc5::tma_prefetch_desc(&tmap_in);
+    }
+    __syncwarp();
+    if (warp == 0) tc5::tmem_alloc(smem_u32(ctrl + 240), tc5v3::TMEM_COLS);
+    for (int i = tid; i < L.total / 16; i += NTHREADS) cp_async16(wsm + i * 16, wimg + i * 16, 16);
+    cp_async_commit();
+    for (int i = tid; i < XS_BYTES_ALL / 16; i += NTHREADS) {  // zero (pixel rows 612..639 stay zero); last plane = 1.0 in channels 0,1
+        const bool one = (i * 16) >= XS_ONE;
+        *reinterpret_cast<uint4 *>(xs + i * 16) = make_uint4(one ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+    }
+    for (int i = tid; i < 16; i += NTHREADS) *reinterpret_cast<uint4 *>(t2 + 3 * T2_COPY + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    cp_async_wait<0>();
+    tc5::fence_proxy_async();
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(ctrl + 240);
+#ifdef B200SR_TC5_PROF
+    prof__[6] = (unsigned long long)(clock64() - kstart__);
+#endif
+    const int nmine = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    auto tile_origin = [&](int it, int &x0, int &y0, int &n) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        x0 = (tile % tiles_x) * TW - 1;
+        y0 = ((tile / tiles_x) % tiles_y) * TH - 1;
+        n = tile / (tiles_x * tiles_y);
+    };
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (tc5::elect_one()) {
+            for (int it = 0; it < nmine; ++it) {
+                int x0, y0, n;
+                tile_origin(it, x0, y0, n);
+                const int xb = it % XS_NBUF;
+                tc5::mbar_wait(bar(XS_EMPTY + xb), ((it / XS_NBUF) & 1) ^ 1);
+                tc5::mbar_arrive_expect_tx(bar(XS_FULL + xb), TMA_BYTES);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    tc5::tma_load_5d(xs_u + xb * XS_BUF + c * XS_PLANE, &tmap_in, bar(XS_FULL + xb), 0, c, x0, y0, n);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        const bool leader = tc5::elect_one();
+        const uint32_t idesc1 = tc5::idesc_bf16_f32(128, M1P), idesc32 = tc5::idesc_bf16_f32(128, 32);
+        const uint64_t bw1a = tc5::smem_desc(w_u + L.w1, 128, 512), bw1b = tc5::smem_desc(w_u + L.w1 + 256, 128, 512);
+        const uint64_t bw2 = tc5::smem_desc(w_u + L.w2, 128, L.sbo2);
+        const uint64_t ax0 = tc5::smem_desc(xs_u, XS_PLANE, 128);  // planes paired through LBO
+        const int nk2 = M1P / 16;
+        auto issue_g1 = [&](int xb, int m) {  // leader only
+            const uint32_t off = xb * XS_BUF + m * 2048;
+            const int e = m & 1;
+            tc5::mma_ss(tmem + d1_col(e), ax0 + (uint64_t)(off >> 4), bw1a, idesc1, false);  // planes 0,1
+            // plane 2 paired with the shared constant-one plane: LBO = their distance
+            tc5::mma_ss(tmem + d1_col(e), tc5::smem_desc(xs_u + off + 2 * XS_PLANE, XS_ONE - xb * XS_BUF - 2 * XS_PLANE, 128), bw1b, idesc1,
+                        true);
+            tc5::commit(bar(D1_FULL + e));
+        };
+        uint32_t n_g2[2] = {0, 0};
+        V3_T0();
+        for (int it = 0; it < nmine; ++it) {
+            const int xb = it % XS_NBUF;
+            if (it == 0) {
+                tc5::mbar_wait(bar(XS_FULL + xb), 0);
+                tc5::fence_after_sync();
+                if (leader) {
+                    issue_g1(xb, 0);
+                    issue_g1(xb, 1);
+                }
+                __syncwarp();
+            }
+            for (int m = 0; m < NMT; ++m) {
+                const int e = m & 1;
+                V3_WAIT(0, bar(G2_READY + e), n_g2[e] & 1);
+                ++n_g2[e];
+                const bool next_g1 = (m >= NMT - 2) && (it + 1 < nmine);  // m = 3 -> G1'(1), m = 4 -> G1'(0)
+                if (next_g1 && m == NMT - 2) V3_WAIT(2, bar(XS_FULL + ((it + 1) % XS_NBUF)), ((it + 1) / XS_NBUF) & 1);
+                tc5::fence_after_sync();
+                if (leader) {
+                    const uint32_t d2 = tmem + d2_col(e), a2 = tmem + d1_col(e);
+                    tc5::mma_ts(d2, a2, bw2, idesc32, false);
+#pragma unroll 4
+                    for (int j = 1; j < nk2; ++j) tc5::mma_ts(d2, a2 + 8 * j, bw2 + (uint64_t)(16 * j), idesc32, true);
+                    tc5::commit(bar(D2_FULL + e));
+                    if (m + 2 < NMT) {
+                        issue_g1(xb, m + 2);
+                        if (m + 2 == NMT - 1) tc5::commit(bar(XS_EMPTY + xb));  // all G1 reads of XS[xb] retired
+                    } else if (next_g1) {
+                        issue_g1((it + 1) % XS_NBUF, m == NMT - 2 ? 1 : 0);  // D1[1] is free after G2(3), D1[0] after G2(4)
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        V3_ADD(5);
+        if (nmine > 0) tc5::mbar_wait(bar(D2_FULL + 0), (n_g2[0] - 1) & 1);  // the last G2 (M-tile 4, buffer 0) and all before it retired
+    } else if (warp == 18) {
+        // ============================== MMA issuer B: the 3x3 stream ==============================
+        const bool leader = tc5::elect_one();
+        const uint32_t idesc32 = tc5::idesc_bf16_f32(128, 32);
+        const uint64_t bw3 = tc5::smem_desc(w_u + L.w3, 128, 28 * 128);
+        const uint64_t at0 = tc5::smem_desc(t2_u, 0, T2_GROUP);    // LBO added per instruction
+        auto issue_g3 = [&](int k) {  // leader only
+            const uint64_t abase = at0 + (uint64_t)((k * 4 * T2_ROW) >> 4);
+            const uint32_t d3 = tmem + d3_col(k);
+#pragma unroll
+            for (int i = 0; i < 14; ++i) {
+                const int q0 = 2 * i, q1 = 2 * i + 1;
+                const int a0 = (q0 / 9) * T2_COPY + ((q0 / 3) % 3) * T2_ROW + (q0 % 3) * 128;
+                const int a1 = q1 < 27 ? (q1 / 9) * T2_COPY + ((q1 / 3) % 3) * T2_ROW + (q1 % 3) * 128 : a0 + 128;
+                tc5::mma_ss(d3, abase + (uint64_t)(a0 >> 4) + ((uint64_t)((a1 - a0) >> 4) << 16), bw3 + (uint64_t)(16 * i), idesc32,
+                            i > 0);
+            }
+            tc5::commit(bar(D3_FULL + k));
+            tc5::commit(bar(T2R_FREE + k));
+        };
+        // wait (whole warp) for what G3(k) of tile `t` needs, then issue it
+        auto do_g3 = [&](int t, int k) {
+            V3_WAIT(3, bar(G3_READY + k), t & 1);
+            tc5::fence_after_sync();
+            if (leader) issue_g3(k);
+            __syncwarp();
+        };
+        V3_T0();
+        for (int it = 0; it < nmine; ++it)
+            for (int k = 0; k < 4; ++k) do_g3(it, k);
+        V3_ADD(5);
+        if (nmine > 0) tc5::mbar_wait(bar(T2R_FREE + 3), (nmine - 1) & 1);  // every G3 of this CTA has retired
+    } else {
+        // ============================== epilogue warpgroups ==============================
+        const int wg = (warp - 2) >> 2;          // 0 = A, 1 = B, 2 = C, 3 = D
+        const int e = wg & 1;                    // M-tile parity / buffer index this warpgroup serves
+        const int row = (warp & 3) * 32 + lane;  // row of the M-tile == TMEM lane
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const float *b2s = reinterpret_cast<const float *>(wsm + L.b2);
+        const float *b3s = reinterpret_cast<const float *>(wsm + L.b3);
+        uint32_t n_d1 = 0, n_d2 = 0;
+
+        // ---- E1: relu(D1) -> bf16 A2, in place; TMEM loads of the next 64 columns are in flight while a batch is converted
+        auto e1 = [&]() {
+            V3_WAIT(8 + 16 * e + 0, bar(D1_FULL + e), n_d1 & 1);
+            ++n_d1;
+            V3_T0();
+            tc5::fence_after_sync();
+            const uint32_t d1 = tmem + lane_base + d1_col(e);
+#ifdef B200SR_EXP_NOE1
+            if (false) {
+#else
+            if (M1P == 144) {
+#endif
+                uint32_t va[32], vb[32];
+                auto cvt_store = [&](uint32_t (&v)[32], int col) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = tc5::relu_pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                    tc5::tmem_st16(d1 + col, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                };
+                tc5::tmem_ld32(d1, va);
+                tc5::tmem_wait_ld();
+                tc5::tmem_ld32(d1 + 32, vb);
+                cvt_store(va, 0);
+                tc5::tmem_wait_ld();
+                tc5::tmem_ld32(d1 + 64, va);
+                cvt_store(vb, 16);
+                tc5::tmem_wait_ld();
+                tc5::tmem_ld32(d1 + 96, vb);
+                cvt_store(va, 32);
+                tc5::tmem_wait_ld();
+                tc5::tmem_ld16(d1 + 128, *reinterpret_cast<uint32_t(*)[16]>(&va[0]));
+                cvt_store(vb, 48);
+                tc5::tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) va[j] = tc5::relu_pack_bf16x2(va[2 * j], va[2 * j + 1]);
+                tc5::tmem_st8(d1 + 64, *reinterpret_cast<uint32_t(*)[8]>(&va[0]));
+#ifdef B200SR_EXP_NOE1
+            } else if (false) {
+#else
+            } else {
+#endif
+                for (int k = 0; k < M1P; k += 16) {
+                    uint32_t v[16], pk[8];
+                    tc5::tmem_ld16(d1 + k, v);
+                    tc5::tmem_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pk[j] = tc5::relu_pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                    tc5::tmem_st8(d1 + k / 2, pk);
+                }
+            }
+            tc5::tmem_wait_st();
+            tc5::fence_before_sync();
+            tc5::mbar_arrive(bar(G2_READY + e));
+            V3_ADD(8 + 16 * e + 5);
+        };
+        // ---- E2: D2 + b2 -> bf16 -> three x-shifted copies of t2 (zero outside the image)
+        auto e2 = [&](int it, int m) {
+            int x0, y0, n;
+            tile_origin(it, x0, y0, n);
+            V3_WAIT(8 + 16 * e + 1, bar(D2_FULL + e), n_d2 & 1);
+            ++n_d2;
+            V3_T0();
+            tc5::fence_after_sync();
+            uint32_t v[32];
+            tc5::tmem_ld32(tmem + lane_base + d2_col(e), v);
+            tc5::tmem_wait_ld();
+            tc5::fence_before_sync();
+            tc5::mbar_arrive(bar(G2_READY + e));  // D2[e] drained: counts towards the NEXT G2 on this buffer
+            // the T2 rows this M-tile overwrites were last read by G3(min(m,3)) of the previous tile
+            V3_WAIT(8 + 16 * e + 2, bar(T2R_FREE + (m < 3 ? m : 3)), (it & 1) ^ 1);
+            const int p = m * 128 + row;
+#ifdef B200SR_EXP_NOE2
+            if (false) {
+#else
+            if (p < HP) {
+#endif
+                const int r = p / HW_, hx = p - r * HW_;
+                const int gy = y0 + r, gx = x0 + hx;
+                const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+                uint4 c[3];
+                uint32_t *cw = reinterpret_cast<uint32_t *>(c);
+#pragma unroll
+                for (int j4 = 0; j4 < 6; ++j4) {
+                    const float4 bb = *reinterpret_cast<const float4 *>(b2s + 4 * j4);  // broadcast read
+                    cw[2 * j4] = ok ? pack_bf16x2(__uint_as_float(v[4 * j4]) + bb.x, __uint_as_float(v[4 * j4 + 1]) + bb.y) : 0u;
+                    cw[2 * j4 + 1] = ok ? pack_bf16x2(__uint_as_float(v[4 * j4 + 2]) + bb.z, __uint_as_float(v[4 * j4 + 3]) + bb.w) : 0u;
+                }
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const int xi = hx - d;
+                    if (xi >= 0 && xi < TW) {
+                        uint8_t *dst = t2 + d * T2_COPY + r * T2_ROW + (xi >> 3) * T2_GROUP + (xi & 7) * 16;
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) *reinterpret_cast<uint4 *>(dst + q * 128) = c[q];
+                    }
+                }
+            }
+            tc5::fence_proxy_async();
+            if (m >= 1) tc5::mbar_arrive(bar(G3_READY + m - 1));
+            if (m <= 3) tc5::mbar_arrive(bar(G3_READY + m));
+            V3_ADD(8 + 16 * e + 6);
+        };
+        // ---- E3: D3 + b3 + residual -> bf16 NHWC (3x3 M-tile k of tile iteration t)
+        auto e3 = [&](int t, int k) {
+            int x0, y0, n;
+            tile_origin(t, x0, y0, n);
+            const int xb = t % XS_NBUF;
+            V3_WAIT(8 + 16 * e + 4, bar(XS_FULL + xb), (t / XS_NBUF) & 1);  // direct acquire of the TMA-written tile before generic reads
+            V3_WAIT(8 + 16 * e + 3, bar(D3_FULL + k), t & 1);
+            V3_T0();
+            tc5::fence_after_sync();
+            uint32_t v[32];
+            tc5::tmem_ld16(tmem + lane_base + d3_col(k), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+            tc5::tmem_ld8(tmem + lane_base + d3_col(k) + 16, *reinterpret_cast<uint32_t(*)[8]>(&v[16]));
+            tc5::tmem_wait_ld();
+            tc5::fence_before_sync();
+            tc5::mbar_arrive(bar(G3_READY + k));  // D3[k] drained: counts towards the next tile's G3(k)
+            const int ly = 4 * k + (row >> 5), lx = row & 31;
+            const int gy = y0 + 1 + ly, gx = x0 + 1 + lx;
+            const int p = (ly + 1) * HW_ + lx + 1;
+            const uint8_t *res = xs + xb * XS_BUF + p * 16;
+#ifdef B200SR_EXP_NOE3
+            if (false) {
+#else
+            if (gy < H && gx < W) {
+#endif
+                bf16 *o = out + (((long long)n * H + gy) * W + gx) * 24;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const uint4 rv = *reinterpret_cast<const uint4 *>(res + q * XS_PLANE);
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(&rv);
+                    uint4 ov;
+                    uint32_t *ow = reinterpret_cast<uint32_t *>(&ov);
+#pragma unroll
+                    for (int j2 = 0; j2 < 2; ++j2) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(b3s + q * 8 + 4 * j2);  // broadcast read
+                        const float2 ra = unpack_bf16x2(rw[2 * j2]), rb = unpack_bf16x2(rw[2 * j2 + 1]);
+                        const int ch = q * 8 + 4 * j2;
+                        ow[2 * j2] = pack_bf16x2(__uint_as_float(v[ch]) + bb.x + ra.x, __uint_as_float(v[ch + 1]) + bb.y + ra.y);
+                        ow[2 * j2 + 1] = pack_bf16x2(__uint_as_float(v[ch + 2]) + bb.z + rb.x, __uint_as_float(v[ch + 3]) + bb.w + rb.y);
+                    }
+                    *reinterpret_cast<uint4 *>(o + q * 8) = ov;
+                }
+            }
+            V3_ADD(8 + 16 * e + 7);
+        };
+        // stand-ins for the "previous use drained" arrivals of the very first phases
+        if (wg == 2) { tc5::mbar_arrive(bar(G2_READY + 0)); tc5::mbar_arrive(bar(G3_READY + 3)); }
+        if (wg == 3) { tc5::mbar_arrive(bar(G2_READY + 1)); for (int k = 0; k < 3; ++k) tc5::mbar_arrive(bar(G3_READY + k)); }
+        if (wg == 0) {          // WG-A
+            for (int it = 0; it < nmine; ++it) { e1(); e1(); e1(); }
+        } else if (wg == 1) {   // WG-B
+            for (int it = 0; it < nmine; ++it) { e1(); e1(); }
+        } else if (wg == 2) {   // WG-C: the 3x3 M-tile 3 of a tile is issued behind G2(0) of the NEXT tile (see the MMA schedule)
+            for (int it = 0; it < nmine; ++it) {
+                if (it > 0) {
+                    e3(it - 1, 3);
+                    tc5::mbar_arrive(bar(XS_EMPTY + ((it - 1) % XS_NBUF)));
+                }
+                e2(it, 0);
+                e2(it, 2);
+                e2(it, 4);
+            }
+            if (nmine > 0) {
+                e3(nmine - 1, 3);
+                tc5::mbar_arrive(bar(XS_EMPTY + ((nmine - 1) % XS_NBUF)));
+            }
+        } else {                // WG-D
+            for (int it = 0; it < nmine; ++it) {
+                e2(it, 1);
+                e2(it, 3);
+                e3(it, 0);
+                e3(it, 1);
+                e3(it, 2);
+                tc5::mbar_arrive(bar(XS_EMPTY + (it % XS_NBUF)));
+            }
+        }
+    }
+#ifdef B200SR_TC5_PROF
+    if (threadIdx.x == 0) g_tc5p_cta[blockIdx.x][1] = gtimer__();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { g_tc5p_prof[56] = (unsigned long long)(clock64() - kstart__); }
+    if (blockIdx.x == 0 && threadIdx.x == 32) { g_tc5p_prof[57] = prof__[6]; }
+#endif
+    if (warp == 1) V3_FLUSH(0);
+    if (warp == 18) V3_FLUSH(40);
+    if (warp == 2) V3_FLUSH(8);
+    if (warp == 14) V3_FLUSH(24);
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc5::tmem_free(tmem, tc5v3::TMEM_COLS);
+}
+
+}  // namespace b200sr

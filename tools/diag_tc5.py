@@ -40,4 +40,33 @@ a.record()
 for i in range(16):
     _lib.check(_lib.lib().b200sr_wdsr_block(pl.handle, i, tr.data_ptr(), tb.data_ptr(), 64, 96, 96, _lib.BF16, _lib.current_stream_ptr(tr.device)))
 b.record(); torch.cuda.synchronize()
-print("block us/launch @cfg2", a.elapsed_time(b) / 16 * 1e3)
+print("block us/launch @cfg2 (eager launches)", a.elapsed_time(b) / 16 * 1e3)
+def graph_time(shape):
+    tr = torch.randn(*shape, device="cuda").bfloat16(); tb = torch.empty_like(tr)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(2): pl.block(0, tr, "bf16")
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            src, dst = tr, tb
+            for i in range(16):
+                _lib.check(_lib.lib().b200sr_wdsr_block(pl.handle, i, src.data_ptr(), dst.data_ptr(), shape[0], shape[1], shape[2], _lib.BF16, _lib.current_stream_ptr(tr.device)))
+                src, dst = dst, src
+        for _ in range(3): g.replay()
+        st.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(10): g.replay()
+        e1.record(st); st.synchronize()
+    return e0.elapsed_time(e1) / 160 * 1e3
+for nm, shape in [("cfg2", (64, 96, 96, 24)), ("360p", (1, 360, 640, 24)), ("1080p", (1, 1080, 1920, 24))]:
+    print("block us/launch (CUDA graph) @", nm, graph_time(shape))
+for nm, shape in [("360p", (1, 360, 640, 24)), ("1080p", (1, 1080, 1920, 24))]:
+    tr = torch.randn(*shape, device="cuda").bfloat16(); tb = torch.empty_like(tr)
+    for _ in range(2): pl.block(0, tr, "bf16")
+    torch.cuda.synchronize(); a.record()
+    for i in range(16):
+        _lib.check(_lib.lib().b200sr_wdsr_block(pl.handle, i, tr.data_ptr(), tb.data_ptr(), shape[0], shape[1], shape[2], _lib.BF16, _lib.current_stream_ptr(tr.device)))
+    b.record(); torch.cuda.synchronize()
+    print("block us/launch @", nm, a.elapsed_time(b) / 16 * 1e3)
