@@ -132,6 +132,47 @@ B200SR_API int b200sr_flow_warp_nchw(const float *x_dev, const float *flow_dev, 
 B200SR_API int b200sr_flow_warp_nhwc(const void *x_dev, const float *flow_nchw_dev, void *y_dev, int n, int c, int h, int w,
                           int padding_mode, int dtype, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Video path building blocks (SPyNet + BasicVSR).  The Python mirror (mobilesuperresolution_b200/video.py)
+ * sequences these exactly as the reference's forward does:
+ *   SpyNet.process / forward          models/spynet_arch.py:49-96
+ *   BasicVSR_origin.forward           models/basicvsr_arch_origin.py:53-96
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200sr_conv b200sr_conv_t;
+
+/* nn.Conv2d(cin, cout, k, stride 1, padding k/2) with k in {1,3,7}; w_host is PyTorch OIHW float32, bias may be NULL.
+ * (models/spynet_arch.py:17-22, models/basicvsr_arch_origin.py:31-35,110-131) */
+B200SR_API int b200sr_conv_create(int cin, int cout, int k, const float *w_host, const float *bias_host, b200sr_conv_t **out);
+B200SR_API void b200sr_conv_destroy(b200sr_conv_t *conv);
+/* y = act(conv(x)) (+ residual).  x / y / residual are NHWC tensors of n x h x w pixels whose used channels start at
+ * *_coff inside a pixel of *_cstride channels (so concatenations are views).  shuffle = 2 folds PixelShuffle(2) into the
+ * store (y is then n x 2h x 2w x cout/4).  act: B200SR_ACT_*.  precision F32: in/out float32; BF16: in bf16|f32, out bf16|f32. */
+B200SR_API int b200sr_conv_forward(const b200sr_conv_t *conv, const void *x_dev, int x_cstride, int x_coff, void *y_dev, int y_cstride,
+                                   int y_coff, const void *residual_dev, int r_cstride, int r_coff, int n, int h, int w, int act,
+                                   int shuffle, int in_dtype, int out_dtype, int precision, void *stream);
+
+/* F.interpolate(x, size=(oh,ow), mode='bilinear', align_corners) on NCHW, then (v - sub[c%4]) * mul[c%4]; y float32.
+ * (models/spynet_arch.py:88-94 pre/post resize, normalisation :45-47; models/basicvsr_arch_origin.py:93) */
+B200SR_API int b200sr_resize_bilinear_nchw(const void *x_dev, int x_dtype, float *y_dev, int n, int c, int h, int w, int oh, int ow,
+                                           int align_corners, const float *sub4_host, const float *mul4_host, void *stream);
+/* F.avg_pool2d(x, 2, 2, count_include_pad=False), NCHW float32   (models/spynet_arch.py:56-57) */
+B200SR_API int b200sr_avg_pool2_nchw(const float *x_dev, float *y_dev, int n, int c, int h, int w, void *stream);
+/* One SPyNet level's network input, fused (models/spynet_arch.py:64-78): up = 2*interpolate(flow_prev, x2, align_corners=True)
+ * (replicate-padded to h x w), warped = flow_warp(supp, up, 'border'); out NHWC [ref|warped|up|0..] with cs channels;
+ * up_dev (n,2,h,w) float32.  flow_prev_dev NULL = the coarsest level's zero flow; (ph,pw) = its size. */
+B200SR_API int b200sr_spynet_level_input(const float *ref_dev, const float *supp_dev, const float *flow_prev_dev, void *out_dev,
+                                         int out_dtype, float *up_dev, int n, int h, int w, int ph, int pw, int cs, void *stream);
+/* y[n,c,h,w] = a[n,h,w,c] + b[n,c,h,w]  (a NHWC float32 with cs channels, b may be NULL)   (models/spynet_arch.py:72-78) */
+B200SR_API int b200sr_nhwc_plus_nchw(const float *a_dev, const float *b_dev, float *y_dev, int n, int c, int h, int w, int cs, void *stream);
+/* copy a 3-channel NCHW image (image n at x + n*x_nstride elements) into channels [co,co+3) of an NHWC tensor
+ * (torch.cat([x_i, feat_prop], 1), models/basicvsr_arch_origin.py:69,81) */
+B200SR_API int b200sr_nchw3_to_nhwc(const void *x_dev, int x_dtype, int64_t x_nstride, void *y_dev, int y_dtype, int n, int h, int w,
+                                    int cs, int co, void *stream);
+/* out[n,c,4h,4w] = a[n,4h,4w,c] + F.interpolate(img, scale_factor=4, 'bilinear', align_corners=False)
+ * (models/basicvsr_arch_origin.py:90-92); a NHWC with cs channels, out float32 with image stride y_nstride elements */
+B200SR_API int b200sr_vsr_base_add(const void *a_dev, int a_dtype, int cs, const void *img_dev, int img_dtype, int64_t img_nstride,
+                                   float *y_dev, int64_t y_nstride, int n, int h, int w, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

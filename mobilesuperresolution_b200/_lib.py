@@ -48,6 +48,18 @@ SYMBOLS = {
     "b200sr_flow_warp_nchw": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
                                       c_int, c_int, c_void_p]),
     "b200sr_flow_warp_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sr_conv_create": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, POINTER(c_void_p)]),
+    "b200sr_conv_destroy": (None, [c_void_p]),
+    "b200sr_conv_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sr_resize_bilinear_nchw": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                            c_void_p]),
+    "b200sr_avg_pool2_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sr_spynet_level_input": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          c_void_p]),
+    "b200sr_nhwc_plus_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sr_nchw3_to_nhwc": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sr_vsr_base_add": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -13,6 +13,7 @@
 
 #include "../../include/b200sr.h"
 #include "common.cuh"
+#include "conv.cuh"
 #include "launch.h"
 #include "wdsr_bf16.cuh"
 #include "wdsr_f32.cuh"
@@ -423,6 +424,115 @@ int b200sr_flow_warp_nhwc(const void *x, const float *flow, void *y, int n, int 
         return fail(B200SR_E_UNSUPPORTED, "flow_warp_nhwc: padding_mode %d", padding_mode);
     cudaError_t e = launch_flow_warp_nhwc(x, flow, y, n, c, h, w, padding_mode == B200SR_PAD_BORDER, dtype, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "flow_warp_nhwc (c must be a multiple of 8 (bf16) / 4 (f32), c*esize/16 in {1,2,3,4,6,8,16})");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// video path
+// ---------------------------------------------------------------------------------------------------------
+struct b200sr_conv {
+    int cin = 0, cout = 0, k = 0, cinp_f32 = 0, coutp_f32 = 0, cinp_bf16 = 0, coutp_bf16 = 0, nt = 0;
+    float *d_w_f32 = nullptr, *d_bias = nullptr;
+    uint16_t *d_w_bf16 = nullptr;
+};
+
+int b200sr_conv_create(int cin, int cout, int k, const float *w, const float *bias, b200sr_conv_t **out) {
+    if (!w || !out) return fail(B200SR_E_INVAL, "conv_create: null argument");
+    if (cin < 1 || cout < 1 || (k != 1 && k != 3 && k != 7)) return fail(B200SR_E_UNSUPPORTED, "conv_create: cin=%d cout=%d k=%d (k in {1,3,7})", cin, cout, k);
+    if (b200sr_device_count() <= 0) return fail(B200SR_E_STATE, "conv_create: no CUDA device (this library has no CPU fallback)");
+    b200sr_conv *c = new (std::nothrow) b200sr_conv();
+    if (!c) return fail(B200SR_E_INVAL, "conv_create: out of memory");
+    c->cin = cin, c->cout = cout, c->k = k;
+    c->cinp_f32 = round_up(cin, 8), c->coutp_f32 = round_up(cout, 32);
+    c->nt = cout <= 8 ? 1 : cout <= 16 ? 2 : cout <= 32 ? 4 : 8;
+    c->cinp_bf16 = round_up(cin, 16), c->coutp_bf16 = round_up(cout, 8 * c->nt);
+    const int kk = k * k, bp = c->coutp_f32 > c->coutp_bf16 ? c->coutp_f32 : c->coutp_bf16;
+    std::vector<float> wf((size_t)kk * c->cinp_f32 * c->coutp_f32, 0.f), bb((size_t)bp, 0.f);
+    std::vector<uint16_t> wb((size_t)kk * c->coutp_bf16 * c->cinp_bf16, 0);
+    for (int o = 0; o < cout; ++o) {
+        for (int i = 0; i < cin; ++i)
+            for (int t = 0; t < kk; ++t) {
+                const float v = w[((size_t)o * cin + i) * kk + t];
+                wf[((size_t)t * c->cinp_f32 + i) * c->coutp_f32 + o] = v;
+                wb[((size_t)t * c->coutp_bf16 + o) * c->cinp_bf16 + i] = f2bf(v);
+            }
+        if (bias) bb[o] = bias[o];
+    }
+    int rc;
+    if ((rc = upload(wf.data(), wf.size() * 4, (void **)&c->d_w_f32)) || (rc = upload(wb.data(), wb.size() * 2, (void **)&c->d_w_bf16)) ||
+        (rc = upload(bb.data(), bb.size() * 4, (void **)&c->d_bias))) {
+        b200sr_conv_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+void b200sr_conv_destroy(b200sr_conv_t *c) {
+    if (!c) return;
+    if (c->d_w_f32) cudaFree(c->d_w_f32);
+    if (c->d_w_bf16) cudaFree(c->d_w_bf16);
+    if (c->d_bias) cudaFree(c->d_bias);
+    delete c;
+}
+
+int b200sr_conv_forward(const b200sr_conv_t *c, const void *x, int x_cs, int x_co, void *y, int y_cs, int y_co, const void *res, int r_cs,
+                        int r_co, int n, int h, int w, int act, int shuffle, int in_dtype, int out_dtype, int precision, void *stream) {
+    if (!c || !x || !y) return fail(B200SR_E_INVAL, "conv_forward: null argument");
+    if (n <= 0 || h <= 0 || w <= 0) return fail(B200SR_E_INVAL, "conv_forward: bad shape");
+    if (shuffle != 1 && shuffle != 2) return fail(B200SR_E_UNSUPPORTED, "conv_forward: shuffle %d (1 or 2)", shuffle);
+    if (shuffle == 2 && (c->cout % 4)) return fail(B200SR_E_INVAL, "conv_forward: PixelShuffle(2) needs cout %% 4 == 0");
+    if (act < 0 || act > 2) return fail(B200SR_E_INVAL, "conv_forward: bad activation %d", act);
+    if (x_co + c->cin > x_cs || y_co + (shuffle == 2 ? c->cout / 4 : c->cout) > y_cs) return fail(B200SR_E_INVAL, "conv_forward: channel window outside tensor");
+    ConvArgs a;
+    a.x = x, a.y = y, a.residual = res, a.bias = c->d_bias;
+    a.n = n, a.h = h, a.w_ = w, a.cin = c->cin, a.cout = c->cout, a.x_cs = x_cs, a.x_co = x_co, a.y_cs = y_cs, a.y_co = y_co, a.r_cs = r_cs,
+    a.r_co = r_co, a.act = act, a.shuffle = shuffle;
+    if (precision == B200SR_F32) {
+        a.w = c->d_w_f32, a.cinp = c->cinp_f32, a.coutp = c->coutp_f32;
+    } else {
+        a.w = c->d_w_bf16, a.cinp = c->cinp_bf16, a.coutp = c->coutp_bf16;
+    }
+    cudaError_t e = launch_conv(a, c->k, c->nt, in_dtype, out_dtype, precision, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_forward (fp32 precision needs float32 tensors; bf16 precision: bf16|f32 in, bf16|f32 out)");
+    return 0;
+}
+
+int b200sr_resize_bilinear_nchw(const void *x, int x_dtype, float *y, int n, int c, int h, int w, int oh, int ow, int align,
+                                const float *sub4, const float *mul4, void *stream) {
+    if (!x || !y) return fail(B200SR_E_INVAL, "resize_bilinear: null tensor");
+    if (h <= 0 || w <= 0 || oh <= 0 || ow <= 0) return fail(B200SR_E_INVAL, "resize_bilinear: bad shape");
+    const float z[4] = {0, 0, 0, 0}, o[4] = {1, 1, 1, 1};
+    CU(launch_resize_bilinear_nchw(x, x_dtype, y, n, c, h, w, oh, ow, align, sub4 ? sub4 : z, mul4 ? mul4 : o, (cudaStream_t)stream));
+    return 0;
+}
+int b200sr_avg_pool2_nchw(const float *x, float *y, int n, int c, int h, int w, void *stream) {
+    if (!x || !y) return fail(B200SR_E_INVAL, "avg_pool2: null tensor");
+    CU(launch_avg_pool2(x, y, n, c, h, w, (cudaStream_t)stream));
+    return 0;
+}
+int b200sr_spynet_level_input(const float *ref, const float *supp, const float *flow_prev, void *out, int out_dtype, float *up, int n,
+                              int h, int w, int ph, int pw, int cs, void *stream) {
+    if (!ref || !supp || !out || !up) return fail(B200SR_E_INVAL, "spynet_level_input: null tensor");
+    if (cs < 8 || ph < 1 || pw < 1 || h < 2 * ph || h > 2 * ph + 1 || w < 2 * pw || w > 2 * pw + 1)
+        return fail(B200SR_E_INVAL, "spynet_level_input: level %dx%d does not follow previous flow %dx%d", h, w, ph, pw);
+    CU(launch_spynet_level_input(ref, supp, flow_prev, out, out_dtype, up, n, h, w, ph, pw, cs, (cudaStream_t)stream));
+    return 0;
+}
+int b200sr_nhwc_plus_nchw(const float *a, const float *b, float *y, int n, int c, int h, int w, int cs, void *stream) {
+    if (!a || !y) return fail(B200SR_E_INVAL, "nhwc_plus_nchw: null tensor");
+    CU(launch_nhwc_plus_nchw(a, b, y, n, c, h, w, cs, (cudaStream_t)stream));
+    return 0;
+}
+int b200sr_nchw3_to_nhwc(const void *x, int x_dtype, int64_t x_nstride, void *y, int y_dtype, int n, int h, int w, int cs, int co, void *stream) {
+    if (!x || !y || co + 3 > cs) return fail(B200SR_E_INVAL, "nchw3_to_nhwc: bad argument");
+    CU(launch_nchw3_to_nhwc(x, x_dtype, x_nstride, y, y_dtype, n, h, w, cs, co, (cudaStream_t)stream));
+    return 0;
+}
+int b200sr_vsr_base_add(const void *a, int a_dtype, int cs, const void *img, int img_dtype, int64_t img_nstride, float *y, int64_t y_nstride,
+                        int n, int h, int w, void *stream) {
+    if (!a || !img || !y || cs < 3) return fail(B200SR_E_INVAL, "vsr_base_add: bad argument");
+    CU(launch_vsr_base_add(a, a_dtype, cs, img, img_dtype, img_nstride, y, y_nstride, n, h, w, (cudaStream_t)stream));
     return 0;
 }
 

@@ -32,4 +32,19 @@ cudaError_t launch_flow_warp_nchw(const float *x, const float *flow, long long f
 cudaError_t launch_flow_warp_nhwc(const void *x, const float *flow_nchw, void *y, int n, int c, int h, int w, int border,
                                   int dtype, cudaStream_t st);
 
+struct ConvArgs;
+// generic NHWC convolution (conv.cuh); nt = output-channel n-tiles per CTA of the bf16 kernel (1,2,4,8)
+cudaError_t launch_conv(const ConvArgs &a, int k, int nt, int in_dtype, int out_dtype, int precision, cudaStream_t st);
+// video glue (video_glue.cu)
+cudaError_t launch_resize_bilinear_nchw(const void *x, int x_dtype, float *y, int n, int c, int h, int w, int oh, int ow, int align,
+                                        const float *sub4, const float *mul4, cudaStream_t st);
+cudaError_t launch_avg_pool2(const float *x, float *y, int n, int c, int h, int w, cudaStream_t st);
+cudaError_t launch_spynet_level_input(const float *ref, const float *supp, const float *flow_prev, void *out, int out_dtype, float *up,
+                                      int n, int h, int w, int ph, int pw, int cs, cudaStream_t st);
+cudaError_t launch_nhwc_plus_nchw(const float *a, const float *b, float *y, int n, int c, int h, int w, int cs, cudaStream_t st);
+cudaError_t launch_nchw3_to_nhwc(const void *x, int x_dtype, long long x_nstride, void *y, int y_dtype, int n, int h, int w, int cs, int co,
+                                 cudaStream_t st);
+cudaError_t launch_vsr_base_add(const void *a, int a_dtype, int cs, const void *img, int img_dtype, long long img_nstride, float *y,
+                                long long y_nstride, int n, int h, int w, cudaStream_t st);
+
 }  // namespace b200sr

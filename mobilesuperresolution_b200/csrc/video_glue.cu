@@ -1,0 +1,231 @@
+// video_glue.cu -- the memory-bound kernels around the convolutions of the video path (SPyNet pyramid, BasicVSR glue).
+// Every resampling formula is the closed form of the ATen op the reference calls; coordinates and
+// flows are always fp32.
+#include "common.cuh"
+#include "launch.h"
+
+namespace b200sr {
+
+__device__ __forceinline__ void src_index(float scale, int d, int in_size, bool align, int &i0, int &i1, float &l) {
+    const float s = align ? scale * (float)d : fmaxf(scale * ((float)d + 0.5f) - 0.5f, 0.f);
+    i0 = min((int)s, in_size - 1);
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l = s - (float)i0;
+}
+__host__ __device__ inline float resize_scale(int in, int out, bool align) {
+    if (align) return out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    return (float)in / (float)out;
+}
+
+// F.interpolate(mode='bilinear') on NCHW, then y = (y - sub[c]) * mul[c]  (c indexes a 4-entry table, c % 4).
+//   SPyNet pre-resize + ImageNet normalisation   models/spynet_arch.py:88-89,45-47   (align_corners=False)
+//   SPyNet final flow resize + rescale           models/spynet_arch.py:91-94
+//   BasicVSR final resize                        models/basicvsr_arch_origin.py:93
+template <typename TIN>
+__global__ void __launch_bounds__(256) resize_bilinear_nchw_kernel(const TIN *__restrict__ x, float *__restrict__ y, int NC, int C, int H,
+                                                                   int W, int OH, int OW, int align, float4 sub, float4 mul) {
+    const float sh = resize_scale(H, OH, align), sw = resize_scale(W, OW, align);
+    const long long total = (long long)NC * OH * OW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % OW), oy = (int)((i / OW) % OH), nc = (int)(i / ((long long)OW * OH));
+        int y0, y1, x0, x1;
+        float ly, lx;
+        src_index(sh, oy, H, align, y0, y1, ly);
+        src_index(sw, ox, W, align, x0, x1, lx);
+        const TIN *p = x + (long long)nc * H * W;
+        const float v = (1.f - ly) * ((1.f - lx) * to_f32<TIN>(p[(long long)y0 * W + x0]) + lx * to_f32<TIN>(p[(long long)y0 * W + x1])) +
+                        ly * ((1.f - lx) * to_f32<TIN>(p[(long long)y1 * W + x0]) + lx * to_f32<TIN>(p[(long long)y1 * W + x1]));
+        const int c = (nc % C) & 3;
+        const float s = c == 0 ? sub.x : c == 1 ? sub.y : c == 2 ? sub.z : sub.w;
+        const float m = c == 0 ? mul.x : c == 1 ? mul.y : c == 2 ? mul.z : mul.w;
+        y[i] = (v - s) * m;
+    }
+}
+
+cudaError_t launch_resize_bilinear_nchw(const void *x, int x_dtype, float *y, int n, int c, int h, int w, int oh, int ow, int align,
+                                        const float *sub4, const float *mul4, cudaStream_t st) {
+    const long long total = (long long)n * c * oh * ow;
+    if (total == 0) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    const float4 s = make_float4(sub4[0], sub4[1], sub4[2], sub4[3]), m = make_float4(mul4[0], mul4[1], mul4[2], mul4[3]);
+    if (x_dtype == kF32)
+        resize_bilinear_nchw_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float *)x, y, n * c, c, h, w, oh, ow, align, s, m);
+    else
+        resize_bilinear_nchw_kernel<bf16><<<(unsigned)blocks, 256, 0, st>>>((const bf16 *)x, y, n * c, c, h, w, oh, ow, align, s, m);
+    return cudaGetLastError();
+}
+
+// F.avg_pool2d(2, 2, count_include_pad=False) on NCHW fp32       models/spynet_arch.py:56-57
+__global__ void __launch_bounds__(256) avg_pool2_kernel(const float *__restrict__ x, float *__restrict__ y, int NC, int H, int W) {
+    const int OH = H / 2, OW = W / 2;
+    const long long total = (long long)NC * OH * OW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % OW), oy = (int)((i / OW) % OH), nc = (int)(i / ((long long)OW * OH));
+        const float *p = x + ((long long)nc * H + 2 * oy) * W + 2 * ox;
+        y[i] = (p[0] + p[1] + p[W] + p[W + 1]) * 0.25f;
+    }
+}
+cudaError_t launch_avg_pool2(const float *x, float *y, int n, int c, int h, int w, cudaStream_t st) {
+    const long long total = (long long)n * c * (h / 2) * (w / 2);
+    if (total == 0) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    avg_pool2_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, n * c, h, w);
+    return cudaGetLastError();
+}
+
+// One SPyNet pyramid level's network input, fused (models/spynet_arch.py:64-78):
+//   up   = interpolate(flow_prev, x2, bilinear, align_corners=True) * 2   (+ replicate pad by one row/col if the level is odd)
+//   warp = flow_warp(supp, up, padding 'border')
+//   out  = NHWC [ref(3) | warp(3) | up(2) | zero pad to CS channels],  up also kept NCHW fp32 for the residual
+// flow_prev == nullptr means the zero flow of the coarsest level.
+template <typename TOUT>
+__global__ void __launch_bounds__(256) spynet_level_input_kernel(const float *__restrict__ ref, const float *__restrict__ supp,
+                                                                 const float *__restrict__ flow_prev, TOUT *__restrict__ out,
+                                                                 float *__restrict__ up, int N, int H, int W, int PH, int PW, int CS) {
+    const long long P = (long long)N * H * W;
+    const float sh = resize_scale(PH, 2 * PH, true), sw = resize_scale(PW, 2 * PW, true);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        const int xw = (int)(i % W), yh = (int)((i / W) % H), n = (int)(i / ((long long)W * H));
+        float fu = 0.f, fv = 0.f;
+        if (flow_prev) {
+            const int uy = min(yh, 2 * PH - 1), ux = min(xw, 2 * PW - 1);  // replicate pad of the x2 upsampled flow
+            int y0, y1, x0, x1;
+            float ly, lx;
+            src_index(sh, uy, PH, true, y0, y1, ly);
+            src_index(sw, ux, PW, true, x0, x1, lx);
+            const float *p = flow_prev + (long long)n * 2 * PH * PW;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float *q = p + (long long)c * PH * PW;
+                const float v = (1.f - ly) * ((1.f - lx) * q[y0 * PW + x0] + lx * q[y0 * PW + x1]) +
+                                ly * ((1.f - lx) * q[y1 * PW + x0] + lx * q[y1 * PW + x1]);
+                (c == 0 ? fu : fv) = v * 2.0f;
+            }
+        }
+        // flow_warp(supp, up, border): same fp32 normalise / un-normalise round trip as the reference
+        const float dw = (float)max(W - 1, 1), dh = (float)max(H - 1, 1);
+        float ix = ((2.0f * ((float)xw + fu) / dw - 1.0f + 1.f) / 2.f) * (float)(W - 1);
+        float iy = ((2.0f * ((float)yh + fv) / dh - 1.0f + 1.f) / 2.f) * (float)(H - 1);
+        ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
+        iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        const int x0 = (int)fx0, y0 = (int)fy0;
+        const float ex = (fx0 + 1.f) - ix, wx = ix - fx0, ey = (fy0 + 1.f) - iy, wy = iy - fy0;
+        const bool vx1 = x0 + 1 < W, vy1 = y0 + 1 < H;
+        TOUT *o = out + i * CS;
+        const long long plane = (long long)H * W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            o[c] = from_f32<TOUT>(ref[((long long)n * 3 + c) * plane + (long long)yh * W + xw]);
+            const float *s = supp + ((long long)n * 3 + c) * plane;
+            float v = s[(long long)y0 * W + x0] * (ex * ey);
+            if (vx1) v += s[(long long)y0 * W + x0 + 1] * (wx * ey);
+            if (vy1) v += s[(long long)(y0 + 1) * W + x0] * (ex * wy);
+            if (vx1 && vy1) v += s[(long long)(y0 + 1) * W + x0 + 1] * (wx * wy);
+            o[3 + c] = from_f32<TOUT>(v);
+        }
+        o[6] = from_f32<TOUT>(fu);
+        o[7] = from_f32<TOUT>(fv);
+        for (int c = 8; c < CS; ++c) o[c] = from_f32<TOUT>(0.f);
+        up[((long long)n * 2) * plane + (long long)yh * W + xw] = fu;
+        up[((long long)n * 2 + 1) * plane + (long long)yh * W + xw] = fv;
+    }
+}
+cudaError_t launch_spynet_level_input(const float *ref, const float *supp, const float *flow_prev, void *out, int out_dtype, float *up,
+                                      int n, int h, int w, int ph, int pw, int cs, cudaStream_t st) {
+    const long long P = (long long)n * h * w;
+    if (P == 0) return cudaSuccess;
+    long long blocks = (P + 255) / 256;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    if (out_dtype == kF32)
+        spynet_level_input_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(ref, supp, flow_prev, (float *)out, up, n, h, w, ph, pw, cs);
+    else
+        spynet_level_input_kernel<bf16><<<(unsigned)blocks, 256, 0, st>>>(ref, supp, flow_prev, (bf16 *)out, up, n, h, w, ph, pw, cs);
+    return cudaGetLastError();
+}
+
+// y_nchw[n,c,h,w] = a_nhwc[n,h,w,c] (first C of CS channels) + b_nchw[n,c,h,w]      (flow = BasicModule(...) + up, :72-78)
+__global__ void __launch_bounds__(256) nhwc_plus_nchw_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                                             float *__restrict__ y, int N, int C, int H, int W, int CS) {
+    const long long total = (long long)N * C * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int xw = (int)(i % W), yh = (int)((i / W) % H), c = (int)((i / ((long long)W * H)) % C), n = (int)(i / ((long long)W * H * C));
+        y[i] = a[(((long long)n * H + yh) * W + xw) * CS + c] + (b ? b[i] : 0.f);
+    }
+}
+cudaError_t launch_nhwc_plus_nchw(const float *a, const float *b, float *y, int n, int c, int h, int w, int cs, cudaStream_t st) {
+    const long long total = (long long)n * c * h * w;
+    if (total == 0) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    nhwc_plus_nchw_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, b, y, n, c, h, w, cs);
+    return cudaGetLastError();
+}
+
+// NCHW image (3 channels) -> channels [co, co+3) of an NHWC tensor with CS channels     (torch.cat([x_i, feat_prop]), :69,81)
+template <typename TIN, typename TOUT>
+__global__ void __launch_bounds__(256) nchw3_to_nhwc_kernel(const TIN *__restrict__ x, long long x_nstride, TOUT *__restrict__ y, int N,
+                                                            int H, int W, int CS, int co) {
+    const long long P = (long long)N * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        const long long hw = i % ((long long)H * W);
+        const int n = (int)(i / ((long long)H * W));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) y[i * CS + co + c] = from_f32<TOUT>(to_f32<TIN>(x[n * x_nstride + (long long)c * H * W + hw]));
+    }
+}
+cudaError_t launch_nchw3_to_nhwc(const void *x, int x_dtype, long long x_nstride, void *y, int y_dtype, int n, int h, int w, int cs, int co,
+                                 cudaStream_t st) {
+    const long long P = (long long)n * h * w;
+    if (P == 0) return cudaSuccess;
+    long long blocks = (P + 255) / 256;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    if (x_dtype == kF32 && y_dtype == kF32)
+        nchw3_to_nhwc_kernel<float, float><<<(unsigned)blocks, 256, 0, st>>>((const float *)x, x_nstride, (float *)y, n, h, w, cs, co);
+    else if (x_dtype == kF32 && y_dtype == kBF16)
+        nchw3_to_nhwc_kernel<float, bf16><<<(unsigned)blocks, 256, 0, st>>>((const float *)x, x_nstride, (bf16 *)y, n, h, w, cs, co);
+    else if (x_dtype == kBF16 && y_dtype == kBF16)
+        nchw3_to_nhwc_kernel<bf16, bf16><<<(unsigned)blocks, 256, 0, st>>>((const bf16 *)x, x_nstride, (bf16 *)y, n, h, w, cs, co);
+    else
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+// out_nchw[n,c,Y,X] = a_nhwc[n,Y,X,c] + bilinear_x4(img)[n,c,Y,X]   (conv_last + F.interpolate(x_i, scale 4, align False), :90-92)
+template <typename TA, typename TIMG>
+__global__ void __launch_bounds__(256) vsr_base_add_kernel(const TA *__restrict__ a, int CS, const TIMG *__restrict__ img, long long img_nstride,
+                                                           float *__restrict__ y, long long y_nstride, int N, int h, int w) {
+    const int OH = 4 * h, OW = 4 * w;
+    const long long total = (long long)N * 3 * OH * OW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % OW), oy = (int)((i / OW) % OH), c = (int)((i / ((long long)OW * OH)) % 3), n = (int)(i / ((long long)OW * OH * 3));
+        int y0, y1, x0, x1;
+        float ly, lx;
+        src_index(0.25f, oy, h, false, y0, y1, ly);
+        src_index(0.25f, ox, w, false, x0, x1, lx);
+        const TIMG *p = img + n * img_nstride + (long long)c * h * w;
+        const float base = (1.f - ly) * ((1.f - lx) * to_f32<TIMG>(p[y0 * w + x0]) + lx * to_f32<TIMG>(p[y0 * w + x1])) +
+                           ly * ((1.f - lx) * to_f32<TIMG>(p[y1 * w + x0]) + lx * to_f32<TIMG>(p[y1 * w + x1]));
+        y[n * y_nstride + ((long long)c * OH + oy) * OW + ox] = to_f32<TA>(a[(((long long)n * OH + oy) * OW + ox) * CS + c]) + base;
+    }
+}
+cudaError_t launch_vsr_base_add(const void *a, int a_dtype, int cs, const void *img, int img_dtype, long long img_nstride, float *y,
+                                long long y_nstride, int n, int h, int w, cudaStream_t st) {
+    const long long total = (long long)n * 3 * 16 * h * w;
+    if (total == 0) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    if (a_dtype == kF32 && img_dtype == kF32)
+        vsr_base_add_kernel<float, float><<<(unsigned)blocks, 256, 0, st>>>((const float *)a, cs, (const float *)img, img_nstride, y, y_nstride, n, h, w);
+    else if (a_dtype == kBF16 && img_dtype == kF32)
+        vsr_base_add_kernel<bf16, float><<<(unsigned)blocks, 256, 0, st>>>((const bf16 *)a, cs, (const float *)img, img_nstride, y, y_nstride, n, h, w);
+    else if (a_dtype == kBF16 && img_dtype == kBF16)
+        vsr_base_add_kernel<bf16, bf16><<<(unsigned)blocks, 256, 0, st>>>((const bf16 *)a, cs, (const bf16 *)img, img_nstride, y, y_nstride, n, h, w);
+    else
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+}  // namespace b200sr

@@ -18,11 +18,8 @@ int sm_count() {
 
 template <typename TIN, typename TOUT, int CP>
 static cudaError_t head_t(const void *x, void *trunk, const float *wpack, int N, int H, int W, float mean, cudaStream_t st) {
-    const long long P = (long long)N * H * W;
-    long long blocks = (P + 255) / 256;
-    const long long cap = (long long)sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    wdsr_head_kernel<TIN, TOUT, CP><<<(unsigned)blocks, 256, 0, st>>>((const TIN *)x, (TOUT *)trunk, wpack, N, H, W, mean);
+    const int tx = ceil_div(W, 64), ty = ceil_div(H, 4);
+    wdsr_head_kernel<TIN, TOUT, CP><<<tx * ty * N, 256, 0, st>>>((const TIN *)x, (TOUT *)trunk, wpack, N, H, W, mean, tx, ty);
     return cudaGetLastError();
 }
 

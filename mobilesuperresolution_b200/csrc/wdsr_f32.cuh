@@ -19,57 +19,71 @@ namespace b200sr {
 // ------------------------------------------------------------------------------------------------------------------
 template <typename TIN, typename TOUT, int CP>
 __global__ void __launch_bounds__(256) wdsr_head_kernel(const TIN *__restrict__ x, TOUT *__restrict__ trunk,
-                                                        const float *__restrict__ wpack, int N, int H, int W, float mean) {
+                                                        const float *__restrict__ wpack, int N, int H, int W, float mean,
+                                                        int tiles_x, int tiles_y) {
+    // one CTA = 64 x 4 pixels; the (x - mean) halo tile is staged once (coalesced NCHW reads), the NHWC result is staged
+    // in shared memory and written back as contiguous 16-byte vectors (one tile row = 64 * CP * sizeof(TOUT) contiguous bytes)
+    constexpr int TW = 64, TH = 4, HW_ = TW + 2, HH_ = TH + 2, HS = HW_ + 1;
     __shared__ __align__(16) float ws[27 * CP + CP];
-    for (int i = threadIdx.x; i < 27 * CP + CP; i += blockDim.x) ws[i] = wpack[i];
+    __shared__ float xin[3][HH_][HS];
+    __shared__ __align__(16) TOUT ostage[TW * TH * CP];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 27 * CP + CP; i += 256) ws[i] = wpack[i];
+    const int tile = blockIdx.x;
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, n = tile / (tiles_x * tiles_y);
+    const int x0 = tx * TW, y0 = ty * TH;
+    for (int i = tid; i < 3 * HH_ * HW_; i += 256) {
+        const int c = i / (HH_ * HW_), r = (i / HW_) % HH_, q = i % HW_;
+        const int gy = y0 - 1 + r, gx = x0 - 1 + q;
+        float v = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = to_f32<TIN>(x[(((long long)n * 3 + c) * H + gy) * W + gx]) - mean;
+        xin[c][r][q] = v;
+    }
     __syncthreads();
-    const long long P = (long long)N * H * W;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
-        const int xw = (int)(p % W);
-        const int yh = (int)((p / W) % H);
-        const int n = (int)(p / ((long long)W * H));
-        float acc[CP];
+    const int lx = tid % TW, ly = tid / TW;
+    float acc[CP];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) acc[c] = ws[27 * CP + c];
+    for (int c = 0; c < CP; ++c) acc[c] = ws[27 * CP + c];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const TIN *xp = x + ((long long)n * 3 + c) * H * W;
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int yy = yh + ky - 1;
+        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int xx = xw + kx - 1;
-                    float v = 0.f;
-                    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = to_f32<TIN>(xp[(long long)yy * W + xx]) - mean;
-                    const float4 *wr = reinterpret_cast<const float4 *>(&ws[(c * 9 + ky * 3 + kx) * CP]);
+            for (int kx = 0; kx < 3; ++kx) {
+                const float v = xin[c][ly + ky][lx + kx];
+                const float4 *wr = reinterpret_cast<const float4 *>(&ws[(c * 9 + ky * 3 + kx) * CP]);
 #pragma unroll
-                    for (int q = 0; q < CP / 4; ++q) {
-                        float4 wv = wr[q];
-                        acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
-                        acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
-                        acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
-                    }
+                for (int q = 0; q < CP / 4; ++q) {
+                    const float4 wv = wr[q];
+                    acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
                 }
             }
-        }
-        TOUT *o = trunk + p * CP;
-        if constexpr (sizeof(TOUT) == 4) {
+    TOUT *o = ostage + tid * CP;
+    if constexpr (sizeof(TOUT) == 4) {
 #pragma unroll
-            for (int q = 0; q < CP / 4; ++q)
-                reinterpret_cast<float4 *>(o)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-        } else {
+        for (int q = 0; q < CP / 4; ++q)
+            reinterpret_cast<float4 *>(o)[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    } else {
 #pragma unroll
-            for (int q = 0; q < CP / 8; ++q) {
-                uint4 v;
-                v.x = pack_bf16x2(acc[8 * q + 0], acc[8 * q + 1]);
-                v.y = pack_bf16x2(acc[8 * q + 2], acc[8 * q + 3]);
-                v.z = pack_bf16x2(acc[8 * q + 4], acc[8 * q + 5]);
-                v.w = pack_bf16x2(acc[8 * q + 6], acc[8 * q + 7]);
-                reinterpret_cast<uint4 *>(o)[q] = v;
-            }
+        for (int q = 0; q < CP / 8; ++q) {
+            uint4 v;
+            v.x = pack_bf16x2(acc[8 * q + 0], acc[8 * q + 1]);
+            v.y = pack_bf16x2(acc[8 * q + 2], acc[8 * q + 3]);
+            v.z = pack_bf16x2(acc[8 * q + 4], acc[8 * q + 5]);
+            v.w = pack_bf16x2(acc[8 * q + 6], acc[8 * q + 7]);
+            reinterpret_cast<uint4 *>(o)[q] = v;
         }
+    }
+    __syncthreads();
+    constexpr int VPP = CP * (int)sizeof(TOUT) / 16;  // 16-byte vectors per pixel
+    for (int i = tid; i < TW * TH * VPP; i += 256) {
+        const int p = i / VPP, q = i % VPP, px = p % TW, py = p / TW;
+        const int gx = x0 + px, gy = y0 + py;
+        if (gx < W && gy < H)
+            reinterpret_cast<uint4 *>(trunk + (((long long)n * H + gy) * W + gx) * CP)[q] = reinterpret_cast<const uint4 *>(ostage + p * CP)[q];
     }
 }
 

@@ -1,0 +1,163 @@
+"""GPU parity: generic conv, SPyNet and BasicVSR (video path) against golden vectors / the oracle."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from conftest import golden_case, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def V():
+    from mobilesuperresolution_b200 import video
+    assert torch.cuda.is_available()
+    return video
+
+
+def _t(sd):
+    return {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("cin,cout,k", [(8, 32, 7), (32, 64, 7), (16, 2, 7), (67, 64, 3), (64, 64, 3), (128, 64, 1), (64, 256, 3), (64, 3, 3), (5, 9, 3)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv_vs_torch(V, cin, cout, k, precision):
+    g = torch.Generator().manual_seed(cin * 100 + cout + k)
+    conv = nn.Conv2d(cin, cout, k, 1, k // 2)
+    x = torch.randn(2, cin, 19, 37, generator=g)
+    res = torch.randn(2, cout, 19, 37, generator=g)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    xq = x.to(dt).float()
+    resq = res.to(dt).float()
+    h = V._ConvHandle(conv, torch.device("cuda:0"))
+    xn = xq.permute(0, 2, 3, 1).contiguous().to(dt).cuda()
+    with torch.no_grad():
+        ref = F.leaky_relu(F.conv2d(xq, conv.weight, conv.bias, padding=k // 2), 0.1) + resq
+    y = h(xn, precision, V.ACT_LRELU, residual=resq.permute(0, 2, 3, 1).contiguous().to(dt).cuda()).float().cpu().permute(0, 3, 1, 2)
+    err = float((y - ref).abs().max())
+    assert err <= (2e-5 if precision == "fp32" else 0.05), err
+    if cout % 4 == 0:   # PixelShuffle(2) folded into the store
+        with torch.no_grad():
+            ref2 = F.pixel_shuffle(F.relu(F.conv2d(xq, conv.weight, conv.bias, padding=k // 2)), 2)
+        y2 = h(xn, precision, V.ACT_RELU, shuffle=2).float().cpu().permute(0, 3, 1, 2)
+        assert float((y2 - ref2).abs().max()) <= (2e-5 if precision == "fp32" else 0.05)
+
+
+def test_conv_channel_windows(V):
+    """x and y may be channel windows of wider NHWC tensors (concatenation without copies)."""
+    conv = nn.Conv2d(6, 10, 3, 1, 1)
+    x = torch.randn(1, 16, 9, 11)
+    h = V._ConvHandle(conv, torch.device("cuda:0"))
+    xn = x.permute(0, 2, 3, 1).contiguous().cuda()
+    out = torch.full((1, 9, 11, 24), 7.0, device="cuda")
+    h(xn, "fp32", V.ACT_NONE, x_coff=5, out=out, y_coff=3)
+    with torch.no_grad():
+        ref = F.conv2d(x[:, 5:11], conv.weight, conv.bias, padding=1)
+    o = out.cpu()
+    assert float((o[..., 3:13].permute(0, 3, 1, 2) - ref).abs().max()) <= 2e-5
+    assert float((o[..., :3] - 7).abs().max()) == 0 and float((o[..., 13:] - 7).abs().max()) == 0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_spynet_golden(V, precision):
+    from oracle import synth
+    meta, arrs = load_golden("spynet_small")
+    sp = V.SpyNet().eval()
+    sp.load_state_dict(_t(synth.synth_state_dict(meta["shapes"], meta["wseed"])))
+    a, b = synth.synth_input(meta["shape"], meta["aseed"]), synth.synth_input(meta["shape"], meta["bseed"])
+    sp = sp.cuda().set_precision(precision)
+    f = sp(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).cpu().numpy()
+    err = np.abs(f - arrs["flow"]).max()
+    if precision == "fp32":
+        assert err <= 1e-4, err
+    else:
+        assert err <= 0.1, err          # flows of up to 3.9 px; bf16 conv operands, fp32 flow arithmetic
+
+
+def test_spynet_kat3_180x320(V, kat):
+    """reference-seeded SpyNet on 2 x 180x320 pairs (the cfg4 frame size), fp32."""
+    meta, arrs = load_golden("kat3_spynet_seed0")
+    torch.manual_seed(0)
+    sp = V.SpyNet().eval()
+    assert abs(float(sum(v.double().sum() for v in sp.state_dict().values())) - kat["KAT3"]["weights_sum"]) < 1e-6
+    g = torch.Generator().manual_seed(7)
+    a = torch.rand(2, 3, 180, 320, generator=g)
+    b = torch.rand(2, 3, 180, 320, generator=g)
+    f = sp.cuda()(a.cuda(), b.cuda()).cpu()
+    s = meta["stride"]
+    assert float((f[:, :, ::s, ::s] - torch.from_numpy(arrs["f_strided"])).abs().max()) <= 1e-4
+    assert abs(float(f.double().sum()) - kat["KAT3"]["sum"]) < 1.0
+    assert abs(float(f[0, 0, 90, 160]) - kat["KAT3"]["f[0,0,90,160]"]) < 1e-4
+
+
+def test_spynet_mmedit_key_remap(V):
+    sd = {"basic_module.3.basic_module.2.conv.weight": 1, "basic_module.0.basic_module.4.conv.bias": 2, "mean": 3}
+    out = V.SpyNet.remap_mmedit_state_dict(sd)
+    assert set(out) == {"basic_module.3.basic_module.4.weight", "basic_module.0.basic_module.8.bias", "mean"}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_basicvsr_origin_golden(V, precision):
+    from oracle import port
+    meta, arrs, sd, x = golden_case("basicvsr_origin_small")
+    m = V.BasicVSR_origin(meta["num_feat"], meta["num_block"]).eval()
+    m.load_state_dict(_t(sd))
+    m = m.cuda().set_precision(precision)
+    h, w = meta["out_hw"]
+    y = m(torch.from_numpy(x).cuda(), h, w).cpu()
+    s = meta["stride"]
+    ref_s, ref_c = torch.from_numpy(arrs["y_strided"]), torch.from_numpy(arrs["y_corner"])
+    if precision == "fp32":
+        assert float((y[..., ::s, ::s] - ref_s).abs().max()) <= 1e-4
+        assert float((y[..., :16, :16] - ref_c).abs().max()) <= 1e-4
+    else:
+        assert port.psnr_db(y[..., ::s, ::s], ref_s) >= 50.0
+
+
+def test_basicvsr_origin_resized_output(V):
+    """height/weight different from 4h x 4w goes through the final bilinear resize (basicvsr_arch_origin.py:93)."""
+    from oracle import port
+    meta, arrs, sd, x = golden_case("basicvsr_origin_small")
+    m = V.BasicVSR_origin(meta["num_feat"], meta["num_block"]).eval()
+    m.load_state_dict(_t(sd))
+    xt = torch.from_numpy(x)[:, :2]
+    ref = port.basicvsr_origin_forward(_t(sd), xt, 100, 200)
+    y = m.cuda()(xt.cuda(), 100, 200).cpu()
+    assert float((y - ref).abs().max()) <= 1e-4
+
+
+def test_fork_basicvsr_flow_propagation_and_faithful_error(V):
+    from oracle import port, synth
+    m = V.BasicVSR(num_feat=8, num_block=1).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = _t(synth.synth_state_dict(shapes, 61))
+    m.load_state_dict(sd)
+    x = torch.from_numpy(synth.synth_input((1, 3, 3, 36, 68), 62))
+    m = m.cuda()
+    ff, fb = m.get_flow(x.cuda())
+    rff, rfb = port.vsr_get_flow(sd, x)
+    assert float((ff.cpu() - rff).abs().max()) <= 1e-4 and float((fb.cpu() - rfb).abs().max()) <= 1e-4
+    back, fwd = m.propagate(x.cuda(), ff, fb)
+    rback, rfwd = port.vsr_propagate(sd, x, rff, rfb, 8)
+    for a, r in zip(back + fwd, rback + rfwd):
+        assert float((a.float().cpu().permute(0, 3, 1, 2) - r).abs().max()) <= 1e-4
+    with pytest.raises(RuntimeError, match="must match the size of tensor b"):
+        m(x.cuda(), 144, 272)
+
+
+def test_cfg4_basicvsr_clip_properties(V):
+    """cfg4 size: 15-frame 180x320 clip through BasicVSR_origin(64, 30) in bf16.  Size-independent properties:
+    output shape; clips in a batch are independent (b=2 equals two b=1 runs); fp32 and bf16 paths agree to >= 50 dB."""
+    from oracle import port
+    torch.manual_seed(0)
+    m = V.BasicVSR_origin(64, 30).eval().cuda()
+    x = torch.rand(2, 15, 3, 180, 320, generator=torch.Generator().manual_seed(1234))[:, :5]   # 5 frames keep the fp32 arm short
+    xb = x.cuda()
+    y2 = m.set_precision("bf16")(xb, 720, 1280)
+    assert tuple(y2.shape) == (2, 5, 3, 720, 1280)
+    y1 = m(xb[1:2], 720, 1280)
+    assert torch.equal(y1, y2[1:2])
+    yf = m.set_precision("fp32")(xb[:1], 720, 1280)
+    assert port.psnr_db(y2[:1].cpu(), yf.cpu()) >= 50.0
