@@ -6,10 +6,11 @@
 //   warp 1      MMA issuer A   one elected lane issues the G1 / G2 stream (software-pipelined over M-tiles)
 //   warp 18     MMA issuer B   one elected lane issues the 3x3 (G3) stream; two issuers so that neither stream's barrier
 //                              wait blocks the other -- the tensor pipe interleaves them
-//   warps 2-5   WG-A   E1 (relu -> bf16 A operand) of even M-tiles
-//   warps 6-9   WG-B   E1 of odd M-tiles
-//   warps 10-13 WG-C   E2 (t2 -> shared) of even M-tiles, E3 (bias + residual + store) of 3x3 M-tile 3
-//   warps 14-17 WG-D   E2 of odd M-tiles, E3 of 3x3 M-tiles 0,1,2
+//   warps 2-5   WG-A   E1 (relu -> bf16 A operand) of even M-tiles  +  E3 (bias + residual + store) of 3x3 M-tiles 1,3
+//   warps 6-9   WG-B   E1 of odd M-tiles                            +  E3 of 3x3 M-tiles 0,2
+//               (each warp polls both of its queues and serves E1 first: E1 sits on the G1 -> G2 critical loop)
+//   warps 10-13 WG-C   E2 (t2 -> three shifted copies in shared memory) of even M-tiles
+//   warps 14-17 WG-D   E2 of odd M-tiles
 // (a warp can only touch TMEM lanes 32*(warp%4)..+31, so every warpgroup is 4 consecutive warps.)
 //
 // Shared-memory operand layout (SWIZZLE_NONE, K-major): chunk-planar  XS[plane c][pixel p][16 B]  for the trunk tile
@@ -26,19 +27,23 @@
 #ifdef B200SR_TC5_PROF
 __device__ unsigned long long g_tc5p_prof[64];
 __device__ unsigned long long g_tc5p_cta[1024][3];
+__device__ unsigned long long g_tc5p_evt[20][2048];   // per warp: (id << 48) | clock
+__device__ int g_tc5p_evtn[20];
 __device__ __forceinline__ unsigned long long gtimer__() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned smid__() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 // timers accumulate in registers (prof__[slot & 7]); each warp's lane 0 of CTA 0 flushes them once at kernel end
 #define V3_WAIT(slot, b, par) do { const long long w0__ = clock64(); tc5::mbar_wait(b, par); prof__[(slot) & 7] += (unsigned long long)(clock64() - w0__); } while (0)
 #define V3_T0() const long long v3t0__ = clock64()
 #define V3_ADD(slot) do { prof__[(slot) & 7] += (unsigned long long)(clock64() - v3t0__); } while (0)
-#define V3_DECL() unsigned long long prof__[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define V3_FLUSH(base) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) for (int i__ = 0; i__ < 8; ++i__) g_tc5p_prof[(base) + i__] = prof__[i__]; } while (0)
+#define V3_DECL() unsigned long long prof__[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int evn__ = 0
+#define V3_EVT(id) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && evn__ < 2048) { g_tc5p_evt[threadIdx.x >> 5][evn__++] = ((unsigned long long)(id) << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull); } } while (0)
+#define V3_FLUSH(base) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { for (int i__ = 0; i__ < 8; ++i__) g_tc5p_prof[(base) + i__] = prof__[i__]; } } while (0)
 #else
 #define V3_WAIT(slot, b, par) tc5::mbar_wait(b, par)
 #define V3_T0() do {} while (0)
 #define V3_ADD(slot) do {} while (0)
 #define V3_DECL() do {} while (0)
+#define V3_EVT(id) do {} while (0)
 #define V3_FLUSH(base) do {} while (0)
 #endif
 
@@ -90,7 +95,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
     if (tid == 0) {
         for (int b = 0; b < XS_NBUF; ++b) {
             tc5::mbar_init(bar(XS_FULL + b), 1);
-            tc5::mbar_init(bar(XS_EMPTY + b), 257);  // commit after the last G1 + the 256 threads of WG-C/D after their E3
+            tc5::mbar_init(bar(XS_EMPTY + b), 257);  // commit after the last G1 + the 256 threads of WG-A/B after their E3
         }
         for (int e = 0; e < 2; ++e) {
             tc5::mbar_init(bar(D1_FULL + e), 1);
@@ -183,6 +188,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                 const bool next_g1 = (m >= NMT - 2) && (it + 1 < nmine);  // m = 3 -> G1'(1), m = 4 -> G1'(0)
                 if (next_g1 && m == NMT - 2) V3_WAIT(2, bar(XS_FULL + ((it + 1) % XS_NBUF)), ((it + 1) / XS_NBUF) & 1);
                 tc5::fence_after_sync();
+                V3_EVT(100 + m);
                 if (leader) {
                     const uint32_t d2 = tmem + d2_col(e), a2 = tmem + d1_col(e);
                     tc5::mma_ts(d2, a2, bw2, idesc32, false);
@@ -197,6 +203,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                     }
                 }
                 __syncwarp();
+                V3_EVT(110 + m);
             }
         }
         V3_ADD(5);
@@ -219,14 +226,16 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                             i > 0);
             }
             tc5::commit(bar(D3_FULL + k));
-            tc5::commit(bar(T2R_FREE + k));
+            if (k == 3) tc5::commit(bar(T2R_FREE + 3));  // (in-order) every 3x3 MMA of this tile has retired
         };
         // wait (whole warp) for what G3(k) of tile `t` needs, then issue it
         auto do_g3 = [&](int t, int k) {
             V3_WAIT(3, bar(G3_READY + k), t & 1);
             tc5::fence_after_sync();
+            V3_EVT(200 + k);
             if (leader) issue_g3(k);
             __syncwarp();
+            V3_EVT(210 + k);
         };
         V3_T0();
         for (int it = 0; it < nmine; ++it)
@@ -241,20 +250,14 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const float *b2s = reinterpret_cast<const float *>(wsm + L.b2);
         const float *b3s = reinterpret_cast<const float *>(wsm + L.b3);
-        uint32_t n_d1 = 0, n_d2 = 0;
 
-        // ---- E1: relu(D1) -> bf16 A2, in place; TMEM loads of the next 64 columns are in flight while a batch is converted
+        // ---- E1: relu(D1) -> bf16 A2, in place; the next 32 columns are in flight while a batch is converted
         auto e1 = [&]() {
-            V3_WAIT(8 + 16 * e + 0, bar(D1_FULL + e), n_d1 & 1);
-            ++n_d1;
-            V3_T0();
             tc5::fence_after_sync();
+            V3_T0();
+            V3_EVT(300);
             const uint32_t d1 = tmem + lane_base + d1_col(e);
-#ifdef B200SR_EXP_NOE1
-            if (false) {
-#else
             if (M1P == 144) {
-#endif
                 uint32_t va[32], vb[32];
                 auto cvt_store = [&](uint32_t (&v)[32], int col) {
 #pragma unroll
@@ -278,11 +281,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
 #pragma unroll
                 for (int j = 0; j < 8; ++j) va[j] = tc5::relu_pack_bf16x2(va[2 * j], va[2 * j + 1]);
                 tc5::tmem_st8(d1 + 64, *reinterpret_cast<uint32_t(*)[8]>(&va[0]));
-#ifdef B200SR_EXP_NOE1
-            } else if (false) {
-#else
             } else {
-#endif
                 for (int k = 0; k < M1P; k += 16) {
                     uint32_t v[16], pk[8];
                     tc5::tmem_ld16(d1 + k, v);
@@ -294,33 +293,71 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             }
             tc5::tmem_wait_st();
             tc5::fence_before_sync();
-            tc5::mbar_arrive(bar(G2_READY + e));
-            V3_ADD(8 + 16 * e + 5);
+            tc5::mbar_arrive_relaxed(bar(G2_READY + e));  // A2 is complete (wait::st); no release: E3's output stores may be in flight
+            V3_ADD(5);
+            V3_EVT(301);
+        };
+        // ---- E3: D3 + b3 + residual -> bf16 NHWC (3x3 M-tile k of tile iteration t)
+        auto e3 = [&](int t, int k, int x0, int y0, int n) {
+            const int xb = t % XS_NBUF;
+            tc5::fence_after_sync();
+            V3_T0();
+            V3_EVT(500 + k);
+            uint32_t v[32];
+            tc5::tmem_ld32(tmem + lane_base + d3_col(k), v);
+            const int ly = 4 * k + (row >> 5), lx = row & 31;
+            const int gy = y0 + 1 + ly, gx = x0 + 1 + lx;
+            const uint8_t *res = xs + xb * XS_BUF + ((ly + 1) * HW_ + lx + 1) * 16;
+            uint4 rv[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) rv[q] = *reinterpret_cast<const uint4 *>(res + q * XS_PLANE);
+            V3_EVT(520 + k);
+            tc5::tmem_wait_ld();
+            V3_EVT(530 + k);
+            tc5::fence_before_sync();
+            tc5::mbar_arrive_relaxed(bar(G3_READY + k));
+            V3_EVT(540 + k);  // D3[k] drained (wait::ld): counts towards the next tile's G3(k)
+            if (gy < H && gx < W) {
+                bf16 *o = out + (((long long)n * H + gy) * W + gx) * 24;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(&rv[q]);
+                    uint4 ov;
+                    uint32_t *ow = reinterpret_cast<uint32_t *>(&ov);
+#pragma unroll
+                    for (int j2 = 0; j2 < 2; ++j2) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(b3s + q * 8 + 4 * j2);  // broadcast read
+                        const float2 ra = unpack_bf16x2(rw[2 * j2]), rb = unpack_bf16x2(rw[2 * j2 + 1]);
+                        const int ch = q * 8 + 4 * j2;
+                        ow[2 * j2] = pack_bf16x2(__uint_as_float(v[ch]) + bb.x + ra.x, __uint_as_float(v[ch + 1]) + bb.y + ra.y);
+                        ow[2 * j2 + 1] = pack_bf16x2(__uint_as_float(v[ch + 2]) + bb.z + rb.x, __uint_as_float(v[ch + 3]) + bb.w + rb.y);
+                    }
+                    *reinterpret_cast<uint4 *>(o + q * 8) = ov;
+                }
+            }
+            V3_ADD(7);
+            V3_EVT(510 + k);
         };
         // ---- E2: D2 + b2 -> bf16 -> three x-shifted copies of t2 (zero outside the image)
-        auto e2 = [&](int it, int m) {
-            int x0, y0, n;
-            tile_origin(it, x0, y0, n);
-            V3_WAIT(8 + 16 * e + 1, bar(D2_FULL + e), n_d2 & 1);
-            ++n_d2;
-            V3_T0();
+        auto e2 = [&](int m, uint32_t par, int x0, int y0) {
+            V3_WAIT(1, bar(D2_FULL + e), par);
             tc5::fence_after_sync();
+            V3_T0();
+            V3_EVT(400 + m);
             uint32_t v[32];
             tc5::tmem_ld32(tmem + lane_base + d2_col(e), v);
+            const int p = m * 128 + row;
+            const int r = p / HW_, hx = p - r * HW_;
+            const int gy = y0 + r, gx = x0 + hx;
+            const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
             tc5::tmem_wait_ld();
             tc5::fence_before_sync();
             tc5::mbar_arrive(bar(G2_READY + e));  // D2[e] drained: counts towards the NEXT G2 on this buffer
-            // the T2 rows this M-tile overwrites were last read by G3(min(m,3)) of the previous tile
-            V3_WAIT(8 + 16 * e + 2, bar(T2R_FREE + (m < 3 ? m : 3)), (it & 1) ^ 1);
-            const int p = m * 128 + row;
 #ifdef B200SR_EXP_NOE2
             if (false) {
 #else
             if (p < HP) {
 #endif
-                const int r = p / HW_, hx = p - r * HW_;
-                const int gy = y0 + r, gx = x0 + hx;
-                const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
                 uint4 c[3];
                 uint32_t *cw = reinterpret_cast<uint32_t *>(c);
 #pragma unroll
@@ -342,81 +379,57 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             tc5::fence_proxy_async();
             if (m >= 1) tc5::mbar_arrive(bar(G3_READY + m - 1));
             if (m <= 3) tc5::mbar_arrive(bar(G3_READY + m));
-            V3_ADD(8 + 16 * e + 6);
+            V3_ADD(6);
+            V3_EVT(410 + m);
         };
-        // ---- E3: D3 + b3 + residual -> bf16 NHWC (3x3 M-tile k of tile iteration t)
-        auto e3 = [&](int t, int k) {
-            int x0, y0, n;
-            tile_origin(t, x0, y0, n);
-            const int xb = t % XS_NBUF;
-            V3_WAIT(8 + 16 * e + 4, bar(XS_FULL + xb), (t / XS_NBUF) & 1);  // direct acquire of the TMA-written tile before generic reads
-            V3_WAIT(8 + 16 * e + 3, bar(D3_FULL + k), t & 1);
-            V3_T0();
-            tc5::fence_after_sync();
-            uint32_t v[32];
-            tc5::tmem_ld16(tmem + lane_base + d3_col(k), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-            tc5::tmem_ld8(tmem + lane_base + d3_col(k) + 16, *reinterpret_cast<uint32_t(*)[8]>(&v[16]));
-            tc5::tmem_wait_ld();
-            tc5::fence_before_sync();
-            tc5::mbar_arrive(bar(G3_READY + k));  // D3[k] drained: counts towards the next tile's G3(k)
-            const int ly = 4 * k + (row >> 5), lx = row & 31;
-            const int gy = y0 + 1 + ly, gx = x0 + 1 + lx;
-            const int p = (ly + 1) * HW_ + lx + 1;
-            const uint8_t *res = xs + xb * XS_BUF + p * 16;
-#ifdef B200SR_EXP_NOE3
-            if (false) {
-#else
-            if (gy < H && gx < W) {
-#endif
-                bf16 *o = out + (((long long)n * H + gy) * W + gx) * 24;
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    const uint4 rv = *reinterpret_cast<const uint4 *>(res + q * XS_PLANE);
-                    const uint32_t *rw = reinterpret_cast<const uint32_t *>(&rv);
-                    uint4 ov;
-                    uint32_t *ow = reinterpret_cast<uint32_t *>(&ov);
-#pragma unroll
-                    for (int j2 = 0; j2 < 2; ++j2) {
-                        const float4 bb = *reinterpret_cast<const float4 *>(b3s + q * 8 + 4 * j2);  // broadcast read
-                        const float2 ra = unpack_bf16x2(rw[2 * j2]), rb = unpack_bf16x2(rw[2 * j2 + 1]);
-                        const int ch = q * 8 + 4 * j2;
-                        ow[2 * j2] = pack_bf16x2(__uint_as_float(v[ch]) + bb.x + ra.x, __uint_as_float(v[ch + 1]) + bb.y + ra.y);
-                        ow[2 * j2 + 1] = pack_bf16x2(__uint_as_float(v[ch + 2]) + bb.z + rb.x, __uint_as_float(v[ch + 3]) + bb.w + rb.y);
+
+        if (wg < 2) {
+            // WG-A / WG-B: E1 of M-tiles m = e, e+2, .. and E3 of 3x3 M-tiles k = 1-e, 3-e.  Per warp, two in-order queues;
+            // E1 is served first whenever its accumulator is ready.  Warps of a warpgroup need not agree on the order.
+            tc5::mbar_arrive(bar(G3_READY + 1 - e));  // stand-ins for "previous tile's E3 drained D3[k]"
+            tc5::mbar_arrive(bar(G3_READY + 3 - e));
+            const int ne1 = (e == 0 ? 3 : 2) * nmine, ne3 = 2 * nmine;
+            int i1 = 0, i3 = 0, ox = 0, oy = 0, on = 0;
+            if (nmine > 0) tile_origin(0, ox, oy, on);
+            while (i1 < ne1 || i3 < ne3) {
+                bool did = false;
+                if (i1 < ne1) {
+                    const bool rdy = __any_sync(0xffffffffu, tc5::mbar_test(bar(D1_FULL + e), i1 & 1));
+                    if (rdy) {
+                        tc5::mbar_wait(bar(D1_FULL + e), i1 & 1);  // already complete: per-lane acquire
+                        e1();
+                        ++i1;
+                        did = true;
                     }
-                    *reinterpret_cast<uint4 *>(o + q * 8) = ov;
                 }
-            }
-            V3_ADD(8 + 16 * e + 7);
-        };
-        // stand-ins for the "previous use drained" arrivals of the very first phases
-        if (wg == 2) { tc5::mbar_arrive(bar(G2_READY + 0)); tc5::mbar_arrive(bar(G3_READY + 3)); }
-        if (wg == 3) { tc5::mbar_arrive(bar(G2_READY + 1)); for (int k = 0; k < 3; ++k) tc5::mbar_arrive(bar(G3_READY + k)); }
-        if (wg == 0) {          // WG-A
-            for (int it = 0; it < nmine; ++it) { e1(); e1(); e1(); }
-        } else if (wg == 1) {   // WG-B
-            for (int it = 0; it < nmine; ++it) { e1(); e1(); }
-        } else if (wg == 2) {   // WG-C: the 3x3 M-tile 3 of a tile is issued behind G2(0) of the NEXT tile (see the MMA schedule)
-            for (int it = 0; it < nmine; ++it) {
-                if (it > 0) {
-                    e3(it - 1, 3);
-                    tc5::mbar_arrive(bar(XS_EMPTY + ((it - 1) % XS_NBUF)));
+                if (!did && i3 < ne3) {
+                    const int t = i3 >> 1, k = (1 - e) + 2 * (i3 & 1);
+                    const bool rdy = __any_sync(0xffffffffu, tc5::mbar_test(bar(D3_FULL + k), t & 1));
+                    if (rdy) {
+                        tc5::mbar_wait(bar(D3_FULL + k), t & 1);
+                        if ((i3 & 1) == 0) tc5::mbar_wait(bar(XS_FULL + (t % XS_NBUF)), (t / XS_NBUF) & 1);  // acquire the TMA-written tile
+                        e3(t, k, ox, oy, on);
+                        if ((i3 & 1) && t + 1 < nmine) tile_origin(t + 1, ox, oy, on);
+                        if (i3 & 1) tc5::mbar_arrive_relaxed(bar(XS_EMPTY + (t % XS_NBUF)));  // both E3 done: residual values were consumed
+                        ++i3;
+                        did = true;
+                    }
                 }
-                e2(it, 0);
-                e2(it, 2);
-                e2(it, 4);
+                if (!did) __nanosleep(40);  // do not steal issue slots from the MMA issuers / other epilogue warps while polling
             }
-            if (nmine > 0) {
-                e3(nmine - 1, 3);
-                tc5::mbar_arrive(bar(XS_EMPTY + ((nmine - 1) % XS_NBUF)));
-            }
-        } else {                // WG-D
+        } else {
+            // WG-C / WG-D: E2 of M-tiles m = e, e+2, ..
+            tc5::mbar_arrive(bar(G2_READY + e));  // stand-in for "previous E2 drained D2[e]"
+            uint32_t n_d2 = 0;
             for (int it = 0; it < nmine; ++it) {
-                e2(it, 1);
-                e2(it, 3);
-                e3(it, 0);
-                e3(it, 1);
-                e3(it, 2);
-                tc5::mbar_arrive(bar(XS_EMPTY + (it % XS_NBUF)));
+                // every 3x3 MMA of the previous tile has retired (commits are in order) before T2 is overwritten
+                int x0, y0, n;
+                tile_origin(it, x0, y0, n);
+                V3_WAIT(2, bar(T2R_FREE + 3), (it & 1) ^ 1);
+                for (int m = e; m < NMT; m += 2) {
+                    e2(m, n_d2 & 1, x0, y0);
+                    ++n_d2;
+                }
             }
         }
     }
@@ -425,10 +438,13 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
     if (blockIdx.x == 0 && threadIdx.x == 0) { g_tc5p_prof[56] = (unsigned long long)(clock64() - kstart__); }
     if (blockIdx.x == 0 && threadIdx.x == 32) { g_tc5p_prof[57] = prof__[6]; }
 #endif
+#ifdef B200SR_TC5_PROF
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_tc5p_evtn[threadIdx.x >> 5] = evn__;
+#endif
     if (warp == 1) V3_FLUSH(0);
     if (warp == 18) V3_FLUSH(40);
     if (warp == 2) V3_FLUSH(8);
-    if (warp == 14) V3_FLUSH(24);
+    if (warp == 10) V3_FLUSH(24);
     tc5::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc5::tmem_free(tmem, tc5v3::TMEM_COLS);

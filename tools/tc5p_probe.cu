@@ -1,6 +1,7 @@
 // tc5p_probe.cu -- barrier-wait / stage timers of the production tcgen05 block kernel (developer tool).
 #include <cstdio>
 #include <vector>
+#include <algorithm>
 #include "wdsr_tc5p.cuh"
 #include "tma_map.h"
 using namespace b200sr;
@@ -39,6 +40,20 @@ int main() {
             printf("   warp%d per tile: waits D1_FULL %llu D2_FULL %llu T2R_FREE %llu D3_FULL %llu XS_FULL %llu | work E1 %llu E2 %llu E3 %llu\n", w,
                    q[0] / t, q[1] / t, q[2] / t, q[3] / t, q[4] / t, q[5] / t, q[6] / t, q[7] / t);
         }
+    }
+    {   // timeline of CTA 0 (last rep): events of warps 1 (MMA-A), 18 (MMA-B), 2 (WG-A), 6 (WG-B), 10 (WG-C), 14 (WG-D)
+        static unsigned long long ev[20][2048]; int evn[20];
+        cudaMemcpyFromSymbol(ev, g_tc5p_evt, sizeof ev); cudaMemcpyFromSymbol(evn, g_tc5p_evtn, sizeof evn);
+        struct E { unsigned long long t; int w, id; };
+        std::vector<E> all;
+        const int ws[] = {1, 18, 2, 6, 10, 14};
+        for (int w : ws) for (int i = 0; i < evn[w]; ++i) all.push_back({ev[w][i] & 0xFFFFFFFFFFFFull, w, (int)(ev[w][i] >> 48)});
+        std::sort(all.begin(), all.end(), [](const E &a, const E &b) { return a.t < b.t; });
+        // print tiles 3..4 window: find the 4th occurrence of id 100 (G2 step m=0)
+        int seen = 0; unsigned long long t0 = 0, t1 = 0;
+        for (auto &e : all) if (e.w == 1 && e.id == 100) { ++seen; if (seen == 4) t0 = e.t; if (seen == 5) t1 = e.t; }
+        printf("timeline of tile 3 (cycles since its first G2 step; tile period %llu):\n", t1 - t0);
+        for (auto &e : all) if (e.t >= t0 && e.t < t1) printf("  %6llu  warp %2d  evt %d\n", e.t - t0, e.w, e.id);
     }
     return 0;
 }
