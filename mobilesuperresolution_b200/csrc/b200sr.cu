@@ -18,6 +18,7 @@
 #include "wdsr_bf16.cuh"
 #include "wdsr_f32.cuh"
 #include "wdsr_tc5_layout.cuh"
+#include "wdsr_tc5_tail.cuh"
 
 #include <cstdlib>
 
@@ -79,6 +80,8 @@ struct b200sr_wdsr {
     int block_impl = 0;                // 0 = mma.sync kernel, 1 = tcgen05 sequential form, 2 = tcgen05 pipelined form
     float *d_tail_f32 = nullptr;
     uint8_t *d_tail_bf16 = nullptr;
+    uint8_t *d_tail_tc5 = nullptr;   // tcgen05 tail image (nullptr unless the trunk is padded to 24 channels)
+    int tail_impl = 1;               // 0 = mma.sync kernel, 1 = tcgen05 kernel
     mutable int launches = 0;
 
     void free_device() {
@@ -90,6 +93,7 @@ struct b200sr_wdsr {
         d_blk_f32.clear(), d_blk_bf16.clear(), d_blk_tc5.clear();
         if (d_tail_f32) cudaFree(d_tail_f32), d_tail_f32 = nullptr;
         if (d_tail_bf16) cudaFree(d_tail_bf16), d_tail_bf16 = nullptr;
+        if (d_tail_tc5) cudaFree(d_tail_tc5), d_tail_tc5 = nullptr;
     }
 };
 
@@ -309,6 +313,32 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
         }
         if ((rc = upload(img.data(), img.size(), (void **)&p->d_tail_bf16))) return rc;
     }
+    if (CP == 24) {   // tcgen05 tail image (wdsr_tc5_tail.cuh): 3x3 chunks ordered (dx, c, dy); skip = 25 window pixels x 4 channels
+        const int NOP = round_up(NO, 16);
+        TailTc5Layout L(NOP);
+        std::vector<uint8_t> img((size_t)L.total, 0);
+        auto at = [&](int off) { return (uint16_t *)(img.data() + off); };
+        for (int o = 0; o < NO; ++o) {
+            for (int c = 0; c < C; ++c)
+                for (int dy = 0; dy < 3; ++dy)
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const int q = (dx * 3 + c / 8) * 3 + dy;
+                        at(L.wt + (o / 8) * L.sbo_t + q * 128 + (o % 8) * 16)[c % 8] = f2bf(p->tail_w[((size_t)o * C + c) * 9 + dy * 3 + dx]);
+                    }
+            for (int c = 0; c < 3; ++c)
+                for (int ky = 0; ky < 5; ++ky)
+                    for (int kx = 0; kx < 5; ++kx) {
+                        const int k = (ky * 5 + kx) * 4 + c;   // window pixel * 4 + channel
+                        at(L.ws + (o / 8) * L.sbo_s + (k / 8) * 128 + (o % 8) * 16)[k % 8] = f2bf(p->skip_w[(size_t)o * 75 + c * 25 + ky * 5 + kx]);
+                    }
+            ((float *)(img.data() + L.bias))[o] = p->tail_b[o] + p->skip_b[o];
+        }
+        if ((rc = upload(img.data(), img.size(), (void **)&p->d_tail_tc5))) return rc;
+    }
+    {
+        const char *e = getenv("B200SR_TAIL_IMPL");   // developer switch: mma | tc5
+        p->tail_impl = (e && !strcmp(e, "mma")) ? 0 : 1;
+    }
     p->committed = true;
     return 0;
 }
@@ -365,6 +395,8 @@ int b200sr_wdsr_tail(const b200sr_wdsr_t *p, const void *trunk, const void *x, i
     if (precision == B200SR_F32)
         CU(launch_tail_f32(p->cp, p->scale, x_dtype, y_dtype, (const float *)trunk, x, y, p->d_tail_f32, n, h, w, p->mean,
                            out_add, (cudaStream_t)stream));
+    else if (p->tail_impl && p->d_tail_tc5)
+        CU(launch_tail_tc5(p->scale, x_dtype, y_dtype, trunk, x, y, p->d_tail_tc5, n, h, w, p->mean, out_add, (cudaStream_t)stream));
     else
         CU(launch_tail_bf16(p->cp, p->scale, x_dtype, y_dtype, trunk, x, y, p->d_tail_bf16, n, h, w, p->mean, out_add,
                             (cudaStream_t)stream));

@@ -1,0 +1,241 @@
+// wdsr_tc5_tail.cuh -- fused WDSR-B tail on tcgen05:
+//   y = PixelShuffle_s( conv3x3(trunk, Wt) + conv5x5(x - mean, Ws) + (bt + bs) ) + out_add          models/basic_wdsr_b.py:90-92
+//
+// One persistent CTA per SM, 32 x 8 LR-pixel tiles = two M-tiles of 128 pixels (4 rows x 32).  No stage depends on another
+// CTA-local result, so the pipeline is a plain producer -> MMA -> epilogue chain:
+//   warp 0      TMA      nine cp.async.bulk.tensor.5d per tile: three x-shifted copies (one per horizontal tap) of the three
+//                        8-channel planes of the trunk tile + 1-row halo, so every 3x3 tap is a constant address offset;
+//                        out-of-image pixels are zero-filled by the TMA unit (= the conv's zero padding); double buffered
+//   warps 2-5   builder  stages (x - mean) as an NHWC4 bf16 tile, then im2col of the 5x5 skip for one M-tile: pixel p's 25
+//                        window pixels x 4 channels are 25 8-byte loads and 13 16-byte stores, no repacking (K = 104)
+//   warp 1      MMA      14 (3x3: 27 (tap, chunk) slices paired through the LBO stride) + 7 (skip) tcgen05.mma, N = 3 s^2 padded to 16
+//   warps 6-9   epilogue tcgen05.ld -> + bias + mean -> PixelShuffle store: lane = LR pixel, 32 lanes x s outputs are one
+//                        contiguous segment of an HR row
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc5.cuh"
+
+namespace b200sr {
+
+struct TailTc5Layout {  // weight image (bytes); rows = output channel (NOP = 3 s^2 padded to 16)
+    int wt, ws, bias, total, sbo_t, sbo_s;
+    __host__ __device__ TailTc5Layout(int NOP) {
+        sbo_t = 28 * 128;  // 27 (dx, c, dy) chunks + zero chunk
+        sbo_s = 14 * 128;  // 13 window chunks + zero chunk
+        wt = 0;
+        ws = wt + (NOP / 8) * sbo_t;
+        bias = ws + (NOP / 8) * sbo_s;
+        total = bias + NOP * 4;
+    }
+};
+
+namespace tc5tail {
+constexpr int TW = 32, TH = 8, NTHREADS = 320;
+constexpr int PLANE = (TH + 2) * TW * 16;  // 5,120 B: 10 rows x 32 px x 16 B
+constexpr int TC_BUF = 9 * PLANE;          // 46,080 B per tile (3 copies x 3 planes)
+constexpr int SK_BUF = 13 * 128 * 16;      // 26,624 B per M-tile (+ 2 KB slack read by the dummy half of the 7th instruction)
+constexpr int SK_STRIDE = SK_BUF + 2048;
+constexpr int XW = TW + 4, XH = TH + 4;    // x tile with 2-pixel halo, 8 bytes per pixel
+constexpr int X4_BUF = XH * XW * 8;        // 3,456 B
+constexpr int CTRL = 256;
+enum Bar { TC_FULL = 0, TC_EMPTY = 2, SK_FULL = 4, SK_EMPTY = 6, D_FULL = 8, D_EMPTY = 10, NBARS = 12 };
+__host__ __device__ inline size_t smem_bytes(int NOP) {
+    return (size_t)CTRL + 2 * TC_BUF + 2 * SK_STRIDE + X4_BUF + (size_t)TailTc5Layout(NOP).total;
+}
+}  // namespace tc5tail
+
+template <typename TIN, typename TOUT, int S>
+__global__ void __launch_bounds__(tc5tail::NTHREADS, 1)
+wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *__restrict__ x, TOUT *__restrict__ y,
+                     const uint8_t *__restrict__ wimg, int N, int H, int W, int tiles_x, int tiles_y, int ntiles, float mean, float out_add) {
+    using namespace tc5tail;
+    constexpr int NO = 3 * S * S, NOP = round_up(NO, 16);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const TailTc5Layout L(NOP);
+    uint8_t *ctrl = smem_raw;
+    uint8_t *tc = smem_raw + CTRL;       // 2 x TC_BUF
+    uint8_t *sk = tc + 2 * TC_BUF;       // 2 x SK_STRIDE
+    uint8_t *x4 = sk + 2 * SK_STRIDE;    // X4_BUF
+    uint8_t *wsm = x4 + X4_BUF;          // L.total
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bars = smem_u32(ctrl);
+    auto bar = [&](int b) { return bars + 8u * (uint32_t)b; };
+    const uint32_t tc_u = smem_u32(tc), sk_u = smem_u32(sk), w_u = smem_u32(wsm);
+
+    if (tid == 0) {
+        for (int e = 0; e < 2; ++e) {
+            tc5::mbar_init(bar(TC_FULL + e), 1);
+            tc5::mbar_init(bar(TC_EMPTY + e), 1);
+            tc5::mbar_init(bar(SK_FULL + e), 128);
+            tc5::mbar_init(bar(SK_EMPTY + e), 1);
+            tc5::mbar_init(bar(D_FULL + e), 1);
+            tc5::mbar_init(bar(D_EMPTY + e), 128);
+        }
+        tc5::mbar_init_fence();
+        tc5::tma_prefetch_desc(&tmap_trunk);
+    }
+    __syncwarp();
+    if (warp == 0) tc5::tmem_alloc(smem_u32(ctrl + 240), 128);
+    for (int i = tid; i < L.total / 16; i += NTHREADS) cp_async16(wsm + i * 16, wimg + i * 16, 16);
+    cp_async_commit();
+    for (int i = tid; i < 2 * SK_STRIDE / 16; i += NTHREADS) *reinterpret_cast<uint4 *>(sk + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    // the zero-weight dummy half of the 14th 3x3 instruction reads one row past the last plane of a buffer: keep it finite
+    // before buffer 1 has ever been loaded (buffer 1 overflows into the zeroed skip area)
+    for (int i = tid; i < 512 / 16; i += NTHREADS) *reinterpret_cast<uint4 *>(tc + TC_BUF + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    cp_async_wait<0>();
+    tc5::fence_proxy_async();
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(ctrl + 240);
+    const int nmine = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    auto tile_origin = [&](int it, int &x0, int &y0, int &n) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        x0 = (tile % tiles_x) * TW;
+        y0 = ((tile / tiles_x) % tiles_y) * TH;
+        n = tile / (tiles_x * tiles_y);
+    };
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (tc5::elect_one()) {
+            for (int it = 0; it < nmine; ++it) {
+                int x0, y0, n;
+                tile_origin(it, x0, y0, n);
+                const int b = it & 1;
+                tc5::mbar_wait(bar(TC_EMPTY + b), ((it >> 1) & 1) ^ 1);
+                tc5::mbar_arrive_expect_tx(bar(TC_FULL + b), TC_BUF);
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        tc5::tma_load_5d(tc_u + b * TC_BUF + (d * 3 + c) * PLANE, &tmap_trunk, bar(TC_FULL + b), 0, c, x0 - 1 + d, y0 - 1, n);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        const bool leader = tc5::elect_one();
+        const uint32_t idesc = tc5::idesc_bf16_f32(128, NOP);
+        const uint64_t bwt = tc5::smem_desc(w_u + L.wt, 128, L.sbo_t), bws = tc5::smem_desc(w_u + L.ws, 128, L.sbo_s);
+        const uint64_t at0 = tc5::smem_desc(tc_u, 0, 128), as0 = tc5::smem_desc(sk_u, 2048, 128);
+        for (int g = 0; g < 2 * nmine; ++g) {
+            const int it = g >> 1, h = g & 1, b = it & 1, e = g & 1;
+            if (h == 0) tc5::mbar_wait(bar(TC_FULL + b), (it >> 1) & 1);
+            tc5::mbar_wait(bar(SK_FULL + e), (g >> 1) & 1);
+            tc5::mbar_wait(bar(D_EMPTY + e), ((g >> 1) & 1) ^ 1);
+            tc5::fence_after_sync();
+            if (leader) {
+                const uint32_t d = tmem + e * 64;
+                const uint64_t abase = at0 + (uint64_t)((b * TC_BUF + 4 * h * 512) >> 4);
+#pragma unroll
+                for (int i = 0; i < 14; ++i) {  // chunk order q = (dx * 3 + c) * 3 + dy  ->  offset (dx*3+c) * PLANE + dy * 512
+                    const int q0 = 2 * i, q1 = 2 * i + 1;
+                    const int a0 = (q0 / 3) * PLANE + (q0 % 3) * 512;
+                    const int a1 = q1 < 27 ? (q1 / 3) * PLANE + (q1 % 3) * 512 : a0 + 512;
+                    tc5::mma_ss(d, abase + (uint64_t)(a0 >> 4) + ((uint64_t)((a1 - a0) >> 4) << 16), bwt + (uint64_t)(16 * i), idesc, i > 0);
+                }
+                const uint64_t sbase = as0 + (uint64_t)((e * SK_STRIDE) >> 4);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) tc5::mma_ss(d, sbase + (uint64_t)((2 * i * 2048) >> 4), bws + (uint64_t)(16 * i), idesc, true);
+                tc5::commit(bar(D_FULL + e));
+                tc5::commit(bar(SK_EMPTY + e));
+                if (h == 1) tc5::commit(bar(TC_EMPTY + b));
+            }
+            __syncwarp();
+        }
+        if (nmine > 0) tc5::mbar_wait(bar(D_FULL + 1), ((2 * nmine - 1) >> 1) & 1);  // every MMA retired
+    } else if (warp < 6) {
+        // ============================== builders: x - mean tile, skip im2col ==============================
+        const int bt = tid - 64;  // 0..127
+        for (int g = 0; g < 2 * nmine; ++g) {
+            const int it = g >> 1, h = g & 1, e = g & 1;
+            int x0, y0, n;
+            tile_origin(it, x0, y0, n);
+            if (h == 0) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone finished reading the previous tile's x4
+                for (int i = bt; i < XH * XW; i += 128) {
+                    const int gy = y0 - 2 + i / XW, gx = x0 - 2 + i % XW;
+                    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+                    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                        const long long o = (((long long)n * 3) * H + gy) * W + gx;
+                        v0 = to_f32<TIN>(x[o]) - mean;
+                        v1 = to_f32<TIN>(x[o + (long long)H * W]) - mean;
+                        v2 = to_f32<TIN>(x[o + 2ll * H * W]) - mean;
+                    }
+                    uint2 pk;
+                    pk.x = pack_bf16x2(v0, v1);
+                    pk.y = pack_bf16x2(v2, 0.f);
+                    *reinterpret_cast<uint2 *>(x4 + i * 8) = pk;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            tc5::mbar_wait(bar(SK_EMPTY + e), ((g >> 1) & 1) ^ 1);
+            const int ly = 4 * h + (bt >> 5), lx = bt & 31;
+            uint2 wv[26];
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) wv[ky * 5 + kx] = *reinterpret_cast<const uint2 *>(x4 + ((ly + ky) * XW + lx + kx) * 8);
+            wv[25] = make_uint2(0u, 0u);
+            uint8_t *dst = sk + e * SK_STRIDE + bt * 16;
+#pragma unroll
+            for (int j = 0; j < 13; ++j) *reinterpret_cast<uint4 *>(dst + j * 2048) = make_uint4(wv[2 * j].x, wv[2 * j].y, wv[2 * j + 1].x, wv[2 * j + 1].y);
+            tc5::fence_proxy_async();
+            tc5::mbar_arrive(bar(SK_FULL + e));
+        }
+    } else {
+        // ============================== epilogue ==============================
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const float *bias = reinterpret_cast<const float *>(wsm + L.bias);
+        const int OH = S * H, OW = S * W;
+        for (int g = 0; g < 2 * nmine; ++g) {
+            const int it = g >> 1, h = g & 1, e = g & 1;
+            int x0, y0, n;
+            tile_origin(it, x0, y0, n);
+            tc5::mbar_wait(bar(D_FULL + e), (g >> 1) & 1);
+            tc5::fence_after_sync();
+            uint32_t v[NOP];
+#pragma unroll
+            for (int c = 0; c < NOP; c += 16) tc5::tmem_ld16(tmem + lane_base + e * 64 + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+            tc5::tmem_wait_ld();
+            tc5::fence_before_sync();
+            tc5::mbar_arrive_relaxed(bar(D_EMPTY + e));
+            const int gy = y0 + 4 * h + (row >> 5), gx = x0 + (row & 31);
+            if (gy < H && gx < W) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int i = 0; i < S; ++i) {
+                        TOUT *o = y + (((long long)n * 3 + c) * OH + (S * gy + i)) * OW + S * gx;
+                        float r[S];
+#pragma unroll
+                        for (int j = 0; j < S; ++j) {
+                            const int ch = c * S * S + i * S + j;
+                            r[j] = __uint_as_float(v[ch]) + bias[ch] + out_add;
+                        }
+                        if constexpr (S == 4 && sizeof(TOUT) == 2) {
+                            *reinterpret_cast<uint2 *>(o) = make_uint2(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]));
+                        } else if constexpr (S == 4 && sizeof(TOUT) == 4) {
+                            *reinterpret_cast<float4 *>(o) = make_float4(r[0], r[1], r[2], r[3]);
+                        } else if constexpr (S == 2 && sizeof(TOUT) == 2) {
+                            *reinterpret_cast<uint32_t *>(o) = pack_bf16x2(r[0], r[1]);
+                        } else if constexpr (S == 2 && sizeof(TOUT) == 4) {
+                            *reinterpret_cast<float2 *>(o) = make_float2(r[0], r[1]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < S; ++j) o[j] = from_f32<TOUT>(r[j]);
+                        }
+                    }
+            }
+        }
+    }
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc5::tmem_free(tmem, 128);
+}
+
+}  // namespace b200sr
