@@ -18,6 +18,7 @@
 #include "wdsr_bf16.cuh"
 #include "wdsr_f32.cuh"
 #include "wdsr_tc5_layout.cuh"
+#include "wdsr_tc5_head.cuh"
 #include "wdsr_tc5_tail.cuh"
 
 #include <cstdlib>
@@ -80,6 +81,7 @@ struct b200sr_wdsr {
     int block_impl = 0;                // 0 = mma.sync kernel, 1 = tcgen05 sequential form, 2 = tcgen05 pipelined form
     float *d_tail_f32 = nullptr;
     uint8_t *d_tail_bf16 = nullptr;
+    uint8_t *d_head_tc5 = nullptr;   // tcgen05 head image (trunk padded to 24 channels)
     uint8_t *d_tail_tc5 = nullptr;   // tcgen05 tail image (nullptr unless the trunk is padded to 24 channels)
     int tail_impl = 1;               // 0 = mma.sync kernel, 1 = tcgen05 kernel
     mutable int launches = 0;
@@ -94,6 +96,7 @@ struct b200sr_wdsr {
         if (d_tail_f32) cudaFree(d_tail_f32), d_tail_f32 = nullptr;
         if (d_tail_bf16) cudaFree(d_tail_bf16), d_tail_bf16 = nullptr;
         if (d_tail_tc5) cudaFree(d_tail_tc5), d_tail_tc5 = nullptr;
+        if (d_head_tc5) cudaFree(d_head_tc5), d_head_tc5 = nullptr;
     }
 };
 
@@ -313,6 +316,19 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
         }
         if ((rc = upload(img.data(), img.size(), (void **)&p->d_tail_bf16))) return rc;
     }
+    if (CP == 24) {   // tcgen05 head image (wdsr_tc5_head.cuh): k = window pixel (ky*3+kx) * 4 + channel
+        HeadTc5Layout L;
+        std::vector<uint8_t> img((size_t)L.total, 0);
+        for (int o = 0; o < C; ++o) {
+            for (int c = 0; c < 3; ++c)
+                for (int t = 0; t < 9; ++t) {
+                    const int k = t * 4 + c;
+                    ((uint16_t *)(img.data() + L.w + (o / 8) * (6 * 128) + (k / 8) * 128 + (o % 8) * 16))[k % 8] = f2bf(p->head_w[(size_t)o * 27 + c * 9 + t]);
+                }
+            ((float *)(img.data() + L.bias))[o] = p->head_b[o];
+        }
+        if ((rc = upload(img.data(), img.size(), (void **)&p->d_head_tc5))) return rc;
+    }
     if (CP == 24) {   // tcgen05 tail image (wdsr_tc5_tail.cuh): 3x3 chunks ordered (dx, c, dy); skip = 25 window pixels x 4 channels
         const int NOP = round_up(NO, 16);
         TailTc5Layout L(NOP);
@@ -366,7 +382,10 @@ int b200sr_wdsr_head(const b200sr_wdsr_t *p, const void *x, int x_dtype, void *t
     int rc = check_common(p, n, h, w, precision, "wdsr_head");
     if (rc) return rc;
     if (!x || !trunk) return fail(B200SR_E_INVAL, "wdsr_head: null tensor");
-    CU(launch_head(p->cp, x_dtype, precision, x, trunk, p->d_head, n, h, w, p->mean, (cudaStream_t)stream));
+    if (precision == B200SR_BF16 && p->tail_impl && p->d_head_tc5)
+        CU(launch_head_tc5(x_dtype, x, trunk, p->d_head_tc5, n, h, w, p->mean, (cudaStream_t)stream));
+    else
+        CU(launch_head(p->cp, x_dtype, precision, x, trunk, p->d_head, n, h, w, p->mean, (cudaStream_t)stream));
     return 0;
 }
 

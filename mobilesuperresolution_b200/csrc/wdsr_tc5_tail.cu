@@ -1,6 +1,7 @@
 // wdsr_tc5_tail.cu -- launcher of the tcgen05 fused tail kernel.
 #include "launch.h"
 #include "tma_map.h"
+#include "wdsr_tc5_head.cuh"
 #include "wdsr_tc5_tail.cuh"
 
 namespace b200sr {
@@ -56,6 +57,31 @@ cudaError_t launch_tail_tc5(int S, int xd, int yd, const void *trunk, const void
         case 3: return tail_tc5_io<3>(xd, yd, trunk, x, y, wimg, N, H, W, mean, out_add, st);
         case 4: return tail_tc5_io<4>(xd, yd, trunk, x, y, wimg, N, H, W, mean, out_add, st);
     }
+    return cudaErrorInvalidValue;
+}
+
+
+template <typename TIN>
+static cudaError_t head_tc5_t(const void *x, void *trunk, const uint8_t *wimg, int N, int H, int W, float mean, cudaStream_t st) {
+    using namespace tc5head;
+    auto kern = wdsr_head_tc5_kernel<TIN>;
+    const size_t smem = smem_bytes();
+    static thread_local bool set = false;
+    if (!set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        set = true;
+    }
+    const int tx = ceil_div(W, TW), ty = ceil_div(H, TH), ntiles = tx * ty * N;
+    int ctas = 2 * sm_count();
+    if (ctas > ntiles) ctas = ntiles;
+    kern<<<ctas, NTHREADS, smem, st>>>((const TIN *)x, (bf16 *)trunk, wimg, N, H, W, tx, ty, ntiles, mean);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_head_tc5(int xd, const void *x, void *trunk, const uint8_t *wimg, int N, int H, int W, float mean, cudaStream_t st) {
+    if (xd == kF32) return head_tc5_t<float>(x, trunk, wimg, N, H, W, mean, st);
+    if (xd == kBF16) return head_tc5_t<bf16>(x, trunk, wimg, N, H, W, mean, st);
     return cudaErrorInvalidValue;
 }
 
