@@ -94,16 +94,22 @@ wdsr_head_tc5_kernel(const TIN *__restrict__ x, bf16 *__restrict__ trunk, const 
             tile_origin(it, x0, y0, n);
             if (h == 0) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int i = bt; i < XH * XW; i += 128) {
+                // all global loads of the staging pass are issued before the first use (one memory latency per tile, not four)
+                constexpr int NIT = (XH * XW + 127) / 128;
+                float v[NIT][3];
+#pragma unroll
+                for (int k = 0; k < NIT; ++k) {
+                    const int i = bt + 128 * k;
                     const int gy = y0 - 1 + i / XW, gx = x0 - 1 + i % XW;
-                    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-                    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                        const long long o = (((long long)n * 3) * H + gy) * W + gx;
-                        v0 = to_f32<TIN>(x[o]) - mean;
-                        v1 = to_f32<TIN>(x[o + (long long)H * W]) - mean;
-                        v2 = to_f32<TIN>(x[o + 2ll * H * W]) - mean;
-                    }
-                    *reinterpret_cast<uint2 *>(x4 + i * 8) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v2, 0.f));
+                    const bool ok = i < XH * XW && gy >= 0 && gy < H && gx >= 0 && gx < W;
+                    const long long o = ok ? (((long long)n * 3) * H + gy) * W + gx : 0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[k][c] = ok ? to_f32<TIN>(x[o + (long long)c * H * W]) - mean : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < NIT; ++k) {
+                    const int i = bt + 128 * k;
+                    if (i < XH * XW) *reinterpret_cast<uint2 *>(x4 + i * 8) = make_uint2(pack_bf16x2(v[k][0], v[k][1]), pack_bf16x2(v[k][2], 0.f));
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }

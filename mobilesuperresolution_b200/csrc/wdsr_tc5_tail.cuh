@@ -156,19 +156,22 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
             tile_origin(it, x0, y0, n);
             if (h == 0) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone finished reading the previous tile's x4
-                for (int i = bt; i < XH * XW; i += 128) {
+                // all global loads of the staging pass are issued before the first use (one memory latency per tile, not four)
+                constexpr int NIT = (XH * XW + 127) / 128;
+                float v[NIT][3];
+#pragma unroll
+                for (int k = 0; k < NIT; ++k) {
+                    const int i = bt + 128 * k;
                     const int gy = y0 - 2 + i / XW, gx = x0 - 2 + i % XW;
-                    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-                    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                        const long long o = (((long long)n * 3) * H + gy) * W + gx;
-                        v0 = to_f32<TIN>(x[o]) - mean;
-                        v1 = to_f32<TIN>(x[o + (long long)H * W]) - mean;
-                        v2 = to_f32<TIN>(x[o + 2ll * H * W]) - mean;
-                    }
-                    uint2 pk;
-                    pk.x = pack_bf16x2(v0, v1);
-                    pk.y = pack_bf16x2(v2, 0.f);
-                    *reinterpret_cast<uint2 *>(x4 + i * 8) = pk;
+                    const bool ok = i < XH * XW && gy >= 0 && gy < H && gx >= 0 && gx < W;
+                    const long long o = ok ? (((long long)n * 3) * H + gy) * W + gx : 0;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) v[k][c] = ok ? to_f32<TIN>(x[o + (long long)c * H * W]) - mean : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < NIT; ++k) {
+                    const int i = bt + 128 * k;
+                    if (i < XH * XW) *reinterpret_cast<uint2 *>(x4 + i * 8) = make_uint2(pack_bf16x2(v[k][0], v[k][1]), pack_bf16x2(v[k][2], 0.f));
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
@@ -212,10 +215,18 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
                     for (int i = 0; i < S; ++i) {
                         TOUT *o = y + (((long long)n * 3 + c) * OH + (S * gy + i)) * OW + S * gx;
                         float r[S];
+                        if constexpr (S == 4) {
+                            const float4 bb = *reinterpret_cast<const float4 *>(bias + c * 16 + i * 4);  // broadcast read
+                            r[0] = __uint_as_float(v[c * 16 + i * 4 + 0]) + bb.x + out_add;
+                            r[1] = __uint_as_float(v[c * 16 + i * 4 + 1]) + bb.y + out_add;
+                            r[2] = __uint_as_float(v[c * 16 + i * 4 + 2]) + bb.z + out_add;
+                            r[3] = __uint_as_float(v[c * 16 + i * 4 + 3]) + bb.w + out_add;
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < S; ++j) {
-                            const int ch = c * S * S + i * S + j;
-                            r[j] = __uint_as_float(v[ch]) + bias[ch] + out_add;
+                            for (int j = 0; j < S; ++j) {
+                                const int ch = c * S * S + i * S + j;
+                                r[j] = __uint_as_float(v[ch]) + bias[ch] + out_add;
+                            }
                         }
                         if constexpr (S == 4 && sizeof(TOUT) == 2) {
                             *reinterpret_cast<uint2 *>(o) = make_uint2(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]));
