@@ -122,6 +122,10 @@ int b200sr_wdsr_create(const b200sr_wdsr_desc *d, b200sr_wdsr_t **out) {
     b200sr_wdsr *p = new (std::nothrow) b200sr_wdsr();
     if (!p) return fail(B200SR_E_INVAL, "wdsr_create: out of memory");
     p->scale = d->scale, p->nb = d->num_blocks, p->cin = d->c_trunk, p->cp = round_up(d->c_trunk, 8);
+    {   // developer switch: pad every trunk to 24 channels so pruned nets also take the tcgen05 kernels
+        const char *e = getenv("B200SR_TRUNK_PAD24");
+        if (e && e[0] == '1') p->cp = 24;
+    }
     p->add_mean = d->add_mean, p->mean = d->image_mean, p->no = 3 * d->scale * d->scale;
     for (int i = 0; i < p->nb; ++i) {
         const int m1 = d->m1[i], m2 = d->m2[i];

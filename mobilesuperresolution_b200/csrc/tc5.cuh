@@ -155,10 +155,23 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // n
         : "memory");
     return ok != 0;
 }
+#ifdef B200SR_TC5_PROF
+__device__ volatile unsigned *g_tc5_dbg;  // mapped host memory: who timed out on which barrier (developer probes only)
+#endif
 // bounded wait: a protocol bug must fault the launch (caught by the host as a CUDA error), never hang the GPU box
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
-        if (it > (1u << 24)) __trap();
+        if (it > (1u << 22)) {
+#ifdef B200SR_TC5_PROF
+            if (g_tc5_dbg && (threadIdx.x & 31) == 0) {
+                volatile unsigned *d = g_tc5_dbg + 4 * (blockIdx.x * 32 + (threadIdx.x >> 5));
+                d[0] = 0xDEAD0000u | (threadIdx.x >> 5), d[1] = bar, d[2] = parity, d[3] = blockIdx.x;
+                __threadfence_system();
+            }
+            for (volatile int spin = 0; spin < 2000000; ++spin) {}
+#endif
+            __trap();
+        }
 }
 
 }  // namespace tc5

@@ -6,11 +6,13 @@
 //   warp 1      MMA issuer A   one elected lane issues the G1 / G2 stream (software-pipelined over M-tiles)
 //   warp 18     MMA issuer B   one elected lane issues the 3x3 (G3) stream; two issuers so that neither stream's barrier
 //                              wait blocks the other -- the tensor pipe interleaves them
-//   warps 2-5   WG-A   E1 (relu -> bf16 A operand) of even M-tiles  +  E3 (bias + residual + store) of 3x3 M-tiles 1,3
-//   warps 6-9   WG-B   E1 of odd M-tiles                            +  E3 of 3x3 M-tiles 0,2
-//               (each warp polls both of its queues and serves E1 first: E1 sits on the G1 -> G2 critical loop)
-//   warps 10-13 WG-C   E2 (t2 -> three shifted copies in shared memory) of even M-tiles
-//   warps 14-17 WG-D   E2 of odd M-tiles
+//   warps 2-5   WG-A   E1 (relu -> bf16 A operand), expand channels 0..63 of EVERY M-tile
+//   warps 6-9   WG-B   E1, expand channels 64..143 of every M-tile
+//               (E1 sits on the G1 -> G2 critical loop: two warpgroups split its columns and do nothing else;
+//                WG-A packs into columns 0..31 of D1, WG-B into columns 104..143 -- both in place inside their own half)
+//   warps 10-13 WG-C   E2 (t2 -> three shifted copies in shared memory) of even M-tiles  +  E3 (bias + residual + store) of 3x3 M-tiles 1,3
+//   warps 14-17 WG-D   E2 of odd M-tiles                                                  +  E3 of 3x3 M-tiles 0,2
+//               (per warp two in-order queues, E2 first: E2 feeds the 3x3 MMAs, E3 only drains results)
 // (a warp can only touch TMEM lanes 32*(warp%4)..+31, so every warpgroup is 4 consecutive warps.)
 //
 // Shared-memory operand layout (SWIZZLE_NONE, K-major): chunk-planar  XS[plane c][pixel p][16 B]  for the trunk tile
@@ -63,7 +65,7 @@ __host__ __device__ constexpr int d2_col(int e) { return 288 + e * 32; }
 __host__ __device__ constexpr int d3_col(int k) { return 352 + k * 32; }
 // The MMA issuer is one thread and an mbarrier wait costs it ~100 clk even when already complete, so everything a group of
 // MMAs needs is folded into ONE barrier:
-//   G2_READY[e] (256) = E1 of this M-tile wrote A2 into D1[e]  +  E2 of the previous M-tile on this buffer drained D2[e]
+//   G2_READY[e] (384) = both column halves of E1 wrote A2 into D1[e]  +  E2 of the previous M-tile on this buffer drained D2[e]
 //   G3_READY[k] (384) = E2 of M-tiles k and k+1 wrote their t2 rows  +  E3 of the previous tile drained D3[k]
 enum Bar { XS_FULL = 0 /*3*/, XS_EMPTY = 3 /*3*/, D1_FULL = 6, G2_READY = 8, D2_FULL = 10, G3_READY = 12 /*4*/, T2R_FREE = 16 /*4*/,
            D3_FULL = 20 /*4*/, NBARS = 24 };
@@ -95,11 +97,11 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
     if (tid == 0) {
         for (int b = 0; b < XS_NBUF; ++b) {
             tc5::mbar_init(bar(XS_FULL + b), 1);
-            tc5::mbar_init(bar(XS_EMPTY + b), 257);  // commit after the last G1 + the 256 threads of WG-A/B after their E3
+            tc5::mbar_init(bar(XS_EMPTY + b), 257);  // commit after the last G1 + the 256 threads of WG-C/D after their E3
         }
         for (int e = 0; e < 2; ++e) {
             tc5::mbar_init(bar(D1_FULL + e), 1);
-            tc5::mbar_init(bar(G2_READY + e), 256);
+            tc5::mbar_init(bar(G2_READY + e), 384);
             tc5::mbar_init(bar(D2_FULL + e), 1);
         }
         for (int k = 0; k < 4; ++k) {
@@ -159,6 +161,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         const uint64_t bw2 = tc5::smem_desc(w_u + L.w2, 128, L.sbo2);
         const uint64_t ax0 = tc5::smem_desc(xs_u, XS_PLANE, 128);  // planes paired through LBO
         const int nk2 = M1P / 16;
+        const int a2hi = M1P - (M1P - 64) / 2;   // first column of WG-B's packed output (104 for M1P = 144)
         auto issue_g1 = [&](int xb, int m) {  // leader only
             const uint32_t off = xb * XS_BUF + m * 2048;
             const int e = m & 1;
@@ -191,9 +194,10 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                 V3_EVT(100 + m);
                 if (leader) {
                     const uint32_t d2 = tmem + d2_col(e), a2 = tmem + d1_col(e);
+                    // A2 columns: k-steps 0..3 at columns 8j (written by WG-A), k-steps 4.. at 104 + 8(j-4) (WG-B); see e1()
                     tc5::mma_ts(d2, a2, bw2, idesc32, false);
 #pragma unroll 4
-                    for (int j = 1; j < nk2; ++j) tc5::mma_ts(d2, a2 + 8 * j, bw2 + (uint64_t)(16 * j), idesc32, true);
+                    for (int j = 1; j < nk2; ++j) tc5::mma_ts(d2, a2 + (j < 4 ? 8 * j : a2hi + 8 * (j - 4)), bw2 + (uint64_t)(16 * j), idesc32, true);
                     tc5::commit(bar(D2_FULL + e));
                     if (m + 2 < NMT) {
                         issue_g1(xb, m + 2);
@@ -251,49 +255,57 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         const float *b2s = reinterpret_cast<const float *>(wsm + L.b2);
         const float *b3s = reinterpret_cast<const float *>(wsm + L.b3);
 
-        // ---- E1: relu(D1) -> bf16 A2, in place; the next 32 columns are in flight while a batch is converted
-        auto e1 = [&]() {
+        // ---- E1: relu(D1) -> bf16 A2, packed in place.  Column split between the two warpgroups (wg 0: expand channels 0..63 ->
+        //      columns 0..31; wg 1: channels 64..M1P-1 -> the top (M1P-64)/2 columns of D1).  Each thread reads ALL of its
+        //      columns before it writes, so packing in place inside its own half is safe.
+        auto e1 = [&](int eb) {
             tc5::fence_after_sync();
             V3_T0();
             V3_EVT(300);
-            const uint32_t d1 = tmem + lane_base + d1_col(e);
-            if (M1P == 144) {
+            const uint32_t d1 = tmem + lane_base + d1_col(eb);
+            if (wg == 0) {
                 uint32_t va[32], vb[32];
-                auto cvt_store = [&](uint32_t (&v)[32], int col) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = tc5::relu_pack_bf16x2(v[2 * j], v[2 * j + 1]);
-                    tc5::tmem_st16(d1 + col, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-                };
                 tc5::tmem_ld32(d1, va);
-                tc5::tmem_wait_ld();
                 tc5::tmem_ld32(d1 + 32, vb);
-                cvt_store(va, 0);
-                tc5::tmem_wait_ld();
-                tc5::tmem_ld32(d1 + 64, va);
-                cvt_store(vb, 16);
-                tc5::tmem_wait_ld();
-                tc5::tmem_ld32(d1 + 96, vb);
-                cvt_store(va, 32);
-                tc5::tmem_wait_ld();
-                tc5::tmem_ld16(d1 + 128, *reinterpret_cast<uint32_t(*)[16]>(&va[0]));
-                cvt_store(vb, 48);
                 tc5::tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) va[j] = tc5::relu_pack_bf16x2(va[2 * j], va[2 * j + 1]);
-                tc5::tmem_st8(d1 + 64, *reinterpret_cast<uint32_t(*)[8]>(&va[0]));
+                for (int j = 0; j < 16; ++j) va[j] = tc5::relu_pack_bf16x2(va[2 * j], va[2 * j + 1]);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) va[16 + j] = tc5::relu_pack_bf16x2(vb[2 * j], vb[2 * j + 1]);
+                tc5::tmem_st16(d1, *reinterpret_cast<uint32_t(*)[16]>(&va[0]));
+                tc5::tmem_st16(d1 + 16, *reinterpret_cast<uint32_t(*)[16]>(&va[16]));
             } else {
-                for (int k = 0; k < M1P; k += 16) {
-                    uint32_t v[16], pk[8];
-                    tc5::tmem_ld16(d1 + k, v);
+                const int nhi = M1P - 64, dst = M1P - nhi / 2;   // 80 columns -> 40 packed columns at [104, 144)
+                if (M1P == 144) {
+                    uint32_t va[32], vb[32], vc[16];
+                    tc5::tmem_ld32(d1 + 64, va);
+                    tc5::tmem_ld32(d1 + 96, vb);
+                    tc5::tmem_ld16(d1 + 128, vc);
                     tc5::tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) pk[j] = tc5::relu_pack_bf16x2(v[2 * j], v[2 * j + 1]);
-                    tc5::tmem_st8(d1 + k / 2, pk);
+                    for (int j = 0; j < 16; ++j) va[j] = tc5::relu_pack_bf16x2(va[2 * j], va[2 * j + 1]);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) va[16 + j] = tc5::relu_pack_bf16x2(vb[2 * j], vb[2 * j + 1]);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) vc[j] = tc5::relu_pack_bf16x2(vc[2 * j], vc[2 * j + 1]);
+                    tc5::tmem_st16(d1 + dst, *reinterpret_cast<uint32_t(*)[16]>(&va[0]));
+                    tc5::tmem_st16(d1 + dst + 16, *reinterpret_cast<uint32_t(*)[16]>(&va[16]));
+                    tc5::tmem_st8(d1 + dst + 32, *reinterpret_cast<uint32_t(*)[8]>(&vc[0]));
+                } else {
+                    // generic width: 16 columns at a time, top-down so that a packed write never lands on unread columns
+                    for (int k = nhi - 16; k >= 0; k -= 16) {
+                        uint32_t v[16], pk[8];
+                        tc5::tmem_ld16(d1 + 64 + k, v);
+                        tc5::tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) pk[j] = tc5::relu_pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                        tc5::tmem_st8(d1 + dst + k / 2, pk);
+                    }
                 }
             }
             tc5::tmem_wait_st();
             tc5::fence_before_sync();
-            tc5::mbar_arrive_relaxed(bar(G2_READY + e));  // A2 is complete (wait::st); no release: E3's output stores may be in flight
+            tc5::mbar_arrive_relaxed(bar(G2_READY + eb));  // A2 half complete (wait::st); no release: E3's output stores may be in flight
             V3_ADD(5);
             V3_EVT(301);
         };
@@ -384,21 +396,38 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         };
 
         if (wg < 2) {
-            // WG-A / WG-B: E1 of M-tiles m = e, e+2, .. and E3 of 3x3 M-tiles k = 1-e, 3-e.  Per warp, two in-order queues;
-            // E1 is served first whenever its accumulator is ready.  Warps of a warpgroup need not agree on the order.
+            // WG-A / WG-B: their column half of E1 for every M-tile, in issue order.  M-tile i % 5 of tile i / 5 lives in buffer
+            // (i % 5) & 1; a buffer completes 3 (even) or 2 (odd) G1s per tile.
+            for (int i1 = 0; i1 < NMT * nmine; ++i1) {
+                const int mm = i1 % NMT, eb = mm & 1, nth = (i1 / NMT) * (eb == 0 ? 3 : 2) + (mm >> 1);
+                V3_WAIT(0, bar(D1_FULL + eb), nth & 1);
+                e1(eb);
+            }
+        } else {
+            // WG-C / WG-D: E2 of M-tiles m = e, e+2, .. (first) and E3 of 3x3 M-tiles k = 1-e, 3-e.  Per warp, two in-order
+            // queues; warps of a warpgroup need not agree on the order (every hand-off counts thread arrivals).
+            tc5::mbar_arrive(bar(G2_READY + e));      // stand-in for "previous E2 drained D2[e]"
             tc5::mbar_arrive(bar(G3_READY + 1 - e));  // stand-ins for "previous tile's E3 drained D3[k]"
             tc5::mbar_arrive(bar(G3_READY + 3 - e));
-            const int ne1 = (e == 0 ? 3 : 2) * nmine, ne3 = 2 * nmine;
-            int i1 = 0, i3 = 0, ox = 0, oy = 0, on = 0;
-            if (nmine > 0) tile_origin(0, ox, oy, on);
-            while (i1 < ne1 || i3 < ne3) {
+            const int per_tile = e == 0 ? 3 : 2, ne2 = per_tile * nmine, ne3 = 2 * nmine;
+            int i2 = 0, i3 = 0, ox2 = 0, oy2 = 0, on2 = 0, ox3 = 0, oy3 = 0, on3 = 0;
+            if (nmine > 0) {
+                tile_origin(0, ox2, oy2, on2);
+                ox3 = ox2, oy3 = oy2, on3 = on2;
+            }
+            while (i2 < ne2 || i3 < ne3) {
                 bool did = false;
-                if (i1 < ne1) {
-                    const bool rdy = __any_sync(0xffffffffu, tc5::mbar_test(bar(D1_FULL + e), i1 & 1));
+                if (i2 < ne2) {
+                    const int t = i2 / per_tile, j = i2 % per_tile, m = e + 2 * j;
+                    // ready = accumulator complete AND (first E2 of a tile) every 3x3 MMA of the previous tile has retired, so T2 may
+                    // be overwritten.  Never BLOCK on the latter here: that MMA may itself wait for an E3 still queued in this warp.
+                    bool rdy = __any_sync(0xffffffffu, tc5::mbar_test(bar(D2_FULL + e), i2 & 1));
+                    if (rdy && j == 0) rdy = __any_sync(0xffffffffu, tc5::mbar_test(bar(T2R_FREE + 3), (t & 1) ^ 1));
                     if (rdy) {
-                        tc5::mbar_wait(bar(D1_FULL + e), i1 & 1);  // already complete: per-lane acquire
-                        e1();
-                        ++i1;
+                        if (j == 0) tc5::mbar_wait(bar(T2R_FREE + 3), (t & 1) ^ 1);  // complete: per-lane acquire
+                        e2(m, i2 & 1, ox2, oy2);
+                        ++i2;
+                        if (j == per_tile - 1 && t + 1 < nmine) tile_origin(t + 1, ox2, oy2, on2);
                         did = true;
                     }
                 }
@@ -408,28 +437,16 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                     if (rdy) {
                         tc5::mbar_wait(bar(D3_FULL + k), t & 1);
                         if ((i3 & 1) == 0) tc5::mbar_wait(bar(XS_FULL + (t % XS_NBUF)), (t / XS_NBUF) & 1);  // acquire the TMA-written tile
-                        e3(t, k, ox, oy, on);
-                        if ((i3 & 1) && t + 1 < nmine) tile_origin(t + 1, ox, oy, on);
-                        if (i3 & 1) tc5::mbar_arrive_relaxed(bar(XS_EMPTY + (t % XS_NBUF)));  // both E3 done: residual values were consumed
+                        e3(t, k, ox3, oy3, on3);
+                        if (i3 & 1) {
+                            tc5::mbar_arrive_relaxed(bar(XS_EMPTY + (t % XS_NBUF)));  // both E3 done: residual values were consumed
+                            if (t + 1 < nmine) tile_origin(t + 1, ox3, oy3, on3);
+                        }
                         ++i3;
                         did = true;
                     }
                 }
-                if (!did) __nanosleep(40);  // do not steal issue slots from the MMA issuers / other epilogue warps while polling
-            }
-        } else {
-            // WG-C / WG-D: E2 of M-tiles m = e, e+2, ..
-            tc5::mbar_arrive(bar(G2_READY + e));  // stand-in for "previous E2 drained D2[e]"
-            uint32_t n_d2 = 0;
-            for (int it = 0; it < nmine; ++it) {
-                // every 3x3 MMA of the previous tile has retired (commits are in order) before T2 is overwritten
-                int x0, y0, n;
-                tile_origin(it, x0, y0, n);
-                V3_WAIT(2, bar(T2R_FREE + 3), (it & 1) ^ 1);
-                for (int m = e; m < NMT; m += 2) {
-                    e2(m, n_d2 & 1, x0, y0);
-                    ++n_d2;
-                }
+                if (!did) __nanosleep(40);
             }
         }
     }

@@ -1,6 +1,7 @@
 // tc5p_probe.cu -- barrier-wait / stage timers of the production tcgen05 block kernel (developer tool).
 #include <cstdio>
 #include <vector>
+#include <cstring>
 #include <algorithm>
 #include "wdsr_tc5p.cuh"
 #include "tma_map.h"
@@ -17,6 +18,9 @@ int main() {
     CUtensorMap map; if (make_trunk_map(&map, din, N, H, W) != cudaSuccess) { printf("map failed\n"); return 1; }
     size_t smem = tc5v3::smem_bytes(M1P);
     cudaFuncSetAttribute(wdsr_block_tc5p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    unsigned *dbg_h = nullptr, *dbg_d = nullptr;
+    cudaHostAlloc(&dbg_h, 148 * 32 * 16, cudaHostAllocMapped); memset(dbg_h, 0, 148 * 32 * 16); cudaHostGetDevicePointer(&dbg_d, dbg_h, 0);
+    cudaMemcpyToSymbol(tc5::g_tc5_dbg, &dbg_d, sizeof dbg_d);
     for (int rep = 0; rep < 6; ++rep) {
         unsigned long long z[64] = {0};
         cudaMemcpyToSymbol(g_tc5p_prof, z, sizeof z);
@@ -25,6 +29,11 @@ int main() {
         wdsr_block_tc5p_kernel<<<148, tc5v3::NTHREADS, smem>>>(map, din, dout, dimg, M1P, N, H, W, tx, ty, ntiles);
         cudaEventRecord(b);
         cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            printf("FAILED: %s\n", cudaGetErrorString(e));
+            for (int i = 0; i < 148 * 32; ++i) if ((dbg_h[4 * i] >> 16) == 0xDEAD) printf("  cta %u warp %u timed out on barrier byte-offset %u (index %u) parity %u\n", dbg_h[4 * i + 3], dbg_h[4 * i] & 0xffff, dbg_h[4 * i + 1] & 0xff, (dbg_h[4 * i + 1] & 0xff) / 8, dbg_h[4 * i + 2]);
+            return 1;
+        }
         float ms; cudaEventElapsedTime(&ms, a, b);
         unsigned long long p[64]; cudaMemcpyFromSymbol(p, g_tc5p_prof, sizeof p);
         const int t = (ntiles - 1) / 148 + 1;
