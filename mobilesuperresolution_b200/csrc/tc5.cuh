@@ -57,6 +57,10 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---- register re-balancing between warpgroups (all 4 warps of an aligned warpgroup must execute it) ----------------------
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---- TMEM ---------------------------------------------------------------------------------------------------------
 // address = (lane << 16) | column.  One warp allocates / frees; a warp can only touch lanes 32*(warp%4) .. +31.
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_saddr, uint32_t ncols) {

@@ -1,18 +1,22 @@
 // wdsr_tc5p.cuh -- production form of the tcgen05 fused WDSR-B residual block (see wdsr_tc5.cuh for the algebra and the
 // sequential reference form that validated the descriptor / TMEM protocol).
 //
-//   warp 0      TMA producer   3 x cp.async.bulk.tensor.5d per tile (one per 8-channel plane) into a double-buffered,
-//                              chunk-planar trunk tile; out-of-image halo is zero-filled by the TMA unit
-//   warp 1      MMA issuer A   one elected lane issues the G1 / G2 stream (software-pipelined over M-tiles)
-//   warp 18     MMA issuer B   one elected lane issues the 3x3 (G3) stream; two issuers so that neither stream's barrier
-//                              wait blocks the other -- the tensor pipe interleaves them
-//   warps 2-5   WG-A   E1 (relu -> bf16 A operand), expand channels 0..63 of EVERY M-tile
-//   warps 6-9   WG-B   E1, expand channels 64..143 of every M-tile
+//   Six warpgroups (768 threads); EVERY warp has exactly one in-order work queue and only ever blocks on the one mbarrier it
+//   needs next (a failed probe of a pending mbarrier and a polling loop both cost hundreds of cycles of hand-off latency):
+//   WG0  warp 0   TMA producer   3 x cp.async.bulk.tensor.5d per tile (one per 8-channel plane) into a triple-buffered,
+//                                chunk-planar trunk tile; out-of-image halo is zero-filled by the TMA unit
+//        warp 1   MMA issuer A   one elected lane issues the G1 / G2 stream (software-pipelined over M-tiles)
+//        warp 2   MMA issuer B   one elected lane issues the 3x3 (G3) stream; two issuers so that neither stream's barrier
+//                                wait blocks the other -- the tensor pipe interleaves them
+//        warp 3   idle
+//   WG1  warps 4-7    E1 (relu -> bf16 A operand), expand channels 0..63 of EVERY M-tile
+//   WG2  warps 8-11   E1, expand channels 64..143 of every M-tile
 //               (E1 sits on the G1 -> G2 critical loop: two warpgroups split its columns and do nothing else;
-//                WG-A packs into columns 0..31 of D1, WG-B into columns 104..143 -- both in place inside their own half)
-//   warps 10-13 WG-C   E2 (t2 -> three shifted copies in shared memory) of even M-tiles  +  E3 (bias + residual + store) of 3x3 M-tiles 1,3
-//   warps 14-17 WG-D   E2 of odd M-tiles                                                  +  E3 of 3x3 M-tiles 0,2
-//               (per warp two in-order queues, E2 first: E2 feeds the 3x3 MMAs, E3 only drains results)
+//                WG1 packs into columns 0..31 of D1, WG2 into columns 104..143 -- both in place inside their own half)
+//   WG3  warps 12-15  E2 (t2 -> three shifted copies in shared memory) of even M-tiles
+//   WG4  warps 16-19  E2 of odd M-tiles
+//   WG5  warps 20-23  E3 (bias + residual + store) of every 3x3 M-tile -- the only warps with global stores in flight
+//   Registers are re-balanced with setmaxnreg: WG0 40, E1 104, E2 80, E3 72 per thread.
 // (a warp can only touch TMEM lanes 32*(warp%4)..+31, so every warpgroup is 4 consecutive warps.)
 //
 // Shared-memory operand layout (SWIZZLE_NONE, K-major): chunk-planar  XS[plane c][pixel p][16 B]  for the trunk tile
@@ -29,8 +33,8 @@
 #ifdef B200SR_TC5_PROF
 __device__ unsigned long long g_tc5p_prof[64];
 __device__ unsigned long long g_tc5p_cta[1024][3];
-__device__ unsigned long long g_tc5p_evt[20][2048];   // per warp: (id << 48) | clock
-__device__ int g_tc5p_evtn[20];
+__device__ unsigned long long g_tc5p_evt[24][2048];   // per warp: (id << 48) | clock
+__device__ int g_tc5p_evtn[24];
 __device__ __forceinline__ unsigned long long gtimer__() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned smid__() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 // timers accumulate in registers (prof__[slot & 7]); each warp's lane 0 of CTA 0 flushes them once at kernel end
@@ -52,7 +56,7 @@ __device__ __forceinline__ unsigned smid__() { unsigned r; asm volatile("mov.u32
 namespace b200sr {
 namespace tc5v3 {
 using namespace tc5cfg;
-constexpr int NTHREADS = 608;
+constexpr int NTHREADS = 768;
 constexpr int TMEM_COLS = 512;
 constexpr int XS_PLANE = NMT * 128 * 16;       // 10,240 B: 640 pixels x 16 B
 constexpr int XS_NBUF = 3;                    // TMA runs two tiles ahead of the MMA stream
@@ -67,6 +71,7 @@ __host__ __device__ constexpr int d3_col(int k) { return 352 + k * 32; }
 // MMAs needs is folded into ONE barrier:
 //   G2_READY[e] (384) = both column halves of E1 wrote A2 into D1[e]  +  E2 of the previous M-tile on this buffer drained D2[e]
 //   G3_READY[k] (384) = E2 of M-tiles k and k+1 wrote their t2 rows  +  E3 of the previous tile drained D3[k]
+// (arrivals are per thread: 32 lanes arriving in one instruction measured no slower than an elected lane after __syncwarp)
 enum Bar { XS_FULL = 0 /*3*/, XS_EMPTY = 3 /*3*/, D1_FULL = 6, G2_READY = 8, D2_FULL = 10, G3_READY = 12 /*4*/, T2R_FREE = 16 /*4*/,
            D3_FULL = 20 /*4*/, NBARS = 24 };
 constexpr int CTRL_BYTES = 256;  // 22 mbarriers (176 B) + tmem base pointer at byte 240
@@ -97,7 +102,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
     if (tid == 0) {
         for (int b = 0; b < XS_NBUF; ++b) {
             tc5::mbar_init(bar(XS_FULL + b), 1);
-            tc5::mbar_init(bar(XS_EMPTY + b), 257);  // commit after the last G1 + the 256 threads of WG-C/D after their E3
+            tc5::mbar_init(bar(XS_EMPTY + b), 129);  // commit after the last G1 + the 128 threads of WG5 after the tile's last E3
         }
         for (int e = 0; e < 2; ++e) {
             tc5::mbar_init(bar(D1_FULL + e), 1);
@@ -138,7 +143,11 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         n = tile / (tiles_x * tiles_y);
     };
 
-    if (warp == 0) {
+    const int wg = warp >> 2;  // warpgroup 0..5
+    // (each setmaxnreg sits at the top of the branch it governs, so that ptxas sees it dominate that role's code)
+    if (wg == 0) {
+      tc5::setmaxnreg_dec<40>();
+      if (warp == 0) {
         // ============================== TMA producer ==============================
         if (tc5::elect_one()) {
             for (int it = 0; it < nmine; ++it) {
@@ -153,7 +162,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         // ============================== MMA issuer ==============================
         const bool leader = tc5::elect_one();
         const uint32_t idesc1 = tc5::idesc_bf16_f32(128, M1P), idesc32 = tc5::idesc_bf16_f32(128, 32);
@@ -212,7 +221,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         }
         V3_ADD(5);
         if (nmine > 0) tc5::mbar_wait(bar(D2_FULL + 0), (n_g2[0] - 1) & 1);  // the last G2 (M-tile 4, buffer 0) and all before it retired
-    } else if (warp == 18) {
+      } else if (warp == 2) {
         // ============================== MMA issuer B: the 3x3 stream ==============================
         const bool leader = tc5::elect_one();
         const uint32_t idesc32 = tc5::idesc_bf16_f32(128, 32);
@@ -246,10 +255,10 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             for (int k = 0; k < 4; ++k) do_g3(it, k);
         V3_ADD(5);
         if (nmine > 0) tc5::mbar_wait(bar(T2R_FREE + 3), (nmine - 1) & 1);  // every G3 of this CTA has retired
+      }
     } else {
         // ============================== epilogue warpgroups ==============================
-        const int wg = (warp - 2) >> 2;          // 0 = A, 1 = B, 2 = C, 3 = D
-        const int e = wg & 1;                    // M-tile parity / buffer index this warpgroup serves
+        const int e = (wg - 3) & 1;              // WG3 / WG4: M-tile parity / buffer index this warpgroup serves
         const int row = (warp & 3) * 32 + lane;  // row of the M-tile == TMEM lane
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const float *b2s = reinterpret_cast<const float *>(wsm + L.b2);
@@ -263,7 +272,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             V3_T0();
             V3_EVT(300);
             const uint32_t d1 = tmem + lane_base + d1_col(eb);
-            if (wg == 0) {
+            if (wg == 1) {
                 uint32_t va[32], vb[32];
                 tc5::tmem_ld32(d1, va);
                 tc5::tmem_ld32(d1 + 32, vb);
@@ -395,58 +404,46 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             V3_EVT(410 + m);
         };
 
-        if (wg < 2) {
-            // WG-A / WG-B: their column half of E1 for every M-tile, in issue order.  M-tile i % 5 of tile i / 5 lives in buffer
+        if (wg <= 2) {
+            tc5::setmaxnreg_inc<104>();
+            // WG1 / WG2: their column half of E1 for every M-tile, in issue order.  M-tile i % 5 of tile i / 5 lives in buffer
             // (i % 5) & 1; a buffer completes 3 (even) or 2 (odd) G1s per tile.
             for (int i1 = 0; i1 < NMT * nmine; ++i1) {
                 const int mm = i1 % NMT, eb = mm & 1, nth = (i1 / NMT) * (eb == 0 ? 3 : 2) + (mm >> 1);
                 V3_WAIT(0, bar(D1_FULL + eb), nth & 1);
                 e1(eb);
             }
-        } else {
-            // WG-C / WG-D: E2 of M-tiles m = e, e+2, .. (first) and E3 of 3x3 M-tiles k = 1-e, 3-e.  Per warp, two in-order
-            // queues; warps of a warpgroup need not agree on the order (every hand-off counts thread arrivals).
-            tc5::mbar_arrive(bar(G2_READY + e));      // stand-in for "previous E2 drained D2[e]"
-            tc5::mbar_arrive(bar(G3_READY + 1 - e));  // stand-ins for "previous tile's E3 drained D3[k]"
-            tc5::mbar_arrive(bar(G3_READY + 3 - e));
-            const int per_tile = e == 0 ? 3 : 2, ne2 = per_tile * nmine, ne3 = 2 * nmine;
-            int i2 = 0, i3 = 0, ox2 = 0, oy2 = 0, on2 = 0, ox3 = 0, oy3 = 0, on3 = 0;
-            if (nmine > 0) {
-                tile_origin(0, ox2, oy2, on2);
-                ox3 = ox2, oy3 = oy2, on3 = on2;
+        } else if (wg <= 4) {
+            // WG3 / WG4: E2 of M-tiles m = e, e+2, ..
+            tc5::mbar_arrive(bar(G2_READY + e));  // stand-in for "previous E2 drained D2[e]"
+            uint32_t n_d2 = 0;
+            for (int it = 0; it < nmine; ++it) {
+                int x0, y0, n;
+                tile_origin(it, x0, y0, n);
+                for (int m = e; m < NMT; m += 2) {
+                    // t2 rows may be overwritten once the previous tile's 3x3 MMAs that READ them have retired.  M-tile m covers halo
+                    // rows ~3.8m .. 3.8m+3.8 and G3(k) reads halo rows 4k .. 4k+5, so the last reader is G3(min(m, 3)); commits retire
+                    // in order, hence D3_FULL[min(m,3)] of tile it-1 (its phase `it` cannot complete before this very E2 has run, so
+                    // the parity wait is unambiguous).
+                    if (it > 0) V3_WAIT(2, bar(D3_FULL + (m < 3 ? m : 3)), (it - 1) & 1);
+                    e2(m, n_d2 & 1, x0, y0);
+                    ++n_d2;
+                }
             }
-            while (i2 < ne2 || i3 < ne3) {
-                bool did = false;
-                if (i2 < ne2) {
-                    const int t = i2 / per_tile, j = i2 % per_tile, m = e + 2 * j;
-                    // ready = accumulator complete AND (first E2 of a tile) every 3x3 MMA of the previous tile has retired, so T2 may
-                    // be overwritten.  Never BLOCK on the latter here: that MMA may itself wait for an E3 still queued in this warp.
-                    bool rdy = __any_sync(0xffffffffu, tc5::mbar_test(bar(D2_FULL + e), i2 & 1));
-                    if (rdy && j == 0) rdy = __any_sync(0xffffffffu, tc5::mbar_test(bar(T2R_FREE + 3), (t & 1) ^ 1));
-                    if (rdy) {
-                        if (j == 0) tc5::mbar_wait(bar(T2R_FREE + 3), (t & 1) ^ 1);  // complete: per-lane acquire
-                        e2(m, i2 & 1, ox2, oy2);
-                        ++i2;
-                        if (j == per_tile - 1 && t + 1 < nmine) tile_origin(t + 1, ox2, oy2, on2);
-                        did = true;
-                    }
+        } else {
+            tc5::setmaxnreg_dec<72>();
+            // WG5: E3 of 3x3 M-tiles k = 0..3 of every tile
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc5::mbar_arrive(bar(G3_READY + k));  // stand-ins for "previous tile's E3 drained D3[k]"
+            for (int it = 0; it < nmine; ++it) {
+                int x0, y0, n;
+                tile_origin(it, x0, y0, n);
+                for (int k = 0; k < 4; ++k) {
+                    V3_WAIT(3, bar(D3_FULL + k), it & 1);
+                    if (k == 0) V3_WAIT(4, bar(XS_FULL + (it % XS_NBUF)), (it / XS_NBUF) & 1);  // acquire the TMA-written tile (residual)
+                    e3(it, k, x0, y0, n);
                 }
-                if (!did && i3 < ne3) {
-                    const int t = i3 >> 1, k = (1 - e) + 2 * (i3 & 1);
-                    const bool rdy = __any_sync(0xffffffffu, tc5::mbar_test(bar(D3_FULL + k), t & 1));
-                    if (rdy) {
-                        tc5::mbar_wait(bar(D3_FULL + k), t & 1);
-                        if ((i3 & 1) == 0) tc5::mbar_wait(bar(XS_FULL + (t % XS_NBUF)), (t / XS_NBUF) & 1);  // acquire the TMA-written tile
-                        e3(t, k, ox3, oy3, on3);
-                        if (i3 & 1) {
-                            tc5::mbar_arrive_relaxed(bar(XS_EMPTY + (t % XS_NBUF)));  // both E3 done: residual values were consumed
-                            if (t + 1 < nmine) tile_origin(t + 1, ox3, oy3, on3);
-                        }
-                        ++i3;
-                        did = true;
-                    }
-                }
-                if (!did) __nanosleep(40);
+                tc5::mbar_arrive_relaxed(bar(XS_EMPTY + (it % XS_NBUF)));  // all four E3 done: the residual values were consumed
             }
         }
     }
@@ -459,9 +456,10 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
     if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_tc5p_evtn[threadIdx.x >> 5] = evn__;
 #endif
     if (warp == 1) V3_FLUSH(0);
-    if (warp == 18) V3_FLUSH(40);
-    if (warp == 2) V3_FLUSH(8);
-    if (warp == 10) V3_FLUSH(24);
+    if (warp == 2) V3_FLUSH(40);
+    if (warp == 4) V3_FLUSH(8);
+    if (warp == 16) V3_FLUSH(24);
+    if (warp == 20) V3_FLUSH(32);
     tc5::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc5::tmem_free(tmem, tc5v3::TMEM_COLS);

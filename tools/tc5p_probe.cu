@@ -55,7 +55,7 @@ int main() {
         cudaMemcpyFromSymbol(ev, g_tc5p_evt, sizeof ev); cudaMemcpyFromSymbol(evn, g_tc5p_evtn, sizeof evn);
         struct E { unsigned long long t; int w, id; };
         std::vector<E> all;
-        const int ws[] = {1, 18, 2, 6, 10, 14};
+        const int ws[] = {1, 18, 2, 6, 10, 14, 19};
         for (int w : ws) for (int i = 0; i < evn[w]; ++i) all.push_back({ev[w][i] & 0xFFFFFFFFFFFFull, w, (int)(ev[w][i] >> 48)});
         std::sort(all.begin(), all.end(), [](const E &a, const E &b) { return a.t < b.t; });
         // print tiles 3..4 window: find the 4th occurrence of id 100 (G2 step m=0)
