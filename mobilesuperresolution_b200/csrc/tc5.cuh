@@ -57,6 +57,10 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---- programmatic dependent launch (no-ops when the grid was launched without the attribute) ------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- register re-balancing between warpgroups (all 4 warps of an aligned warpgroup must execute it) ----------------------
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }

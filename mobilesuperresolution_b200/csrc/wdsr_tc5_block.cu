@@ -50,8 +50,15 @@ cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8
         if (dev >= 0 && dev < 64) smem_set[dev] = smem;
     }
     const CUtensorMap &map = *mapp;
-    wdsr_block_tc5p_kernel<<<ctas, tc5v3::NTHREADS, smem, st>>>(map, (const bf16 *)in, (bf16 *)out, wimg, M1P, N, H, W, tx, ty, ntiles);
-    return cudaGetLastError();
+    // programmatic stream serialization: this grid may start (and run its prologue) while the previous kernel in the stream
+    // drains; the kernel orders its first trunk load behind griddepcontrol.wait
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas), cfg.blockDim = dim3(tc5v3::NTHREADS), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, wdsr_block_tc5p_kernel, map, (const bf16 *)in, (bf16 *)out, wimg, M1P, N, H, W, tx, ty, ntiles);
 }
 
 }  // namespace b200sr

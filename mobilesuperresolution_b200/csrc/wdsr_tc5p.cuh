@@ -98,7 +98,27 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
     if (threadIdx.x == 0) { g_tc5p_cta[blockIdx.x][0] = gtimer__(); g_tc5p_cta[blockIdx.x][2] = smid__(); }
 #endif
 
-    // ---- one-time setup
+    const int nmine = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    auto tile_origin = [&](int it, int &x0, int &y0, int &n) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        x0 = (tile % tiles_x) * TW - 1;
+        y0 = ((tile / tiles_x) % tiles_y) * TH - 1;
+        n = tile / (tiles_x * tiles_y);
+    };
+    auto tma_tile = [&](int it) {  // one lane: the three plane loads of tile iteration `it` into XS[it % XS_NBUF]
+        int x0, y0, n;
+        tile_origin(it, x0, y0, n);
+        const int xb = it % XS_NBUF;
+        tc5::mbar_arrive_expect_tx(bar(XS_FULL + xb), TMA_BYTES);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tc5::tma_load_5d(xs_u + xb * XS_BUF + c * XS_PLANE, &tmap_in, bar(XS_FULL + xb), 0, c, x0, y0, n);
+    };
+    const int npre = nmine < XS_NBUF ? nmine : XS_NBUF;  // tiles whose loads are issued from the prologue
+
+    // ---- one-time setup.  Launched with programmatic stream serialization: everything up to griddepcontrol.wait (barrier
+    //      init, TMEM allocation, the weight image -- a constant --, shared-memory constants) may overlap the previous block
+    //      kernel's tail; only the trunk loads (and, through them, every store) depend on it.
+    tc5::pdl_launch_dependents();
     if (tid == 0) {
         for (int b = 0; b < XS_NBUF; ++b) {
             tc5::mbar_init(bar(XS_FULL + b), 1);
@@ -116,15 +136,20 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         }
         tc5::mbar_init_fence();
         tc5::tma_prefetch_desc(&tmap_in);
+        tc5::pdl_wait();                                   // the previous kernel's trunk is complete and visible
+        for (int it = 0; it < npre; ++it) tma_tile(it);    // first loads in flight while the rest of the CTA sets up
     }
     __syncwarp();
     if (warp == 0) tc5::tmem_alloc(smem_u32(ctrl + 240), tc5v3::TMEM_COLS);
     for (int i = tid; i < L.total / 16; i += NTHREADS) cp_async16(wsm + i * 16, wimg + i * 16, 16);
     cp_async_commit();
-    for (int i = tid; i < XS_BYTES_ALL / 16; i += NTHREADS) {  // zero (pixel rows 612..639 stay zero); last plane = 1.0 in channels 0,1
-        const bool one = (i * 16) >= XS_ONE;
-        *reinterpret_cast<uint4 *>(xs + i * 16) = make_uint4(one ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+    // shared-memory constants; never touch bytes a TMA box lands on (pixel rows 0..611 of the tile planes): the loads are in flight
+    for (int i = tid; i < 3 * XS_NBUF * (NMT * 128 - HP); i += NTHREADS) {  // pad pixel rows 612..639 of every tile plane stay zero
+        const int pl = i / (NMT * 128 - HP), r = HP + i % (NMT * 128 - HP);
+        *reinterpret_cast<uint4 *>(xs + pl * XS_PLANE + r * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
+    for (int i = tid; i < XS_PLANE / 16; i += NTHREADS)                       // constant-one plane: 1.0 in channels 0,1
+        *reinterpret_cast<uint4 *>(xs + XS_ONE + i * 16) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
     for (int i = tid; i < 16; i += NTHREADS) *reinterpret_cast<uint4 *>(t2 + 3 * T2_COPY + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     cp_async_wait<0>();
     tc5::fence_proxy_async();
@@ -135,30 +160,21 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
 #ifdef B200SR_TC5_PROF
     prof__[6] = (unsigned long long)(clock64() - kstart__);
 #endif
-    const int nmine = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    auto tile_origin = [&](int it, int &x0, int &y0, int &n) {
-        const int tile = blockIdx.x + it * gridDim.x;
-        x0 = (tile % tiles_x) * TW - 1;
-        y0 = ((tile / tiles_x) % tiles_y) * TH - 1;
-        n = tile / (tiles_x * tiles_y);
-    };
 
     const int wg = warp >> 2;  // warpgroup 0..5
     // (each setmaxnreg sits at the top of the branch it governs, so that ptxas sees it dominate that role's code)
     if (wg == 0) {
+#ifdef B200SR_TC5_PROF
+      tc5::setmaxnreg_dec<56>();   // the probe counters need registers
+#else
       tc5::setmaxnreg_dec<40>();
+#endif
       if (warp == 0) {
         // ============================== TMA producer ==============================
-        if (tc5::elect_one()) {
-            for (int it = 0; it < nmine; ++it) {
-                int x0, y0, n;
-                tile_origin(it, x0, y0, n);
-                const int xb = it % XS_NBUF;
-                tc5::mbar_wait(bar(XS_EMPTY + xb), ((it / XS_NBUF) & 1) ^ 1);
-                tc5::mbar_arrive_expect_tx(bar(XS_FULL + xb), TMA_BYTES);
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    tc5::tma_load_5d(xs_u + xb * XS_BUF + c * XS_PLANE, &tmap_in, bar(XS_FULL + xb), 0, c, x0, y0, n);
+        if (lane == 0) {   // (the lane that issued the prologue loads)
+            for (int it = npre; it < nmine; ++it) {
+                tc5::mbar_wait(bar(XS_EMPTY + it % XS_NBUF), ((it / XS_NBUF) & 1) ^ 1);
+                tma_tile(it);
             }
         }
         __syncwarp();
@@ -205,8 +221,13 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                     const uint32_t d2 = tmem + d2_col(e), a2 = tmem + d1_col(e);
                     // A2 columns: k-steps 0..3 at columns 8j (written by WG-A), k-steps 4.. at 104 + 8(j-4) (WG-B); see e1()
                     tc5::mma_ts(d2, a2, bw2, idesc32, false);
+#ifdef B200SR_EXP_G2SHORT
+                    const int nk2x = 2;      // (timing experiment: results are wrong)
+#else
+                    const int nk2x = nk2;
+#endif
 #pragma unroll 4
-                    for (int j = 1; j < nk2; ++j) tc5::mma_ts(d2, a2 + (j < 4 ? 8 * j : a2hi + 8 * (j - 4)), bw2 + (uint64_t)(16 * j), idesc32, true);
+                    for (int j = 1; j < nk2x; ++j) tc5::mma_ts(d2, a2 + (j < 4 ? 8 * j : a2hi + 8 * (j - 4)), bw2 + (uint64_t)(16 * j), idesc32, true);
                     tc5::commit(bar(D2_FULL + e));
                     if (m + 2 < NMT) {
                         issue_g1(xb, m + 2);
@@ -230,8 +251,13 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         auto issue_g3 = [&](int k) {  // leader only
             const uint64_t abase = at0 + (uint64_t)((k * 4 * T2_ROW) >> 4);
             const uint32_t d3 = tmem + d3_col(k);
+#ifdef B200SR_EXP_G3SHORT
+            constexpr int NG3 = 2;   // (timing experiment: results are wrong)
+#else
+            constexpr int NG3 = 14;
+#endif
 #pragma unroll
-            for (int i = 0; i < 14; ++i) {
+            for (int i = 0; i < NG3; ++i) {
                 const int q0 = 2 * i, q1 = 2 * i + 1;
                 const int a0 = (q0 / 9) * T2_COPY + ((q0 / 3) % 3) * T2_ROW + (q0 % 3) * 128;
                 const int a1 = q1 < 27 ? (q1 / 9) * T2_COPY + ((q1 / 3) % 3) * T2_ROW + (q1 % 3) * 128 : a0 + 128;
@@ -272,6 +298,9 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             V3_T0();
             V3_EVT(300);
             const uint32_t d1 = tmem + lane_base + d1_col(eb);
+#ifdef B200SR_EXP_E1SHORT
+            if (true) { uint32_t v8[8]; tc5::tmem_ld8(d1, v8); tc5::tmem_wait_ld(); if (v8[0] == 0x7fc12345u) tc5::tmem_st8(d1, v8); } else   // (timing experiment)
+#endif
             if (wg == 1) {
                 uint32_t va[32], vb[32];
                 tc5::tmem_ld32(d1, va);
@@ -338,7 +367,11 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             tc5::fence_before_sync();
             tc5::mbar_arrive_relaxed(bar(G3_READY + k));
             V3_EVT(540 + k);  // D3[k] drained (wait::ld): counts towards the next tile's G3(k)
+#ifdef B200SR_EXP_NOSTORE
+            if (gy < H && gx < W && v[0] == 0x7fc12345u) {   // (timing experiment)
+#else
             if (gy < H && gx < W) {
+#endif
                 bf16 *o = out + (((long long)n * H + gy) * W + gx) * 24;
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {

@@ -44,18 +44,19 @@ int main() {
           double sumdur = 0, maxstart = 0, mindur = 1e18, maxdur = 0; for (int i = 0; i < 148; ++i) { double d = (double)(c[i][1] - c[i][0]); sumdur += d; if (d < mindur) mindur = d; if (d > maxdur) maxdur = d; double st = (double)(c[i][0] - t0); if (st > maxstart) maxstart = st; }
           printf("   CTAs: first start -> last end %.1f us; CTA duration min %.1f avg %.1f max %.1f us; latest CTA start +%.1f us; sm of cta0,1,147: %llu %llu %llu\n", (t1 - t0) * 1e-3, mindur * 1e-3, sumdur / 148 * 1e-3, maxdur * 1e-3, maxstart * 1e-3, c[0][2], c[1][2], c[147][2]); }
         printf("   MMA-B (G3) per tile: loop %llu | wait G3_READY %llu\n", p[45] / t, p[43] / t);
-        for (int w = 0; w < 2; ++w) { // w=0: warp 2 (WG-A, E1), w=1: warp 14 (WG-D, E2+E3)
+        for (int w = 0; w < 2; ++w) { // w=0: warp 4 (WG1, E1), w=1: warp 16 (WG4, E2 odd)
             const unsigned long long *q = p + 8 + 16 * w;
             printf("   warp%d per tile: waits D1_FULL %llu D2_FULL %llu T2R_FREE %llu D3_FULL %llu XS_FULL %llu | work E1 %llu E2 %llu E3 %llu\n", w,
                    q[0] / t, q[1] / t, q[2] / t, q[3] / t, q[4] / t, q[5] / t, q[6] / t, q[7] / t);
         }
+        { const unsigned long long *q = p + 32; printf("   E3 warp per tile: waits D3_FULL %llu XS_FULL %llu | work E3 %llu\n", q[3] / t, q[4] / t, q[7] / t); }
     }
-    {   // timeline of CTA 0 (last rep): events of warps 1 (MMA-A), 18 (MMA-B), 2 (WG-A), 6 (WG-B), 10 (WG-C), 14 (WG-D)
-        static unsigned long long ev[20][2048]; int evn[20];
+    {   // timeline of CTA 0 (last rep): events of warps 1 (MMA-A), 2 (MMA-B), 4 (WG1 E1 lo), 8 (WG2 E1 hi), 12 (WG3 E2 even), 16 (WG4 E2 odd), 20 (WG5 E3)
+        static unsigned long long ev[24][2048]; int evn[24];
         cudaMemcpyFromSymbol(ev, g_tc5p_evt, sizeof ev); cudaMemcpyFromSymbol(evn, g_tc5p_evtn, sizeof evn);
         struct E { unsigned long long t; int w, id; };
         std::vector<E> all;
-        const int ws[] = {1, 18, 2, 6, 10, 14, 19};
+        const int ws[] = {1, 2, 4, 8, 12, 16, 20};
         for (int w : ws) for (int i = 0; i < evn[w]; ++i) all.push_back({ev[w][i] & 0xFFFFFFFFFFFFull, w, (int)(ev[w][i] >> 48)});
         std::sort(all.begin(), all.end(), [](const E &a, const E &b) { return a.t < b.t; });
         // print tiles 3..4 window: find the 4th occurrence of id 100 (G2 step m=0)

@@ -25,7 +25,19 @@ int main(int argc, char **argv) {
     for (int rep = 0; rep < 12; ++rep) {
         cudaEventRecord(a);
         for (int l = 0; l < 16; ++l)
+        {
+#ifdef NO_PDL
             wdsr_block_tc5p_kernel<<<ctas, tc5v3::NTHREADS, smem>>>(map[l & 1], buf[l & 1], buf[(l & 1) ^ 1], dimg, M1P, N, H, W, tx, ty, ntiles);
+#else
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(ctas), cfg.blockDim = dim3(tc5v3::NTHREADS), cfg.dynamicSmemBytes = smem, cfg.stream = 0;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr, cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, wdsr_block_tc5p_kernel, map[l & 1], (const bf16 *)buf[l & 1], buf[(l & 1) ^ 1], (const uint8_t *)dimg, M1P, N, H, W, tx, ty, ntiles);
+#endif
+        }
         cudaEventRecord(b);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("FAILED: %s\n", cudaGetErrorString(e)); return 1; }
