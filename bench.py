@@ -32,6 +32,9 @@ SCALE, NB, NRU = 4, 16, 24
 BATCH, LR = 64, 96
 FLOP_PER_LR_PX_BLOCK = 2 * (24 * 144 + 144 * 20 + 9 * 20 * 24)      # 21,312
 BYTES_PER_LR_PX_BLOCK = 2 * 24 * 2                                    # read + write the bf16 trunk once = 96
+# measured DRAM bytes of ONE block launch at this workload (ncu --set full, profiles/r01_block_tcgen05_v2_ncu.md):
+# 28,396,288 read + 38,400 written -- the output stays in L2 for the next block
+NCU_DRAM_BYTES_PER_BLOCK_LAUNCH = 28_396_288 + 38_400
 WORKLOAD = "cfg2: WDSR-B x4 nb16 nru24 (reference seeded init), batch 64 x 3x96x96 LR -> 3x384x384, bf16"
 
 
@@ -228,9 +231,9 @@ def run_b200(args, rank, local_rank, world):
     lr_px = BATCH * LR * LR
     ach_tflops = lr_px * FLOP_PER_LR_PX_BLOCK / (blk_ms * 1e-3) / 1e12
     ach_gbs = lr_px * BYTES_PER_LR_PX_BLOCK / (blk_ms * 1e-3) / 1e9
-    roofline = {"kernel": "wdsr_block_bf16_kernel<24,24,32,16,8>", "bound": "tensor", "achieved": ach_tflops,
+    roofline = {"kernel": "wdsr_block_tc5p_kernel (tcgen05 fused residual block)", "bound": "tensor", "achieved": ach_tflops,
                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach_tflops / peaks["bf16_tflops_sustained"],
-                "traffic": None, "peak_source": peaks["source"] + " (sustained bf16 GEMM; kernel timed inside a 16-launch loop)",
+                "traffic": NCU_DRAM_BYTES_PER_BLOCK_LAUNCH, "traffic_source": "profiles/r01_block_tcgen05_v2_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)", "peak_source": peaks["source"] + " (sustained bf16 GEMM; kernel timed inside a 16-launch loop)",
                 "us_per_launch": blk_ms * 1e3, "algorithmic_flop_per_launch": lr_px * FLOP_PER_LR_PX_BLOCK,
                 "algorithmic_bytes_per_launch": lr_px * BYTES_PER_LR_PX_BLOCK,
                 "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"]},
