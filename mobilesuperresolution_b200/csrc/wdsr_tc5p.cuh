@@ -16,7 +16,8 @@
 //   WG3  warps 12-15  E2 (t2 -> three shifted copies in shared memory) of even M-tiles
 //   WG4  warps 16-19  E2 of odd M-tiles
 //   WG5  warps 20-23  E3 (bias + residual + store) of every 3x3 M-tile -- the only warps with global stores in flight
-//   Registers are re-balanced with setmaxnreg: WG0 40, E1 104, E2 80, E3 72 per thread.
+//   Registers are re-balanced with setmaxnreg: WG0 40, E1 104, E2 80, E3 72 per thread; the budgets x 128 threads must sum to at
+//   most the 80 x 768 registers the CTA is launched with, or setmaxnreg.inc waits forever.
 // (a warp can only touch TMEM lanes 32*(warp%4)..+31, so every warpgroup is 4 consecutive warps.)
 //
 // Shared-memory operand layout (SWIZZLE_NONE, K-major): chunk-planar  XS[plane c][pixel p][16 B]  for the trunk tile
@@ -165,7 +166,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
     // (each setmaxnreg sits at the top of the branch it governs, so that ptxas sees it dominate that role's code)
     if (wg == 0) {
 #ifdef B200SR_TC5_PROF
-      tc5::setmaxnreg_dec<56>();   // the probe counters need registers
+      tc5::setmaxnreg_dec<56>();   // the probe counters need registers; paid for by the E2 warpgroups (see below)
 #else
       tc5::setmaxnreg_dec<40>();
 #endif
@@ -447,6 +448,9 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                 e1(eb);
             }
         } else if (wg <= 4) {
+#ifdef B200SR_TC5_PROF
+            tc5::setmaxnreg_dec<72>();   // keep the sum of the warpgroup budgets at the 80 x 768 the CTA was launched with
+#endif
             // WG3 / WG4: E2 of M-tiles m = e, e+2, ..
             tc5::mbar_arrive(bar(G2_READY + e));  // stand-in for "previous E2 drained D2[e]"
             uint32_t n_d2 = 0;
