@@ -257,3 +257,52 @@ def test_cfg5_1080p_x2_crops(G):
         ref = ref[:, :, 2 * (y0 - ya):2 * (y0 - ya + hh), 2 * (x0 - xa):2 * (x0 - xa + ww)]
         assert G.maxabs(yf[n:n + 1, :, 2 * y0:2 * (y0 + hh), 2 * x0:2 * (x0 + ww)], ref) <= FP32_TOL
         assert G.psnr(yb[n:n + 1, :, 2 * y0:2 * (y0 + hh), 2 * x0:2 * (x0 + ww)], ref, peak=1.0) >= BF16_PSNR
+
+
+# ---------------------------------------------------------------- stream / graph behaviour ---------------
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_cuda_graph_capture_and_determinism(G, precision):
+    """The forward must be CUDA-graph capturable on a side stream (the reference's callers own the stream) and
+    bit-reproducible: the block kernels are launched with programmatic stream serialization, so consecutive launches overlap
+    their prologues -- replaying the graph must still give exactly the eager result, every time."""
+    torch.manual_seed(3)
+    m = G.sr.BASIC_MODEL(G.params(4, 4)).eval().to(G.DEV).set_precision(precision)
+    x = torch.rand(3, 3, 70, 90, device=G.DEV)
+    if precision == "bf16":
+        x = x.bfloat16()
+    with torch.no_grad():
+        ref = m(x).clone()
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            for _ in range(2):
+                y = m(x)
+            st.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                y = m(x)
+            outs = []
+            for _ in range(3):
+                y.zero_()
+                g.replay()
+                st.synchronize()
+                outs.append(y.clone())
+    for o in outs:
+        assert torch.equal(o, ref)
+
+
+def test_back_to_back_forwards_do_not_race(G):
+    """Two different inputs through the same plan and workspace, queued back to back without a host sync: the second forward's
+    first block kernel may start its prologue while the first forward's tail still runs, but must not touch the trunk early."""
+    torch.manual_seed(4)
+    m = G.sr.BASIC_MODEL(G.params(4, 3)).eval().to(G.DEV).set_precision("bf16")
+    xa = torch.rand(8, 3, 96, 96, device=G.DEV).bfloat16()
+    xb = torch.rand(8, 3, 96, 96, device=G.DEV).bfloat16()
+    with torch.no_grad():
+        ra, rb = m(xa).clone(), m(xb).clone()
+        torch.cuda.synchronize()
+        for _ in range(5):
+            ya = m(xa)
+            yb = m(xb)
+            torch.cuda.synchronize()
+            assert torch.equal(ya, ra) and torch.equal(yb, rb)
