@@ -122,10 +122,6 @@ int b200sr_wdsr_create(const b200sr_wdsr_desc *d, b200sr_wdsr_t **out) {
     b200sr_wdsr *p = new (std::nothrow) b200sr_wdsr();
     if (!p) return fail(B200SR_E_INVAL, "wdsr_create: out of memory");
     p->scale = d->scale, p->nb = d->num_blocks, p->cin = d->c_trunk, p->cp = round_up(d->c_trunk, 8);
-    {   // developer switch: pad every trunk to 24 channels so pruned nets also take the tcgen05 kernels
-        const char *e = getenv("B200SR_TRUNK_PAD24");
-        if (e && e[0] == '1') p->cp = 24;
-    }
     p->add_mean = d->add_mean, p->mean = d->image_mean, p->no = 3 * d->scale * d->scale;
     for (int i = 0; i < p->nb; ++i) {
         const int m1 = d->m1[i], m2 = d->m2[i];
@@ -137,6 +133,16 @@ int b200sr_wdsr_create(const b200sr_wdsr_desc *d, b200sr_wdsr_t **out) {
         p->m1p.push_back(round_up(m1, 16));
         p->m2p_f32.push_back(round_up(m2, 4) < 8 ? 8 : round_up(m2, 4));
         p->m2p_bf16.push_back(round_up(m2, 8));
+    }
+    {
+        // Pruned trunks (IN < 24) are padded to 24 channels whenever every block then fits the tcgen05 kernels (M1 <= 144):
+        // the padded channels are exact zeros and cost HBM bytes, but the tcgen05 head / block / tail beat the mma.sync
+        // specialisations by 1.2-1.5x even so (cfg3 P1 360p x 8: 1176 -> 791 us, P2: 164 -> 115 us per frame on B200).
+        // B200SR_TRUNK_PAD24=0 keeps the narrow trunk (developer switch, A/B timing).
+        bool fits = true;
+        for (int m1 : p->m1) fits = fits && round_up(m1, 16) <= 144;
+        const char *e = getenv("B200SR_TRUNK_PAD24");
+        if (fits && !(e && e[0] == '0')) p->cp = 24;
     }
     p->blocks.resize(p->nb);
     *out = p;
@@ -250,7 +256,7 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
             if ((rc = upload(img.data(), img.size(), (void **)&d))) return rc;
             p->d_blk_bf16.push_back(d);
         }
-        if (CP == 24 && M2 <= 24) {   // tcgen05 operand image (interleaved K-major core matrices, see wdsr_tc5.cuh)
+        if (CP == 24 && M2 <= 24 && M1P <= 144) {   // tcgen05 operand image (TMEM holds two 144-column expand accumulators) (interleaved K-major core matrices, see wdsr_tc5.cuh)
             BlockTc5Layout L(M1P);
             std::vector<uint8_t> img((size_t)L.total, 0);
             auto at = [&](int off) { return (uint16_t *)(img.data() + off); };

@@ -30,8 +30,10 @@ cases = [("cfg1 x4 1x64x64 fp32", sr.BASIC_MODEL(P(4, 16)), (1, 3, 64, 64), "fp3
          ("cfg1 x4 1x64x64 bf16", sr.BASIC_MODEL(P(4, 16)), (1, 3, 64, 64), "bf16"),
          ("cfg2 x4 64x96x96 bf16", sr.BASIC_MODEL(P(4, 16)), (64, 3, 96, 96), "bf16"),
          ("dense x4 360p bf16", sr.BASIC_MODEL(P(4, 16)), (1, 3, 360, 640), "bf16"),
+         ("dense x4 360p bf16 B=8", sr.BASIC_MODEL(P(4, 16)), (8, 3, 360, 640), "bf16"),
          ("dense x4 360p fp32", sr.BASIC_MODEL(P(4, 16)), (1, 3, 360, 640), "fp32"),
          ("cfg3 P1 x4 360p bf16", pruned(4, P1), (1, 3, 360, 640), "bf16"),
+         ("cfg3 P1 x4 360p bf16 B=8", pruned(4, P1), (8, 3, 360, 640), "bf16"),
          ("cfg3 P2 x4 360p bf16", pruned(4, P2), (1, 3, 360, 640), "bf16"),
          ("cfg5 x2 1080p bf16 B=1", sr.BASIC_MODEL(P(2, 16)), (1, 3, 1080, 1920), "bf16"),
          ("cfg5 x2 1080p bf16 B=4", sr.BASIC_MODEL(P(2, 16)), (4, 3, 1080, 1920), "bf16")]
