@@ -27,6 +27,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc5.cuh"
 #include "wdsr_tc5_layout.cuh"
@@ -314,8 +316,36 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                 tc5::tmem_st16(d1, *reinterpret_cast<uint32_t(*)[16]>(&va[0]));
                 tc5::tmem_st16(d1 + 16, *reinterpret_cast<uint32_t(*)[16]>(&va[16]));
             } else {
-                const int nhi = M1P - 64, dst = M1P - nhi / 2;   // 80 columns -> 40 packed columns at [104, 144)
-                if (M1P == 144) {
+                // columns 64 .. M1P-1 (nhi = 0, 16, .. 80 of them) -> nhi/2 packed columns at the top of D1: [M1P - nhi/2, M1P).
+                // All loads are issued before the one wait; the shape is a compile-time parameter of the body so that the register
+                // arrays stay in registers (pruned widths used to take a 16-columns-at-a-time loop).
+                const int nhi = M1P - 64, dst = M1P - nhi / 2;
+                auto hi = [&](auto n32c, auto r16c) {
+                    constexpr int N32 = decltype(n32c)::value;
+                    constexpr bool R16 = decltype(r16c)::value != 0;
+                    uint32_t va[32], vb[32], vc[16];
+                    if constexpr (N32 >= 1) tc5::tmem_ld32(d1 + 64, va);
+                    if constexpr (N32 >= 2) tc5::tmem_ld32(d1 + 96, vb);
+                    if constexpr (R16) tc5::tmem_ld16(d1 + 64 + 32 * N32, vc);
+                    tc5::tmem_wait_ld();
+                    if constexpr (N32 >= 1) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) va[j] = tc5::relu_pack_bf16x2(va[2 * j], va[2 * j + 1]);
+                        tc5::tmem_st16(d1 + dst, *reinterpret_cast<uint32_t(*)[16]>(&va[0]));
+                    }
+                    if constexpr (N32 >= 2) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) vb[j] = tc5::relu_pack_bf16x2(vb[2 * j], vb[2 * j + 1]);
+                        tc5::tmem_st16(d1 + dst + 16, *reinterpret_cast<uint32_t(*)[16]>(&vb[0]));
+                    }
+                    if constexpr (R16) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) vc[j] = tc5::relu_pack_bf16x2(vc[2 * j], vc[2 * j + 1]);
+                        tc5::tmem_st8(d1 + dst + 16 * N32, *reinterpret_cast<uint32_t(*)[8]>(&vc[0]));
+                    }
+                };
+                using std::integral_constant;
+                if (M1P == 144) {   // the dense width: kept as straight-line code in front of the dispatch
                     uint32_t va[32], vb[32], vc[16];
                     tc5::tmem_ld32(d1 + 64, va);
                     tc5::tmem_ld32(d1 + 96, vb);
@@ -330,16 +360,13 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                     tc5::tmem_st16(d1 + dst, *reinterpret_cast<uint32_t(*)[16]>(&va[0]));
                     tc5::tmem_st16(d1 + dst + 16, *reinterpret_cast<uint32_t(*)[16]>(&va[16]));
                     tc5::tmem_st8(d1 + dst + 32, *reinterpret_cast<uint32_t(*)[8]>(&vc[0]));
-                } else {
-                    // generic width: 16 columns at a time, top-down so that a packed write never lands on unread columns
-                    for (int k = nhi - 16; k >= 0; k -= 16) {
-                        uint32_t v[16], pk[8];
-                        tc5::tmem_ld16(d1 + 64 + k, v);
-                        tc5::tmem_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) pk[j] = tc5::relu_pack_bf16x2(v[2 * j], v[2 * j + 1]);
-                        tc5::tmem_st8(d1 + dst + k / 2, pk);
-                    }
+                } else switch (nhi) {
+                    case 80: hi(integral_constant<int, 2>{}, integral_constant<int, 1>{}); break;
+                    case 64: hi(integral_constant<int, 2>{}, integral_constant<int, 0>{}); break;
+                    case 48: hi(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
+                    case 32: hi(integral_constant<int, 1>{}, integral_constant<int, 0>{}); break;
+                    case 16: hi(integral_constant<int, 0>{}, integral_constant<int, 1>{}); break;
+                    default: break;   // M1P <= 64: nothing in the upper half
                 }
             }
             tc5::tmem_wait_st();
