@@ -40,7 +40,7 @@ def _compile(src: str, force: bool, hdr_mtime: float, verbose: bool) -> str:
     s = os.path.join(CSRC, src)
     if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(s), hdr_mtime):
         return obj
-    cmd = [NVCC, *ARCH, *FLAGS, "-c", s, "-o", obj]
+    cmd = [NVCC, *ARCH, *FLAGS, *os.environ.get("B200SR_NVCC_EXTRA", "").split(), "-c", s, "-o", obj]   # developer -D switches (timing experiments)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -73,7 +73,7 @@ static cudaError_t head_tc5_t(const void *x, void *trunk, const uint8_t *wimg, i
         set = true;
     }
     const int tx = ceil_div(W, TW), ty = ceil_div(H, TH), ntiles = tx * ty * N;
-    int ctas = 2 * sm_count();
+    int ctas = CTAS_PER_SM * sm_count();
     if (ctas > ntiles) ctas = ntiles;
     kern<<<ctas, NTHREADS, smem, st>>>((const TIN *)x, (bf16 *)trunk, wimg, N, H, W, tx, ty, ntiles, mean);
     return cudaGetLastError();
