@@ -207,10 +207,10 @@ def run_b200(args, rank, local_rank, world):
     value = world * out_mpix_step / (ms_per_step / 1e3)
 
     # ---- dominant kernel (fused residual block) timed alone with events: 16 launches per step on real trunk data
-    trunk = plan.head(x_dev, "bf16")
+    trunk = plan.head_internal(x_dev, "bf16")   # the kernels' own trunk layout (planar-8 on the tcgen05 path)
     tb = torch.empty_like(trunk)
     for _ in range(3):
-        plan.block(0, trunk, "bf16")
+        plan.block_internal(0, trunk, "bf16", out=tb)
     torch.cuda.synchronize()
     kev = []
     for _ in range(min(K, 20)):

@@ -107,9 +107,14 @@ B200SR_API int b200sr_wdsr_forward_host(const b200sr_wdsr_t *plan, const void *x
                              int n, int h, int w, int precision, void *x_stage_dev, void *y_stage_dev,
                              void *workspace_dev, size_t workspace_bytes, void *stream);
 
-/* Stage-level entry points (parity tests).  Trunk tensors are NHWC with b200sr_wdsr_trunk_channels()
- * channels (IN padded up to a multiple of 8; padding channels are zero), element type = precision. */
+/* Stage-level entry points (parity tests).  Trunk tensors have b200sr_wdsr_trunk_channels() channels (IN padded up to a
+ * multiple of 8, or to 24 where that lets a pruned net take the tcgen05 kernels; padding channels are zero), element type =
+ * precision, in the layout b200sr_wdsr_trunk_layout() reports for that precision: NHWC, or -- on the bf16 tcgen05 path --
+ * planar-8, [n][channels/8][h][w][8].  The layout is internal to the forward; only these three calls expose it. */
+#define B200SR_TRUNK_NHWC 0
+#define B200SR_TRUNK_PLANAR8 1
 B200SR_API int b200sr_wdsr_trunk_channels(const b200sr_wdsr_t *plan);
+B200SR_API int b200sr_wdsr_trunk_layout(const b200sr_wdsr_t *plan, int precision);
 B200SR_API int b200sr_wdsr_head(const b200sr_wdsr_t *plan, const void *x_dev, int x_dtype, void *trunk_dev, int n, int h, int w,
                      int precision, void *stream);
 B200SR_API int b200sr_wdsr_block(const b200sr_wdsr_t *plan, int block, const void *trunk_in_dev, void *trunk_out_dev, int n,

@@ -41,6 +41,7 @@ SYMBOLS = {
     "b200sr_wdsr_forward_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                          c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200sr_wdsr_trunk_channels": (c_int, [c_void_p]),
+    "b200sr_wdsr_trunk_layout": (c_int, [c_void_p, c_int]),
     "b200sr_wdsr_head": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_wdsr_block": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_wdsr_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -84,6 +84,14 @@ struct b200sr_wdsr {
     uint8_t *d_head_tc5 = nullptr;   // tcgen05 head image (trunk padded to 24 channels)
     uint8_t *d_tail_tc5 = nullptr;   // tcgen05 tail image (nullptr unless the trunk is padded to 24 channels)
     int tail_impl = 1;               // 0 = mma.sync kernel, 1 = tcgen05 kernel
+    // The bf16 forward is one of two uniform paths: head/block/tail all tcgen05 on a planar-8 trunk [N][3][H][W][8] (tma_map.h), or
+    // all mma.sync (+ the sequential tcgen05 reference block) on an NHWC trunk.  Never a mixture: the kernels disagree on the layout.
+    bool tc5_path() const {
+        if (cp != 24 || block_impl != 2 || !tail_impl || !d_head_tc5 || !d_tail_tc5) return false;
+        for (auto b : d_blk_tc5)
+            if (!b) return false;
+        return true;
+    }
     mutable int launches = 0;
 
     void free_device() {
@@ -370,6 +378,9 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
 }
 
 int b200sr_wdsr_trunk_channels(const b200sr_wdsr_t *p) { return p ? p->cp : 0; }
+int b200sr_wdsr_trunk_layout(const b200sr_wdsr_t *p, int precision) {
+    return p && precision == B200SR_BF16 && p->tc5_path() ? B200SR_TRUNK_PLANAR8 : B200SR_TRUNK_NHWC;
+}
 int b200sr_wdsr_launches_per_forward(const b200sr_wdsr_t *p) { return p ? p->launches : 0; }
 
 size_t b200sr_wdsr_workspace_bytes(const b200sr_wdsr_t *p, int n, int h, int w, int precision) {
@@ -392,7 +403,7 @@ int b200sr_wdsr_head(const b200sr_wdsr_t *p, const void *x, int x_dtype, void *t
     int rc = check_common(p, n, h, w, precision, "wdsr_head");
     if (rc) return rc;
     if (!x || !trunk) return fail(B200SR_E_INVAL, "wdsr_head: null tensor");
-    if (precision == B200SR_BF16 && p->tail_impl && p->d_head_tc5)
+    if (precision == B200SR_BF16 && p->tc5_path())
         CU(launch_head_tc5(x_dtype, x, trunk, p->d_head_tc5, n, h, w, p->mean, (cudaStream_t)stream));
     else
         CU(launch_head(p->cp, x_dtype, precision, x, trunk, p->d_head, n, h, w, p->mean, (cudaStream_t)stream));
@@ -408,8 +419,10 @@ int b200sr_wdsr_block(const b200sr_wdsr_t *p, int i, const void *tin, void *tout
     if (precision == B200SR_F32)
         CU(launch_block_f32(p->cp, p->m2p_f32[i], (const float *)tin, (float *)tout, p->d_blk_f32[i], p->m1p[i], n, h, w,
                             (cudaStream_t)stream));
-    else if (p->block_impl && p->d_blk_tc5[i])
-        CU(launch_block_tc5(p->block_impl - 1, tin, tout, p->d_blk_tc5[i], p->m1p[i], n, h, w, (cudaStream_t)stream));
+    else if (p->tc5_path())
+        CU(launch_block_tc5(1, tin, tout, p->d_blk_tc5[i], p->m1p[i], n, h, w, (cudaStream_t)stream));
+    else if (p->block_impl == 1 && p->d_blk_tc5[i])   // sequential tcgen05 reference form (NHWC trunk; developer switch)
+        CU(launch_block_tc5(0, tin, tout, p->d_blk_tc5[i], p->m1p[i], n, h, w, (cudaStream_t)stream));
     else
         CU(launch_block_bf16(p->cp, p->m2p_bf16[i], tin, tout, p->d_blk_bf16[i], p->m1p[i], n, h, w, (cudaStream_t)stream));
     return 0;
@@ -424,7 +437,7 @@ int b200sr_wdsr_tail(const b200sr_wdsr_t *p, const void *trunk, const void *x, i
     if (precision == B200SR_F32)
         CU(launch_tail_f32(p->cp, p->scale, x_dtype, y_dtype, (const float *)trunk, x, y, p->d_tail_f32, n, h, w, p->mean,
                            out_add, (cudaStream_t)stream));
-    else if (p->tail_impl && p->d_tail_tc5)
+    else if (p->tc5_path())
         CU(launch_tail_tc5(p->scale, x_dtype, y_dtype, trunk, x, y, p->d_tail_tc5, n, h, w, p->mean, out_add, (cudaStream_t)stream));
     else
         CU(launch_tail_bf16(p->cp, p->scale, x_dtype, y_dtype, trunk, x, y, p->d_tail_bf16, n, h, w, p->mean, out_add,

@@ -127,6 +127,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst_saddr, const void *tmap
         ::"r"(dst_saddr), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+// one 8-channel plane box of the planar-8 trunk (tma_map.h): coordinates in pixels / rows / plane / image
+__device__ __forceinline__ void tma_load_plane(uint32_t dst_saddr, const void *tmap, uint32_t bar, int x, int y, int plane, int n) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst_saddr), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(4 * x), "r"(y), "r"(plane), "r"(n)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }

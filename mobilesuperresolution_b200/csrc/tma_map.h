@@ -26,16 +26,19 @@ static EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// 5-D view of the NHWC bf16 trunk [N][H][W][24] as (8 ch, 3 chunks, W, H, N): a box {8, 1, 34, 18, 1} is one 8-channel
-// plane of a tile + halo and lands contiguously ([row][px][16 B]) in shared memory; out-of-image elements read as zero.
+// The tcgen05 path keeps the bf16 trunk in the planar-8 layout [N][3 planes][H][W][8 channels] ("NC/8HW8"): one 8-channel plane
+// of a tile + halo is then box_h rows of box_w * 16 CONTIGUOUS bytes.  The tensor map views it as 4-D (4*W uint32, H, 3, N); a box
+// {4 * box_w, box_h, 1, 1} lands as [row][px][16 B] in shared memory, out-of-image elements read as zero.
+// (The first form used the NHWC trunk through a 5-D map with an 8-element inner box: the same shared-memory image, but every
+//  16-byte pixel row was its own TMA request -- 1,836 per block tile, 2,880 per tail tile -- and the tail kernel was bound by it.)
 static cudaError_t make_trunk_map(CUtensorMap *map, const void *trunk, int N, int H, int W, int box_w = tc5cfg::HW_, int box_h = tc5cfg::HH_) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return cudaErrorNotSupported;
-    const cuuint64_t dims[5] = {8, 3, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint64_t strides[4] = {16, 48, (cuuint64_t)W * 48, (cuuint64_t)H * W * 48};
-    const cuuint32_t box[5] = {8, 1, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(trunk), dims, strides, box, estr,
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 4, (cuuint64_t)H, 3, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)H * W * 48};
+    const cuuint32_t box[4] = {(cuuint32_t)box_w * 4, (cuuint32_t)box_h, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void *>(trunk), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;

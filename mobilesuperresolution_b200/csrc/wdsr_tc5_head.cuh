@@ -153,7 +153,7 @@ wdsr_head_tc5_kernel(const TIN *__restrict__ x, bf16 *__restrict__ trunk, const 
             tc5::mbar_arrive_relaxed(bar(D_EMPTY + e));
             const int gy = y0 + 4 * h + (row >> 5), gx = x0 + (row & 31);
             if (gy < H && gx < W) {
-                bf16 *o = trunk + (((long long)n * H + gy) * W + gx) * 24;
+                bf16 *o = trunk + (((long long)n * 3 * H + gy) * W + gx) * 8;   // planar-8 trunk [N][3][H][W][8] (tma_map.h)
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     const float4 ba = *reinterpret_cast<const float4 *>(bias + q * 8), bb = *reinterpret_cast<const float4 *>(bias + q * 8 + 4);
@@ -162,7 +162,7 @@ wdsr_head_tc5_kernel(const TIN *__restrict__ x, bf16 *__restrict__ trunk, const 
                     ov.y = pack_bf16x2(__uint_as_float(v[q * 8 + 2]) + ba.z, __uint_as_float(v[q * 8 + 3]) + ba.w);
                     ov.z = pack_bf16x2(__uint_as_float(v[q * 8 + 4]) + bb.x, __uint_as_float(v[q * 8 + 5]) + bb.y);
                     ov.w = pack_bf16x2(__uint_as_float(v[q * 8 + 6]) + bb.z, __uint_as_float(v[q * 8 + 7]) + bb.w);
-                    *reinterpret_cast<uint4 *>(o + q * 8) = ov;
+                    *reinterpret_cast<uint4 *>(o + (long long)q * H * W * 8) = ov;   // 32 lanes = 512 contiguous bytes
                 }
             }
         }

@@ -111,7 +111,7 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
                 for (int d = 0; d < 3; ++d)
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        tc5::tma_load_5d(tc_u + b * TC_BUF + (d * 3 + c) * PLANE, &tmap_trunk, bar(TC_FULL + b), 0, c, x0 - 1 + d, y0 - 1, n);
+                        tc5::tma_load_plane(tc_u + b * TC_BUF + (d * 3 + c) * PLANE, &tmap_trunk, bar(TC_FULL + b), x0 - 1 + d, y0 - 1, c, n);
             }
         }
         __syncwarp();

@@ -114,7 +114,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         const int xb = it % XS_NBUF;
         tc5::mbar_arrive_expect_tx(bar(XS_FULL + xb), TMA_BYTES);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) tc5::tma_load_5d(xs_u + xb * XS_BUF + c * XS_PLANE, &tmap_in, bar(XS_FULL + xb), 0, c, x0, y0, n);
+        for (int c = 0; c < 3; ++c) tc5::tma_load_plane(xs_u + xb * XS_BUF + c * XS_PLANE, &tmap_in, bar(XS_FULL + xb), x0, y0, c, n);
     };
     const int npre = nmine < XS_NBUF ? nmine : XS_NBUF;  // tiles whose loads are issued from the prologue
 
@@ -400,7 +400,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
 #else
             if (gy < H && gx < W) {
 #endif
-                bf16 *o = out + (((long long)n * H + gy) * W + gx) * 24;
+                bf16 *o = out + (((long long)n * 3 * H + gy) * W + gx) * 8;   // planar-8 trunk: plane q is H*W*8 elements further
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     const uint32_t *rw = reinterpret_cast<const uint32_t *>(&rv[q]);
@@ -414,7 +414,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                         ow[2 * j2] = pack_bf16x2(__uint_as_float(v[ch]) + bb.x + ra.x, __uint_as_float(v[ch + 1]) + bb.y + ra.y);
                         ow[2 * j2 + 1] = pack_bf16x2(__uint_as_float(v[ch + 2]) + bb.z + rb.x, __uint_as_float(v[ch + 3]) + bb.w + rb.y);
                     }
-                    *reinterpret_cast<uint4 *>(o + q * 8) = ov;
+                    *reinterpret_cast<uint4 *>(o + (long long)q * H * W * 8) = ov;   // 32 lanes = 512 contiguous bytes
                 }
             }
             V3_ADD(7);

@@ -142,27 +142,54 @@ class WdsrPlan:
                 prec, _ptr(x_stage), _ptr(y_stage), _ptr(ws), ws.numel(), _lib.current_stream_ptr(self.device)))
 
     # stage-level (tests)
-    def head(self, x: torch.Tensor, precision: str) -> torch.Tensor:
+    # ---- stage-level calls (parity tests, bench).  The public tensors are NHWC; on the bf16 tcgen05 path the kernels keep the
+    #      trunk planar-8 ([n][c/8][h][w][8]), so these wrappers convert on the way in and out.  ``*_internal`` skip the conversion.
+    def _planar(self, prec: int) -> bool:
+        return _lib.lib().b200sr_wdsr_trunk_layout(self._h, prec) == 1
+
+    def to_internal(self, trunk_nhwc: torch.Tensor, precision: str) -> torch.Tensor:
+        if not self._planar(_lib.precision_code(precision)):
+            return trunk_nhwc.contiguous()
+        n, h, w, c = trunk_nhwc.shape
+        return trunk_nhwc.view(n, h, w, c // 8, 8).permute(0, 3, 1, 2, 4).contiguous()
+
+    def from_internal(self, trunk: torch.Tensor, precision: str) -> torch.Tensor:
+        if not self._planar(_lib.precision_code(precision)):
+            return trunk
+        n, cb, h, w, _ = trunk.shape
+        return trunk.permute(0, 2, 3, 1, 4).reshape(n, h, w, cb * 8).contiguous()
+
+    def head_internal(self, x: torch.Tensor, precision: str) -> torch.Tensor:
         n, _, h, w = x.shape
         prec = _lib.precision_code(precision)
-        t = torch.empty((n, h, w, self.trunk_channels), dtype=torch.float32 if prec == _lib.F32 else torch.bfloat16,
-                        device=x.device)
+        c = self.trunk_channels
+        shape = (n, c // 8, h, w, 8) if self._planar(prec) else (n, h, w, c)
+        t = torch.empty(shape, dtype=torch.float32 if prec == _lib.F32 else torch.bfloat16, device=x.device)
         x = x.contiguous()
         _lib.check(_lib.lib().b200sr_wdsr_head(self._h, _ptr(x), _lib.dtype_code(x.dtype), _ptr(t), n, h, w, prec,
                                                _lib.current_stream_ptr(self.device)))
         return t
 
+    def block_internal(self, i: int, trunk: torch.Tensor, precision: str, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        prec = _lib.precision_code(precision)
+        n, h, w = (trunk.shape[0], trunk.shape[2], trunk.shape[3]) if self._planar(prec) else trunk.shape[:3]
+        assert trunk.is_contiguous()
+        out = torch.empty_like(trunk) if out is None else out
+        _lib.check(_lib.lib().b200sr_wdsr_block(self._h, i, _ptr(trunk), _ptr(out), n, h, w, prec, _lib.current_stream_ptr(self.device)))
+        return out
+
+    def head(self, x: torch.Tensor, precision: str) -> torch.Tensor:
+        return self.from_internal(self.head_internal(x, precision), precision)
+
     def block(self, i: int, trunk: torch.Tensor, precision: str) -> torch.Tensor:
         n, h, w, c = trunk.shape
-        assert c == self.trunk_channels and trunk.is_contiguous()
-        out = torch.empty_like(trunk)
-        _lib.check(_lib.lib().b200sr_wdsr_block(self._h, i, _ptr(trunk), _ptr(out), n, h, w, _lib.precision_code(precision),
-                                                _lib.current_stream_ptr(self.device)))
-        return out
+        assert c == self.trunk_channels
+        return self.from_internal(self.block_internal(i, self.to_internal(trunk, precision), precision), precision)
 
     def tail(self, trunk: torch.Tensor, x: torch.Tensor, precision: str, out_dtype=None) -> torch.Tensor:
         n, h, w, _ = trunk.shape
         x = x.contiguous()
+        trunk = self.to_internal(trunk, precision)
         out = torch.empty((n, 3, self.scale * h, self.scale * w), dtype=out_dtype or x.dtype, device=x.device)
         _lib.check(_lib.lib().b200sr_wdsr_tail(self._h, _ptr(trunk), _ptr(x), _lib.dtype_code(x.dtype), _ptr(out),
                                                _lib.dtype_code(out.dtype), n, h, w, _lib.precision_code(precision),

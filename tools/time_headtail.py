@@ -24,7 +24,7 @@ def t(fn, reps=20, flush=False):
     return tot / reps * 1e3
 
 
-trunk = plan.head(x, "bf16")
+trunk = plan.head(x, "bf16")   # NHWC view; plan.tail converts to the internal layout (adds a copy to the tail timing)
 for fl in (False, True):
     print(f"L2 {'flushed' if fl else 'warm   '}: head {t(lambda: plan.head(x, 'bf16'), flush=fl):7.1f} us   tail {t(lambda: plan.tail(trunk, x, 'bf16'), flush=fl):7.1f} us   "
           f"forward {t(lambda: plan.forward(x, 'bf16'), flush=fl):7.1f} us")
