@@ -280,15 +280,17 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
             for (int j = 0; j < M2; ++j)
                 for (int m = 0; m < M1; ++m)
                     at(L.w2 + (j / 8) * L.sbo2 + (m / 8) * 128 + (j % 8) * 16)[m % 8] = f2bf(k.w2[(size_t)j * M1 + m]);
+            const int NC2 = (M2 + 7) / 8;   // 8-channel chunks of t2 (3 dense; pruned blocks skip the 3x3 MMAs of absent chunks)
             for (int o = 0; o < C; ++o)
                 for (int j = 0; j < M2; ++j)
                     for (int dy = 0; dy < 3; ++dy)
                         for (int dx = 0; dx < 3; ++dx) {
-                            const int q = (dx * 3 + dy) * 3 + j / 8;
+                            const int q = (dx * 3 + dy) * NC2 + j / 8;   // only the (tap, chunk) slices t2 really has
                             at(L.w3 + (o / 8) * (28 * 128) + q * 128 + (o % 8) * 16)[j % 8] = f2bf(k.w3[((size_t)o * M2 + j) * 9 + dy * 3 + dx]);
                         }
             float *b2 = (float *)(img.data() + L.b2), *b3 = (float *)(img.data() + L.b3);
             for (int j = 0; j < M2; ++j) b2[j] = k.b2[j];
+            b2[31] = (float)NC2;   // informational (the launcher derives the same count from M2 and picks the kernel instantiation)
             for (int o = 0; o < C; ++o) b3[o] = k.b3[o];
             uint8_t *d = nullptr;
             if ((rc = upload(img.data(), img.size(), (void **)&d))) return rc;
@@ -420,9 +422,9 @@ int b200sr_wdsr_block(const b200sr_wdsr_t *p, int i, const void *tin, void *tout
         CU(launch_block_f32(p->cp, p->m2p_f32[i], (const float *)tin, (float *)tout, p->d_blk_f32[i], p->m1p[i], n, h, w,
                             (cudaStream_t)stream));
     else if (p->tc5_path())
-        CU(launch_block_tc5(1, tin, tout, p->d_blk_tc5[i], p->m1p[i], n, h, w, (cudaStream_t)stream));
-    else if (p->block_impl == 1 && p->d_blk_tc5[i])   // sequential tcgen05 reference form (NHWC trunk; developer switch)
-        CU(launch_block_tc5(0, tin, tout, p->d_blk_tc5[i], p->m1p[i], n, h, w, (cudaStream_t)stream));
+        CU(launch_block_tc5(1, tin, tout, p->d_blk_tc5[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
+    else if (p->block_impl == 1 && p->d_blk_tc5[i] && p->m2[i] > 16)   // sequential tcgen05 reference form (NHWC trunk, all 27 w3 slices; developer switch)
+        CU(launch_block_tc5(0, tin, tout, p->d_blk_tc5[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
     else
         CU(launch_block_bf16(p->cp, p->m2p_bf16[i], tin, tout, p->d_blk_bf16[i], p->m1p[i], n, h, w, (cudaStream_t)stream));
     return 0;

@@ -20,7 +20,7 @@ cudaError_t launch_block_f32(int CP, int M2P, const float *in, float *out, const
 cudaError_t launch_block_bf16(int CP, int M2P, const void *in, void *out, const uint8_t *wimg, int M1P, int N, int H, int W,
                               cudaStream_t st);
 // tcgen05 form of the fused block (CP == 24, M2 <= 24): variant 0 = sequential reference form, 1 = pipelined
-cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8_t *wimg, int M1P, int N, int H, int W,
+cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8_t *wimg, int M1P, int M2, int N, int H, int W,
                              cudaStream_t st);
 // tcgen05 form of the head (bf16 trunk padded to 24 channels)
 cudaError_t launch_head_tc5(int x_dtype, const void *x, void *trunk, const uint8_t *wimg, int N, int H, int W, float mean, cudaStream_t st);

@@ -10,7 +10,7 @@
 
 namespace b200sr {
 
-cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8_t *wimg, int M1P, int N, int H, int W,
+cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8_t *wimg, int M1P, int M2, int N, int H, int W,
                              cudaStream_t st) {
     using namespace tc5cfg;
     const int tx = ceil_div(W, TW), ty = ceil_div(H, TH);
@@ -40,14 +40,16 @@ cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8
         c.p = in, c.n = N, c.h = H, c.w = W;
         mapp = &c.map;
     }
+    const int nc2 = M2 <= 8 ? 1 : M2 <= 16 ? 2 : 3;   // 8-channel chunks of t2 (the image was packed for exactly these, b200sr.cu)
+    auto kern = nc2 == 3 ? wdsr_block_tc5p_kernel<3> : nc2 == 2 ? wdsr_block_tc5p_kernel<2> : wdsr_block_tc5p_kernel<1>;
     const size_t smem = tc5v3::smem_bytes(M1P);
-    static thread_local size_t smem_set[64] = {0};
+    static thread_local size_t smem_set[64][3] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || smem_set[dev] < smem) {
-        e = cudaFuncSetAttribute(wdsr_block_tc5p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (dev < 0 || dev >= 64 || smem_set[dev][nc2 - 1] < smem) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) smem_set[dev] = smem;
+        if (dev >= 0 && dev < 64) smem_set[dev][nc2 - 1] = smem;
     }
     const CUtensorMap &map = *mapp;
     // programmatic stream serialization: this grid may start (and run its prologue) while the previous kernel in the stream
@@ -58,7 +60,7 @@ cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, wdsr_block_tc5p_kernel, map, (const bf16 *)in, (bf16 *)out, wimg, M1P, N, H, W, tx, ty, ntiles);
+    return cudaLaunchKernelEx(&cfg, kern, map, (const bf16 *)in, (bf16 *)out, wimg, M1P, N, H, W, tx, ty, ntiles);
 }
 
 }  // namespace b200sr

@@ -81,6 +81,10 @@ constexpr int CTRL_BYTES = 256;  // 22 mbarriers (176 B) + tmem base pointer at 
 constexpr size_t smem_bytes(int M1P) { return (size_t)tc5v3::CTRL_BYTES + XS_BYTES_ALL + T2_BYTES + (size_t)BlockTc5Layout(M1P).total; }
 }  // namespace tc5v3
 
+// NC2 = 8-channel chunks of t2 the block really has (3 dense; 2 / 1 for pruned M2 <= 16 / <= 8): the host packs only those
+// (tap, chunk) slices of w3 (b200sr.cu) and the 3x3 issues 14 / 9 / 5 MMAs.  A template parameter, not a run-time value: the
+// dense instantiation is then exactly the code that was tuned (a run-time switch cost it 3-5 %).
+template <int NC2>
 __global__ void __launch_bounds__(tc5v3::NTHREADS, 1)
 wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *__restrict__ in, bf16 *__restrict__ out,
                        const uint8_t *__restrict__ wimg, int M1P, int N, int H, int W, int tiles_x, int tiles_y, int ntiles) {
@@ -154,6 +158,9 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
     for (int i = tid; i < XS_PLANE / 16; i += NTHREADS)                       // constant-one plane: 1.0 in channels 0,1
         *reinterpret_cast<uint4 *>(xs + XS_ONE + i * 16) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
     for (int i = tid; i < 16; i += NTHREADS) *reinterpret_cast<uint4 *>(t2 + 3 * T2_COPY + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    if (NC2 < 3)   // a pruned block never writes the absent chunks, and the zero-weight dummy half of its last 3x3 instruction reads
+                   // one chunk past the last slice: t2 must start as zeros (the dense block pays nothing)
+        for (int i = tid; i < T2_BYTES / 16; i += NTHREADS) *reinterpret_cast<uint4 *>(t2 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     cp_async_wait<0>();
     tc5::fence_proxy_async();
     tc5::fence_before_sync();
@@ -251,25 +258,27 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         const uint32_t idesc32 = tc5::idesc_bf16_f32(128, 32);
         const uint64_t bw3 = tc5::smem_desc(w_u + L.w3, 128, 28 * 128);
         const uint64_t at0 = tc5::smem_desc(t2_u, 0, T2_GROUP);    // LBO added per instruction
-        auto issue_g3 = [&](int k) {  // leader only
+        auto issue_g3_nc = [&](int k, auto ncc) {  // leader only; NC = chunks of t2 (3 dense; 2 or 1 for pruned M2 <= 16 / <= 8)
+            constexpr int NC = decltype(ncc)::value, NS = 9 * NC, NM = (NS + 1) / 2;
             const uint64_t abase = at0 + (uint64_t)((k * 4 * T2_ROW) >> 4);
             const uint32_t d3 = tmem + d3_col(k);
 #ifdef B200SR_EXP_G3SHORT
             constexpr int NG3 = 2;   // (timing experiment: results are wrong)
 #else
-            constexpr int NG3 = 14;
+            constexpr int NG3 = NM;
 #endif
 #pragma unroll
-            for (int i = 0; i < NG3; ++i) {
+            for (int i = 0; i < NG3; ++i) {   // slice q = (dx * 3 + dy) * NC + chunk, two slices per K = 16 instruction through LBO
                 const int q0 = 2 * i, q1 = 2 * i + 1;
-                const int a0 = (q0 / 9) * T2_COPY + ((q0 / 3) % 3) * T2_ROW + (q0 % 3) * 128;
-                const int a1 = q1 < 27 ? (q1 / 9) * T2_COPY + ((q1 / 3) % 3) * T2_ROW + (q1 % 3) * 128 : a0 + 128;
+                const int a0 = (q0 / (3 * NC)) * T2_COPY + ((q0 / NC) % 3) * T2_ROW + (q0 % NC) * 128;
+                const int a1 = q1 < NS ? (q1 / (3 * NC)) * T2_COPY + ((q1 / NC) % 3) * T2_ROW + (q1 % NC) * 128 : a0 + 128;
                 tc5::mma_ss(d3, abase + (uint64_t)(a0 >> 4) + ((uint64_t)((a1 - a0) >> 4) << 16), bw3 + (uint64_t)(16 * i), idesc32,
                             i > 0);
             }
             tc5::commit(bar(D3_FULL + k));
             if (k == 3) tc5::commit(bar(T2R_FREE + 3));  // (in-order) every 3x3 MMA of this tile has retired
         };
+        auto issue_g3 = [&](int k) { issue_g3_nc(k, std::integral_constant<int, NC2>{}); };
         // wait (whole warp) for what G3(k) of tile `t` needs, then issue it
         auto do_g3 = [&](int t, int k) {
             V3_WAIT(3, bar(G3_READY + k), t & 1);
@@ -281,6 +290,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         };
         V3_T0();
         for (int it = 0; it < nmine; ++it)
+#pragma unroll 1   // (unrolled over k, the descriptor temporaries of the shorter pruned batches spill at this warpgroup's 40 registers)
             for (int k = 0; k < 4; ++k) do_g3(it, k);
         V3_ADD(5);
         if (nmine > 0) tc5::mbar_wait(bar(T2R_FREE + 3), (nmine - 1) & 1);  // every G3 of this CTA has retired
@@ -440,10 +450,10 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
 #else
             if (p < HP) {
 #endif
-                uint4 c[3];
+                uint4 c[NC2];   // only the chunks this block has (compile-time sized: a partly used array went to local memory)
                 uint32_t *cw = reinterpret_cast<uint32_t *>(c);
 #pragma unroll
-                for (int j4 = 0; j4 < 6; ++j4) {
+                for (int j4 = 0; j4 < 2 * NC2; ++j4) {
                     const float4 bb = *reinterpret_cast<const float4 *>(b2s + 4 * j4);  // broadcast read
                     cw[2 * j4] = ok ? pack_bf16x2(__uint_as_float(v[4 * j4]) + bb.x, __uint_as_float(v[4 * j4 + 1]) + bb.y) : 0u;
                     cw[2 * j4 + 1] = ok ? pack_bf16x2(__uint_as_float(v[4 * j4 + 2]) + bb.z, __uint_as_float(v[4 * j4 + 3]) + bb.w) : 0u;
@@ -454,7 +464,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                     if (xi >= 0 && xi < TW) {
                         uint8_t *dst = t2 + d * T2_COPY + r * T2_ROW + (xi >> 3) * T2_GROUP + (xi & 7) * 16;
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) *reinterpret_cast<uint4 *>(dst + q * 128) = c[q];
+                        for (int q = 0; q < NC2; ++q) *reinterpret_cast<uint4 *>(dst + q * 128) = c[q];
                     }
                 }
             }

@@ -10,6 +10,7 @@ int main() {
     const int N = 64, H = 96, W = 96, M1P = 144;
     BlockTc5Layout L(M1P);
     std::vector<uint8_t> img(L.total, 0);
+    reinterpret_cast<float *>(img.data() + L.b2)[31] = 3.f;   // dense block: all three 8-channel chunks of t2 (see b200sr.cu)
     uint8_t *dimg; bf16 *din, *dout;
     cudaMalloc(&dimg, L.total); cudaMemcpy(dimg, img.data(), L.total, cudaMemcpyHostToDevice);
     size_t nb = (size_t)N * H * W * 24 * 2;
@@ -17,7 +18,7 @@ int main() {
     const int tx = ceil_div(W, 32), ty = ceil_div(H, 16), ntiles = tx * ty * N;
     CUtensorMap map; if (make_trunk_map(&map, din, N, H, W) != cudaSuccess) { printf("map failed\n"); return 1; }
     size_t smem = tc5v3::smem_bytes(M1P);
-    cudaFuncSetAttribute(wdsr_block_tc5p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(wdsr_block_tc5p_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     unsigned *dbg_h = nullptr, *dbg_d = nullptr;
     cudaHostAlloc(&dbg_h, 148 * 32 * 16, cudaHostAllocMapped); memset(dbg_h, 0, 148 * 32 * 16); cudaHostGetDevicePointer(&dbg_d, dbg_h, 0);
     cudaMemcpyToSymbol(tc5::g_tc5_dbg, &dbg_d, sizeof dbg_d);
@@ -26,7 +27,7 @@ int main() {
         cudaMemcpyToSymbol(g_tc5p_prof, z, sizeof z);
         cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
         cudaEventRecord(a);
-        wdsr_block_tc5p_kernel<<<148, tc5v3::NTHREADS, smem>>>(map, din, dout, dimg, M1P, N, H, W, tx, ty, ntiles);
+        wdsr_block_tc5p_kernel<3><<<148, tc5v3::NTHREADS, smem>>>(map, din, dout, dimg, M1P, N, H, W, tx, ty, ntiles);
         cudaEventRecord(b);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {

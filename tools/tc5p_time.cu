@@ -10,6 +10,7 @@ int main(int argc, char **argv) {
     const int N = argc > 1 ? atoi(argv[1]) : 64, H = argc > 2 ? atoi(argv[2]) : 96, W = argc > 3 ? atoi(argv[3]) : 96, M1P = 144;
     BlockTc5Layout L(M1P);
     std::vector<uint8_t> img(L.total, 0);
+    reinterpret_cast<float *>(img.data() + L.b2)[31] = 3.f;   // dense block: all three 8-channel chunks of t2 (see b200sr.cu)
     uint8_t *dimg; bf16 *buf[2];
     cudaMalloc(&dimg, L.total); cudaMemcpy(dimg, img.data(), L.total, cudaMemcpyHostToDevice);
     size_t nb = (size_t)N * H * W * 24 * 2;
@@ -18,7 +19,7 @@ int main(int argc, char **argv) {
     CUtensorMap map[2];
     for (int i = 0; i < 2; ++i) if (make_trunk_map(&map[i], buf[i], N, H, W) != cudaSuccess) { printf("map failed\n"); return 1; }
     size_t smem = tc5v3::smem_bytes(M1P);
-    cudaFuncSetAttribute(wdsr_block_tc5p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(wdsr_block_tc5p_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int ctas = std::min(148, ntiles);
     std::vector<float> t;
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -27,7 +28,7 @@ int main(int argc, char **argv) {
         for (int l = 0; l < 16; ++l)
         {
 #ifdef NO_PDL
-            wdsr_block_tc5p_kernel<<<ctas, tc5v3::NTHREADS, smem>>>(map[l & 1], buf[l & 1], buf[(l & 1) ^ 1], dimg, M1P, N, H, W, tx, ty, ntiles);
+            wdsr_block_tc5p_kernel<3><<<ctas, tc5v3::NTHREADS, smem>>>(map[l & 1], buf[l & 1], buf[(l & 1) ^ 1], dimg, M1P, N, H, W, tx, ty, ntiles);
 #else
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(ctas), cfg.blockDim = dim3(tc5v3::NTHREADS), cfg.dynamicSmemBytes = smem, cfg.stream = 0;
@@ -35,7 +36,7 @@ int main(int argc, char **argv) {
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr, cfg.numAttrs = 1;
-            cudaLaunchKernelEx(&cfg, wdsr_block_tc5p_kernel, map[l & 1], (const bf16 *)buf[l & 1], buf[(l & 1) ^ 1], (const uint8_t *)dimg, M1P, N, H, W, tx, ty, ntiles);
+            cudaLaunchKernelEx(&cfg, wdsr_block_tc5p_kernel<3>, map[l & 1], (const bf16 *)buf[l & 1], buf[(l & 1) ^ 1], (const uint8_t *)dimg, M1P, N, H, W, tx, ty, ntiles);
 #endif
         }
         cudaEventRecord(b);
