@@ -183,10 +183,15 @@ class SpyNet(nn.Module, _VideoPlanMixin):
             raise RuntimeError("Input and output sizes should be greater than 0 (SPyNet needs at least 33 pixels per side)")
         convs = self._convs(dev)
         st = _lib.current_stream_ptr(dev)
-        mean = self.mean.detach().float().cpu().view(-1).tolist() + [0.0]
-        inv_std = (1.0 / self.std.detach().float().cpu().view(-1)).tolist() + [1.0]
-        sub = (ctypes.c_float * 4)(*mean)
-        mul = (ctypes.c_float * 4)(*inv_std)
+        # the normalisation constants travel as kernel arguments; read the (device) buffers back only when they change -- a
+        # device->host copy per call is a stream sync and forbids CUDA-graph capture of the forward
+        nsig = (self.mean.data_ptr(), self.mean._version, self.std.data_ptr(), self.std._version)
+        if getattr(self, "_norm_sig", None) != nsig:
+            mean = self.mean.detach().float().cpu().view(-1).tolist() + [0.0]
+            inv_std = (1.0 / self.std.detach().float().cpu().view(-1)).tolist() + [1.0]
+            self._norm_args = ((ctypes.c_float * 4)(*mean), (ctypes.c_float * 4)(*inv_std))
+            self._norm_sig = nsig
+        sub, mul = self._norm_args
         f32 = dict(dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             def prep(img):

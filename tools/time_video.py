@@ -43,3 +43,19 @@ for prec in ("fp32", "bf16"):
     x = torch.rand(1, 15, 3, 180, 320, device=dev)
     us = timeit(lambda: m(x, 720, 1280), reps=3, warm=1)
     print(f"BasicVSR_origin(64,30) {prec}: clip 15x180x320 -> 720x1280: {us / 1e3:9.2f} ms/clip = {15 / us * 1e6:8.1f} frames/s, {11.23e12 / us / 1e6:7.1f} TFLOP/s (11.23 TFLOP/clip)")
+    try:   # the same forward as ONE CUDA graph (no Python / ctypes launch overhead between the ~4,000 kernels of a clip)
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                y = m(x, 720, 1280)
+            g.replay(); st.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            for _ in range(3): g.replay()
+            b.record(st); st.synchronize()
+        us = a.elapsed_time(b) / 3 * 1e3
+        print(f"    as one CUDA graph: {us / 1e3:9.2f} ms/clip = {15 / us * 1e6:8.1f} frames/s, {11.23e12 / us / 1e6:7.1f} TFLOP/s")
+    except Exception as e:
+        print("    CUDA-graph capture of the clip forward failed:", repr(e)[:200])
