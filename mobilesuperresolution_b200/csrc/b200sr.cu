@@ -57,6 +57,12 @@ uint16_t f2bf(float f) {  // round-to-nearest-even, same as __float2bfloat16_rn 
 
 size_t esize(int dtype) { return dtype == B200SR_F32 ? 4 : 2; }
 
+// B200SR_CONV_IMPL = mma keeps the video path's 3x3 64 -> 64 convolutions on the mma.sync kernel (developer A/B switch, read per call)
+bool conv_tc5_enabled() {
+    const char *e = getenv("B200SR_CONV_IMPL");
+    return !e || strcmp(e, "mma") != 0;
+}
+
 struct BlockW {
     std::vector<float> w1, b1, w2, b2, w3, b3;
     bool set = false;
@@ -510,6 +516,7 @@ struct b200sr_conv {
     int cin = 0, cout = 0, k = 0, cinp_f32 = 0, coutp_f32 = 0, cinp_bf16 = 0, coutp_bf16 = 0, nt = 0;
     float *d_w_f32 = nullptr, *d_bias = nullptr;
     uint16_t *d_w_bf16 = nullptr;
+    uint8_t *d_w_tc5 = nullptr;   // tcgen05 operand image of a 3x3 64 -> 64 filter (conv_tc5.cuh)
 };
 
 int b200sr_conv_create(int cin, int cout, int k, const float *w, const float *bias, b200sr_conv_t **out) {
@@ -535,6 +542,18 @@ int b200sr_conv_create(int cin, int cout, int k, const float *w, const float *bi
         if (bias) bb[o] = bias[o];
     }
     int rc;
+    if (cin == 64 && cout == 64 && k == 3) {
+        // K-major core matrices [8-output-channel group][(tap, 8-input-channel chunk) slice][8 rows][16 B] (conv_tc5.cuh)
+        std::vector<uint16_t> wi((size_t)8 * 72 * 64, 0);
+        for (int o = 0; o < 64; ++o)
+            for (int i = 0; i < 64; ++i)
+                for (int t = 0; t < 9; ++t)
+                    wi[(((size_t)(o / 8) * 72 + t * 8 + i / 8) * 8 + o % 8) * 8 + i % 8] = f2bf(w[((size_t)o * 64 + i) * 9 + t]);
+        if ((rc = upload(wi.data(), wi.size() * 2, (void **)&c->d_w_tc5))) {
+            b200sr_conv_destroy(c);
+            return rc;
+        }
+    }
     if ((rc = upload(wf.data(), wf.size() * 4, (void **)&c->d_w_f32)) || (rc = upload(wb.data(), wb.size() * 2, (void **)&c->d_w_bf16)) ||
         (rc = upload(bb.data(), bb.size() * 4, (void **)&c->d_bias))) {
         b200sr_conv_destroy(c);
@@ -549,6 +568,7 @@ void b200sr_conv_destroy(b200sr_conv_t *c) {
     if (c->d_w_f32) cudaFree(c->d_w_f32);
     if (c->d_w_bf16) cudaFree(c->d_w_bf16);
     if (c->d_bias) cudaFree(c->d_bias);
+    if (c->d_w_tc5) cudaFree(c->d_w_tc5);
     delete c;
 }
 
@@ -568,6 +588,12 @@ int b200sr_conv_forward(const b200sr_conv_t *c, const void *x, int x_cs, int x_c
         a.w = c->d_w_f32, a.cinp = c->cinp_f32, a.coutp = c->coutp_f32;
     } else {
         a.w = c->d_w_bf16, a.cinp = c->cinp_bf16, a.coutp = c->coutp_bf16;
+    }
+    if (precision == B200SR_BF16 && in_dtype == B200SR_BF16 && out_dtype == B200SR_BF16 && c->d_w_tc5 && conv_tc5_enabled() &&
+        conv_tc5_eligible(a)) {
+        cudaError_t e5 = launch_conv3x3_c64_tc5(a, c->d_w_tc5, (cudaStream_t)stream);
+        if (e5 != cudaSuccess) return cuda_fail(e5, "conv_forward (tcgen05 3x3 64->64)");
+        return 0;
     }
     cudaError_t e = launch_conv(a, c->k, c->nt, in_dtype, out_dtype, precision, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "conv_forward (fp32 precision needs float32 tensors; bf16 precision: bf16|f32 in, bf16|f32 out)");

@@ -1,0 +1,190 @@
+// conv_tc5.cuh -- 3x3 "same" convolution, 64 -> 64 channels, bf16 NHWC, on tcgen05: the BasicVSR propagation trunks
+// (ConvResidualBlocks: 30 x [conv-ReLU-conv + x] per frame and direction, models/basicvsr_arch_origin.py:98-137) and conv_hr.
+//
+//   y[n, oy, ox, co] = act( bias[co] + sum_{ky,kx,ci} x[n, oy+ky-1, ox+kx-1, ci] * w[co][ci][ky][kx] ) (+ residual)
+//
+// Same producer -> MMA -> epilogue chain as the WDSR tail (wdsr_tc5_tail.cuh), no builders: an implicit GEMM with pixels as M.
+//   warp 0      TMA      eight cp.async.bulk.tensor.5d per tile (one per 8-channel chunk) of a 32 x 10 pixel box (30 x 8 outputs +
+//                        1-pixel halo) into chunk-planar shared memory [chunk][pixel][16 B]; out-of-image pixels are zero-filled
+//                        by the TMA unit (= the conv's zero padding); three tile buffers
+//   warp 1      MMA      per 128-pixel M-tile (four 32-pixel box rows) 36 tcgen05.mma (M = 128, N = 64, K = 16): a tap is a constant
+//                        pixel offset of the A operand's start address (the two box columns right of the 30 outputs compute
+//                        don't-care rows), the two 8-channel chunks of a K step are paired through the LBO stride
+//   warps 2-5 / 6-9      epilogue of the tile's first / second M-tile: tcgen05.ld -> + bias -> activation -> (+ residual) -> 128-byte
+//                        NHWC pixel stores.  Activations may live inside wider NHWC tensors (channel stride / offset).
+// The generic mma.sync kernel (conv.cuh) ran these convolutions at ~110 TFLOP/s; they are 77 % of a BasicVSR clip's FLOPs.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "conv.cuh"
+#include "tc5.cuh"
+
+namespace b200sr {
+namespace tc5conv {
+constexpr int TWO = 30, TH = 8, BW = 32, BH = TH + 2, NCH = 8, NTHREADS = 320;
+constexpr int PLANE_PX = BW * BH + 8;            // + 8 zero pixels: the last taps of the second M-tile read past the box
+constexpr int PLANE = PLANE_PX * 16;             // 5,248 B
+constexpr int TILE_BUF = NCH * PLANE;            // 41,984 B
+constexpr int NBUF = 3;
+constexpr int W_SBO = 72 * 128;                  // weight image [8 row groups][72 (tap, chunk) slices][8 rows][16 B]
+constexpr int W_BYTES = 8 * W_SBO;               // 73,728 B
+constexpr int CTRL = 256;
+enum Bar { TC_FULL = 0 /*3*/, TC_EMPTY = 3 /*3*/, D_FULL = 6, D_EMPTY = 8, NBARS = 10 };
+constexpr size_t smem_bytes() { return (size_t)CTRL + NBUF * TILE_BUF + W_BYTES + 256; }
+}  // namespace tc5conv
+
+__device__ __forceinline__ void tma_load_5d_conv(uint32_t dst_saddr, const void *tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst_saddr), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(tc5conv::NTHREADS, 1)
+conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, const uint8_t *__restrict__ wimg, int tiles_x, int tiles_y,
+                       int ntiles) {
+    using namespace tc5conv;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *ctrl = smem_raw;
+    uint8_t *tc = smem_raw + CTRL;           // NBUF x TILE_BUF
+    uint8_t *wsm = tc + NBUF * TILE_BUF;     // W_BYTES
+    float *bias_s = reinterpret_cast<float *>(wsm + W_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bars = smem_u32(ctrl);
+    auto bar = [&](int b) { return bars + 8u * (uint32_t)b; };
+    const uint32_t tc_u = smem_u32(tc), w_u = smem_u32(wsm);
+    const int H = a.h, W = a.w_;
+
+    // Launched with programmatic stream serialization: the set-up below (barriers, TMEM, the constant weight image) may overlap the
+    // previous kernel's tail; every read of an activation tensor sits behind griddepcontrol.wait, every store behind those reads.
+    tc5::pdl_launch_dependents();
+    if (tid == 0) {
+        for (int b = 0; b < NBUF; ++b) {
+            tc5::mbar_init(bar(TC_FULL + b), 1);
+            tc5::mbar_init(bar(TC_EMPTY + b), 1);
+        }
+        for (int e = 0; e < 2; ++e) {
+            tc5::mbar_init(bar(D_FULL + e), 1);
+            tc5::mbar_init(bar(D_EMPTY + e), 128);
+        }
+        tc5::mbar_init_fence();
+        tc5::tma_prefetch_desc(&tmap_x);
+    }
+    __syncwarp();
+    if (warp == 0) tc5::tmem_alloc(smem_u32(ctrl + 240), 128);
+    for (int i = tid; i < W_BYTES / 16; i += NTHREADS) cp_async16(wsm + i * 16, wimg + i * 16, 16);
+    cp_async_commit();
+    if (tid < 64) bias_s[tid] = a.bias[tid];
+    for (int i = tid; i < NBUF * NCH * 8; i += NTHREADS)   // the 8 pad pixels of every plane stay zero (TMA never writes them)
+        *reinterpret_cast<uint4 *>(tc + (i / 8) * PLANE + (BW * BH + i % 8) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    cp_async_wait<0>();
+    tc5::fence_proxy_async();
+    tc5::fence_before_sync();
+    __syncthreads();
+    tc5::fence_after_sync();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(ctrl + 240);
+    const int nmine = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    auto tile_origin = [&](int it, int &x0, int &y0, int &n) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        x0 = (tile % tiles_x) * TWO;
+        y0 = ((tile / tiles_x) % tiles_y) * TH;
+        n = tile / (tiles_x * tiles_y);
+    };
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (tc5::elect_one()) {
+            tc5::pdl_wait();
+            for (int it = 0; it < nmine; ++it) {
+                int x0, y0, n;
+                tile_origin(it, x0, y0, n);
+                const int b = it % NBUF;
+                tc5::mbar_wait(bar(TC_EMPTY + b), ((it / NBUF) & 1) ^ 1);
+                tc5::mbar_arrive_expect_tx(bar(TC_FULL + b), NCH * BW * BH * 16);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) tma_load_5d_conv(tc_u + b * TILE_BUF + c * PLANE, &tmap_x, bar(TC_FULL + b), 0, c, x0 - 1, y0 - 1, n);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        const bool leader = tc5::elect_one();
+        const uint32_t idesc = tc5::idesc_bf16_f32(128, 64);
+        const uint64_t bw = tc5::smem_desc(w_u, 128, W_SBO), a0d = tc5::smem_desc(tc_u, PLANE, 128);   // A: chunk pairs through LBO = plane stride
+        for (int g = 0; g < 2 * nmine; ++g) {
+            const int it = g >> 1, m = g & 1, b = it % NBUF, e = m;
+            if (m == 0) tc5::mbar_wait(bar(TC_FULL + b), (it / NBUF) & 1);
+            tc5::mbar_wait(bar(D_EMPTY + e), (it & 1) ^ 1);
+            tc5::fence_after_sync();
+            if (leader) {
+                const uint32_t d = tmem + e * 64;
+                const uint64_t abase = a0d + (uint64_t)((b * TILE_BUF + m * 128 * 16) >> 4);
+#pragma unroll
+                for (int i = 0; i < 36; ++i) {   // (tap t = i / 4, chunks 2 (i % 4), 2 (i % 4) + 1)
+                    const int t = i >> 2, cp = i & 3, dy = t / 3, dx = t % 3;
+                    const int aoff = 2 * cp * PLANE + (dy * BW + dx) * 16;
+                    tc5::mma_ss(d, abase + (uint64_t)(aoff >> 4), bw + (uint64_t)(16 * i), idesc, i > 0);
+                }
+                tc5::commit(bar(D_FULL + e));
+                if (m == 1) tc5::commit(bar(TC_EMPTY + b));
+            }
+            __syncwarp();
+        }
+        if (nmine > 0) tc5::mbar_wait(bar(D_FULL + 1), (nmine - 1) & 1);  // every MMA retired
+    } else {
+        // ============================== epilogue: M-tile e of every tile ==============================
+        const int e = (warp - 2) >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        bf16 *y = reinterpret_cast<bf16 *>(a.y);
+        const bf16 *res = reinterpret_cast<const bf16 *>(a.residual);
+        const int act = a.act;
+        tc5::pdl_wait();
+        for (int it = 0; it < nmine; ++it) {
+            int x0, y0, n;
+            tile_origin(it, x0, y0, n);
+            const int p = e * 128 + row, by = p >> 5, bx = p & 31;
+            const int gy = y0 + by, gx = x0 + bx;
+            const bool ok = bx < TWO && gx < W && gy < H;
+            const long long pix = ((long long)n * H + gy) * W + gx;
+            uint4 rv[8];
+            if (res && ok) {   // residual of this pixel: in flight while the accumulator is waited for
+                const uint4 *rp = reinterpret_cast<const uint4 *>(res + pix * a.r_cs + a.r_co);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) rv[q] = __ldg(rp + q);
+            }
+            tc5::mbar_wait(bar(D_FULL + e), it & 1);
+            tc5::fence_after_sync();
+            uint32_t v[64];
+            tc5::tmem_ld32(tmem + lane_base + e * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tc5::tmem_ld32(tmem + lane_base + e * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+            tc5::tmem_wait_ld();
+            tc5::fence_before_sync();
+            tc5::mbar_arrive_relaxed(bar(D_EMPTY + e));
+            if (ok) {
+                uint4 *yp = reinterpret_cast<uint4 *>(y + pix * a.y_cs + a.y_co);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = apply_act(__uint_as_float(v[q * 8 + j]) + bias_s[q * 8 + j], act);
+                    if (res) {
+                        const uint32_t *rw = reinterpret_cast<const uint32_t *>(&rv[q]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 r2 = unpack_bf16x2(rw[j]);
+                            f[2 * j] += r2.x, f[2 * j + 1] += r2.y;
+                        }
+                    }
+                    yp[q] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                }
+            }
+        }
+    }
+    tc5::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc5::tmem_free(tmem, 128);
+}
+
+}  // namespace b200sr

@@ -40,6 +40,9 @@ cudaError_t launch_flow_warp_nhwc(const void *x, const float *flow_nchw, void *y
 struct ConvArgs;
 // generic NHWC convolution (conv.cuh); nt = output-channel n-tiles per CTA of the bf16 kernel (1,2,4,8)
 cudaError_t launch_conv(const ConvArgs &a, int k, int nt, int in_dtype, int out_dtype, int precision, cudaStream_t st);
+// tcgen05 3x3 64 -> 64 bf16 NHWC convolution (conv_tc5.cuh): wimg = its operand image; eligibility = channel windows 16-byte aligned
+bool conv_tc5_eligible(const ConvArgs &a);
+cudaError_t launch_conv3x3_c64_tc5(const ConvArgs &a, const uint8_t *wimg, cudaStream_t st);
 // video glue (video_glue.cu)
 cudaError_t launch_resize_bilinear_nchw(const void *x, int x_dtype, float *y, int n, int c, int h, int w, int oh, int ow, int align,
                                         const float *sub4, const float *mul4, cudaStream_t st);

@@ -161,3 +161,59 @@ def test_cfg4_basicvsr_clip_properties(V):
     assert torch.equal(y1, y2[1:2])
     yf = m.set_precision("fp32")(xb[:1], 720, 1280)
     assert port.psnr_db(y2[:1].cpu(), yf.cpu()) >= 50.0
+
+
+@pytest.mark.parametrize("n,h,w", [(1, 8, 30), (2, 19, 37), (1, 180, 320), (3, 33, 61)])
+@pytest.mark.parametrize("act,with_res", [(0, True), (1, False), (2, True)])
+def test_conv3x3_c64_tcgen05(V, n, h, w, act, with_res, monkeypatch):
+    """The tcgen05 form of the BasicVSR trunk convolution (3x3, 64 -> 64, bf16 NHWC; models/basicvsr_arch_origin.py:115-137):
+    against torch fp32 on the bf16-rounded operands, and against the mma.sync kernel it replaces (B200SR_CONV_IMPL=mma).
+    Exercises partial tiles in x and y, several images per launch and the image border (TMA zero fill = the conv's zero padding)."""
+    g = torch.Generator().manual_seed(n * 1000 + h * 10 + w + act)
+    conv = nn.Conv2d(64, 64, 3, 1, 1)
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.bfloat16().float())
+    x = torch.randn(n, 64, h, w, generator=g).bfloat16()
+    res = torch.randn(n, 64, h, w, generator=g).bfloat16()
+    hd = V._ConvHandle(conv, torch.device("cuda:0"))
+    xn = x.permute(0, 2, 3, 1).contiguous().cuda()
+    rn = res.permute(0, 2, 3, 1).contiguous().cuda() if with_res else None
+    with torch.no_grad():
+        ref = F.conv2d(x.double(), conv.weight.double(), conv.bias.double(), padding=1)
+        ref = F.relu(ref) if act == 1 else F.leaky_relu(ref, 0.1) if act == 2 else ref
+        if with_res:
+            ref = ref + res.double()
+    y = hd(xn, "bf16", act, residual=rn)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("B200SR_CONV_IMPL", "mma")
+    y_mma = hd(xn, "bf16", act, residual=rn)
+    torch.cuda.synchronize()
+    yf = y.float().cpu().permute(0, 3, 1, 2).double()
+    # fp32 accumulation of exact bf16 products, one rounding to bf16 at the store: half an ulp of the output magnitude
+    tol = 2.0 ** -8 * ref.abs().clamp_min(1.0) + 1e-3
+    assert bool(((yf - ref).abs() <= tol).all()), float((yf - ref).abs().max())
+    assert float((y.float() - y_mma.float()).abs().max()) <= 2.0 ** -6 * float(ref.abs().max())
+
+
+def test_conv3x3_c64_tcgen05_channel_windows(V):
+    """x / y / residual as 16-byte aligned channel windows of wider NHWC tensors."""
+    conv = nn.Conv2d(64, 64, 3, 1, 1)
+    g = torch.Generator().manual_seed(77)
+    xw = torch.randn(1, 21, 45, 144, generator=g).bfloat16()
+    rw = torch.randn(1, 21, 45, 72, generator=g).bfloat16()
+    hd = V._ConvHandle(conv, torch.device("cuda:0"))
+    out = torch.full((1, 21, 45, 80), 3.0, dtype=torch.bfloat16, device="cuda")
+    import ctypes
+    from mobilesuperresolution_b200 import _lib
+    L = _lib.lib()
+    xd, rd = xw.cuda(), rw.cuda()
+    _lib.check(L.b200sr_conv_forward(hd._h, ctypes.c_void_p(xd.data_ptr()), 144, 72, ctypes.c_void_p(out.data_ptr()), 80, 8,
+                                     ctypes.c_void_p(rd.data_ptr()), 72, 8, 1, 21, 45, 0, 1, _lib.BF16, _lib.BF16, _lib.precision_code("bf16"),
+                                     _lib.current_stream_ptr(xd.device)))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = F.conv2d(xw[..., 72:136].permute(0, 3, 1, 2).float(), conv.weight.bfloat16().float(), conv.bias, padding=1) + \
+            rw[..., 8:72].permute(0, 3, 1, 2).float()
+    o = out.float().cpu()
+    assert float((o[..., 8:72].permute(0, 3, 1, 2) - ref).abs().max()) <= 0.05
+    assert float((o[..., :8] - 3).abs().max()) == 0 and float((o[..., 72:] - 3).abs().max()) == 0
