@@ -156,6 +156,17 @@ B200SR_API int b200sr_conv_forward(const b200sr_conv_t *conv, const void *x_dev,
                                    int y_coff, const void *residual_dev, int r_cstride, int r_coff, int n, int h, int w, int act,
                                    int shuffle, int in_dtype, int out_dtype, int precision, void *stream);
 
+/* The same convolution with explicit activation layouts (B200SR_TRUNK_NHWC | B200SR_TRUNK_PLANAR8).  Planar-8,
+ * [n][channels/8][h][w][8] bf16 with exactly 64 channels and no channel window, is what the BasicVSR propagation trunks
+ * (ConvResidualBlocks, models/basicvsr_arch_origin.py:98-137) keep their private 64-channel tensors in: only the tcgen05
+ * 3x3 (64..80) -> 64 kernel takes it (bf16 precision, bf16 tensors, shuffle 1); anything else returns B200SR_E_UNSUPPORTED.
+ * The residual is laid out like x.  b200sr_conv_tcgen05_ok() != 0 says that kernel would serve this conv (developer switch
+ * B200SR_CONV_IMPL=mma turns it off). */
+B200SR_API int b200sr_conv_forward_layout(const b200sr_conv_t *conv, const void *x_dev, int x_layout, int x_cstride, int x_coff, void *y_dev,
+                                          int y_layout, int y_cstride, int y_coff, const void *residual_dev, int r_cstride, int r_coff, int n,
+                                          int h, int w, int act, int shuffle, int in_dtype, int out_dtype, int precision, void *stream);
+B200SR_API int b200sr_conv_tcgen05_ok(const b200sr_conv_t *conv);
+
 /* F.interpolate(x, size=(oh,ow), mode='bilinear', align_corners) on NCHW, then (v - sub[c%4]) * mul[c%4]; y float32.
  * (models/spynet_arch.py:88-94 pre/post resize, normalisation :45-47; models/basicvsr_arch_origin.py:93) */
 B200SR_API int b200sr_resize_bilinear_nchw(const void *x_dev, int x_dtype, float *y_dev, int n, int c, int h, int w, int oh, int ow,

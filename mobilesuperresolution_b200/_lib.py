@@ -51,6 +51,9 @@ SYMBOLS = {
     "b200sr_flow_warp_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_conv_create": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, POINTER(c_void_p)]),
     "b200sr_conv_destroy": (None, [c_void_p]),
+    "b200sr_conv_forward_layout": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                                           c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sr_conv_tcgen05_ok": (c_int, [c_void_p]),
     "b200sr_conv_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_resize_bilinear_nchw": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -542,13 +542,18 @@ int b200sr_conv_create(int cin, int cout, int k, const float *w, const float *bi
         if (bias) bb[o] = bias[o];
     }
     int rc;
-    if (cin == 64 && cout == 64 && k == 3) {
-        // K-major core matrices [8-output-channel group][(tap, 8-input-channel chunk) slice][8 rows][16 B] (conv_tc5.cuh)
-        std::vector<uint16_t> wi((size_t)8 * 72 * 64, 0);
-        for (int o = 0; o < 64; ++o)
-            for (int i = 0; i < 64; ++i)
+    if (cin >= 64 && cin <= 80 && cout % 64 == 0 && cout <= 256 && k == 3) {
+        // per group of 64 output channels: K-major core matrices [8-output-channel group][(tap, 8-input-channel chunk) slice]
+        // [8 rows][16 B] (conv_tc5.cuh); 8 chunks for 64 input channels, 10 (zero rows past cin) for the trunk's first conv on
+        // [x_i | warped features]
+        const int nch = cin == 64 ? 8 : 10;
+        const size_t img = (size_t)8 * 9 * nch * 64;
+        std::vector<uint16_t> wi(img * (cout / 64), 0);
+        for (int o = 0; o < cout; ++o)
+            for (int i = 0; i < cin; ++i)
                 for (int t = 0; t < 9; ++t)
-                    wi[(((size_t)(o / 8) * 72 + t * 8 + i / 8) * 8 + o % 8) * 8 + i % 8] = f2bf(w[((size_t)o * 64 + i) * 9 + t]);
+                    wi[(o / 64) * img + (((size_t)(o % 64 / 8) * 9 * nch + t * nch + i / 8) * 8 + o % 8) * 8 + i % 8] =
+                        f2bf(w[((size_t)o * cin + i) * 9 + t]);
         if ((rc = upload(wi.data(), wi.size() * 2, (void **)&c->d_w_tc5))) {
             b200sr_conv_destroy(c);
             return rc;
@@ -572,18 +577,24 @@ void b200sr_conv_destroy(b200sr_conv_t *c) {
     delete c;
 }
 
-int b200sr_conv_forward(const b200sr_conv_t *c, const void *x, int x_cs, int x_co, void *y, int y_cs, int y_co, const void *res, int r_cs,
-                        int r_co, int n, int h, int w, int act, int shuffle, int in_dtype, int out_dtype, int precision, void *stream) {
+int b200sr_conv_tcgen05_ok(const b200sr_conv_t *c) { return c && c->d_w_tc5 && conv_tc5_enabled() ? 1 : 0; }
+
+int b200sr_conv_forward_layout(const b200sr_conv_t *c, const void *x, int x_layout, int x_cs, int x_co, void *y, int y_layout, int y_cs,
+                               int y_co, const void *res, int r_cs, int r_co, int n, int h, int w, int act, int shuffle, int in_dtype,
+                               int out_dtype, int precision, void *stream) {
     if (!c || !x || !y) return fail(B200SR_E_INVAL, "conv_forward: null argument");
     if (n <= 0 || h <= 0 || w <= 0) return fail(B200SR_E_INVAL, "conv_forward: bad shape");
     if (shuffle != 1 && shuffle != 2) return fail(B200SR_E_UNSUPPORTED, "conv_forward: shuffle %d (1 or 2)", shuffle);
     if (shuffle == 2 && (c->cout % 4)) return fail(B200SR_E_INVAL, "conv_forward: PixelShuffle(2) needs cout %% 4 == 0");
     if (act < 0 || act > 2) return fail(B200SR_E_INVAL, "conv_forward: bad activation %d", act);
-    if (x_co + c->cin > x_cs || y_co + (shuffle == 2 ? c->cout / 4 : c->cout) > y_cs) return fail(B200SR_E_INVAL, "conv_forward: channel window outside tensor");
+    const bool xp = x_layout == B200SR_TRUNK_PLANAR8, yp = y_layout == B200SR_TRUNK_PLANAR8;
+    if ((!xp && x_layout != B200SR_TRUNK_NHWC) || (!yp && y_layout != B200SR_TRUNK_NHWC)) return fail(B200SR_E_INVAL, "conv_forward: bad layout");
+    if ((!xp && x_co + c->cin > x_cs) || (!yp && y_co + (shuffle == 2 ? c->cout / 4 : c->cout) > y_cs))
+        return fail(B200SR_E_INVAL, "conv_forward: channel window outside tensor");
     ConvArgs a;
     a.x = x, a.y = y, a.residual = res, a.bias = c->d_bias;
     a.n = n, a.h = h, a.w_ = w, a.cin = c->cin, a.cout = c->cout, a.x_cs = x_cs, a.x_co = x_co, a.y_cs = y_cs, a.y_co = y_co, a.r_cs = r_cs,
-    a.r_co = r_co, a.act = act, a.shuffle = shuffle;
+    a.r_co = r_co, a.act = act, a.shuffle = shuffle, a.x_planar = xp, a.y_planar = yp;
     if (precision == B200SR_F32) {
         a.w = c->d_w_f32, a.cinp = c->cinp_f32, a.coutp = c->coutp_f32;
     } else {
@@ -592,12 +603,20 @@ int b200sr_conv_forward(const b200sr_conv_t *c, const void *x, int x_cs, int x_c
     if (precision == B200SR_BF16 && in_dtype == B200SR_BF16 && out_dtype == B200SR_BF16 && c->d_w_tc5 && conv_tc5_enabled() &&
         conv_tc5_eligible(a)) {
         cudaError_t e5 = launch_conv3x3_c64_tc5(a, c->d_w_tc5, (cudaStream_t)stream);
-        if (e5 != cudaSuccess) return cuda_fail(e5, "conv_forward (tcgen05 3x3 64->64)");
+        if (e5 != cudaSuccess) return cuda_fail(e5, "conv_forward (tcgen05 3x3 -> 64)");
         return 0;
     }
+    if (xp || yp)
+        return fail(B200SR_E_UNSUPPORTED, "conv_forward: the planar-8 layout is served by the tcgen05 3x3 (64..80) -> 64 bf16 kernel only");
     cudaError_t e = launch_conv(a, c->k, c->nt, in_dtype, out_dtype, precision, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "conv_forward (fp32 precision needs float32 tensors; bf16 precision: bf16|f32 in, bf16|f32 out)");
     return 0;
+}
+
+int b200sr_conv_forward(const b200sr_conv_t *c, const void *x, int x_cs, int x_co, void *y, int y_cs, int y_co, const void *res, int r_cs,
+                        int r_co, int n, int h, int w, int act, int shuffle, int in_dtype, int out_dtype, int precision, void *stream) {
+    return b200sr_conv_forward_layout(c, x, B200SR_TRUNK_NHWC, x_cs, x_co, y, B200SR_TRUNK_NHWC, y_cs, y_co, res, r_cs, r_co, n, h, w, act,
+                                      shuffle, in_dtype, out_dtype, precision, stream);
 }
 
 int b200sr_resize_bilinear_nchw(const void *x, int x_dtype, float *y, int n, int c, int h, int w, int oh, int ow, int align,

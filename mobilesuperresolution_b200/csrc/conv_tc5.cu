@@ -1,4 +1,4 @@
-// conv_tc5.cu -- launcher of the tcgen05 3x3 64 -> 64 convolution (BasicVSR trunks, conv_hr).
+// conv_tc5.cu -- launcher of the tcgen05 3x3 (64 | 65..80) -> 64 convolution (BasicVSR trunks, conv_hr).
 #include "conv_tc5.cuh"
 
 #include "launch.h"
@@ -6,64 +6,93 @@
 
 namespace b200sr {
 
-// NHWC bf16 activation window (64 channels starting at a 16-byte aligned offset inside pixels of `cs` channels) viewed as
-// 5-D (8 channels, 8 chunks, W, H, N); a box {8, 1, 32, 10, 1} lands as [row][pixel][16 B]; out-of-image pixels read as zero.
-static cudaError_t make_nhwc64_map(CUtensorMap *map, const void *base, int N, int H, int W, int cs) {
+// NHWC bf16 activation window (cin channels starting at a 16-byte aligned offset inside pixels of `cs` channels) viewed as
+// 4-D (cin, W, H, N); a box {8, 32, 10, 1} at channel 8c lands as [row][pixel][16 B]; out-of-image pixels and channels >= cin
+// read as zero.
+static cudaError_t make_nhwc_map(CUtensorMap *map, const void *base, int N, int H, int W, int cs, int cin) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return cudaErrorNotSupported;
-    const cuuint64_t dims[5] = {8, 8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    const cuuint64_t strides[4] = {16, (cuuint64_t)cs * 2, (cuuint64_t)W * cs * 2, (cuuint64_t)H * W * cs * 2};
-    const cuuint32_t box[5] = {8, 1, (cuuint32_t)tc5conv::BW, (cuuint32_t)tc5conv::BH, 1};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(base), dims, strides, box, estr,
+    const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)cs * 2, (cuuint64_t)W * cs * 2, (cuuint64_t)H * W * cs * 2};
+    const cuuint32_t box[4] = {8, (cuuint32_t)tc5conv::BW, (cuuint32_t)tc5conv::BH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+// planar-8 activation [N][8 planes][H][W][8 channels] viewed as 4-D (4 * W uint32, H, 8, N); a box {128, 10, 1, 1} is ten rows of
+// 512 contiguous bytes and lands as the same [row][pixel][16 B] image.
+static cudaError_t make_planar_map(CUtensorMap *map, const void *base, int N, int H, int W) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return cudaErrorNotSupported;
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 4, (cuuint64_t)H, 8, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)H * W * 128};
+    const cuuint32_t box[4] = {(cuuint32_t)tc5conv::BW * 4, (cuuint32_t)tc5conv::BH, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void *>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 bool conv_tc5_eligible(const ConvArgs &a) {
-    return a.cin == 64 && a.cout == 64 && a.shuffle == 1 && a.x_cs % 8 == 0 && a.x_co % 8 == 0 && a.y_cs % 8 == 0 && a.y_co % 8 == 0 &&
-           (!a.residual || (a.r_cs % 8 == 0 && a.r_co % 8 == 0)) && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 &&
-           (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.residual) & 15) == 0;
+    const auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (a.cout % 64 || a.cout > 256 || a.cin < 64 || a.cin > 80 || !al16(a.x) || !al16(a.y) || !al16(a.residual)) return false;
+    if (a.shuffle == 2 ? (a.residual || a.y_planar) : a.shuffle != 1) return false;
+    if (a.x_planar) {
+        if (a.cin != 64 || (a.residual && a.cout != 64)) return false;
+    } else if (a.x_cs % 8 || a.x_co % 8 || (a.residual && (a.r_cs % 8 || a.r_co % 8))) {
+        return false;
+    }
+    return a.y_planar ? a.cout == 64 : (a.y_cs % 8 == 0 && a.y_co % 8 == 0);
 }
 
-cudaError_t launch_conv3x3_c64_tc5(const ConvArgs &a, const uint8_t *wimg, cudaStream_t st) {
+template <int NCH>
+static cudaError_t launch_t(const ConvArgs &a, const CUtensorMap &map, const uint8_t *wimg, cudaStream_t st) {
     using namespace tc5conv;
-    // the recurrent trunks cycle through a handful of activation buffers: tensor maps are cached per (pointer, geometry)
-    struct MapKey { const void *p; int n, h, w, cs; CUtensorMap map; };
-    constexpr int NCACHE = 32;
-    static thread_local MapKey cache[NCACHE];
-    static thread_local int next_slot = 0;
-    const void *base = reinterpret_cast<const bf16 *>(a.x) + a.x_co;
-    const CUtensorMap *mapp = nullptr;
-    for (auto &c : cache)
-        if (c.p == base && c.n == a.n && c.h == a.h && c.w == a.w_ && c.cs == a.x_cs) { mapp = &c.map; break; }
-    cudaError_t e;
-    if (!mapp) {
-        MapKey &c = cache[next_slot++ % NCACHE];
-        e = make_nhwc64_map(&c.map, base, a.n, a.h, a.w_, a.x_cs);
-        if (e != cudaSuccess) { c.p = nullptr; return e; }
-        c.p = base, c.n = a.n, c.h = a.h, c.w = a.w_, c.cs = a.x_cs;
-        mapp = &c.map;
-    }
+    auto kern = conv3x3_c64_tc5_kernel<NCH>;
     static thread_local bool set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !set[dev]) {
-        e = cudaFuncSetAttribute(conv3x3_c64_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes());
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<NCH>::smem_bytes());
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) set[dev] = true;
     }
     const int tx = ceil_div(a.w_, TWO), ty = ceil_div(a.h, TH), ntiles = tx * ty * a.n;
-    int ctas = sm_count();
-    if (ctas > ntiles) ctas = ntiles;
+    const int G = a.cout / 64;                       // output-channel groups: a CTA serves one (conv_tc5.cuh)
+    int ctas = sm_count() / G * G;
+    if (ctas > ntiles * G) ctas = ntiles * G;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctas), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = smem_bytes(), cfg.stream = st;
+    cfg.gridDim = dim3(ctas), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<NCH>::smem_bytes(), cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv3x3_c64_tc5_kernel, *mapp, a, wimg, tx, ty, ntiles);
+    return cudaLaunchKernelEx(&cfg, kern, map, a, wimg, tx, ty, ntiles);
+}
+
+cudaError_t launch_conv3x3_c64_tc5(const ConvArgs &a, const uint8_t *wimg, cudaStream_t st) {
+    // the recurrent trunks cycle through a handful of activation buffers: tensor maps are cached per (pointer, geometry)
+    struct MapKey { const void *p; int n, h, w, cs, cin; CUtensorMap map; };
+    constexpr int NCACHE = 32;
+    static thread_local MapKey cache[NCACHE];
+    static thread_local int next_slot = 0;
+    const void *base = a.x_planar ? a.x : reinterpret_cast<const bf16 *>(a.x) + a.x_co;
+    const int cs = a.x_planar ? -1 : a.x_cs;
+    const CUtensorMap *mapp = nullptr;
+    for (auto &c : cache)
+        if (c.p == base && c.n == a.n && c.h == a.h && c.w == a.w_ && c.cs == cs && c.cin == a.cin) { mapp = &c.map; break; }
+    if (!mapp) {
+        MapKey &c = cache[next_slot++ % NCACHE];
+        cudaError_t e = a.x_planar ? make_planar_map(&c.map, base, a.n, a.h, a.w_) : make_nhwc_map(&c.map, base, a.n, a.h, a.w_, a.x_cs, a.cin);
+        if (e != cudaSuccess) { c.p = nullptr; return e; }
+        c.p = base, c.n = a.n, c.h = a.h, c.w = a.w_, c.cs = cs, c.cin = a.cin;
+        mapp = &c.map;
+    }
+    return a.cin == 64 ? launch_t<8>(a, *mapp, wimg, st) : launch_t<10>(a, *mapp, wimg, st);
 }
 
 }  // namespace b200sr

@@ -4,9 +4,11 @@
 //   y[n, oy, ox, co] = act( bias[co] + sum_{ky,kx,ci} x[n, oy+ky-1, ox+kx-1, ci] * w[co][ci][ky][kx] ) (+ residual)
 //
 // Same producer -> MMA -> epilogue chain as the WDSR tail (wdsr_tc5_tail.cuh), no builders: an implicit GEMM with pixels as M.
-//   warp 0      TMA      eight cp.async.bulk.tensor.5d per tile (one per 8-channel chunk) of a 32 x 10 pixel box (30 x 8 outputs +
-//                        1-pixel halo) into chunk-planar shared memory [chunk][pixel][16 B]; out-of-image pixels are zero-filled
-//                        by the TMA unit (= the conv's zero padding); three tile buffers
+//   warp 0      TMA      NCH cp.async.bulk.tensor.4d per tile (one per 8-channel chunk) of a 32 x 10 pixel box (30 x 8 outputs +
+//                        1-pixel halo) into chunk-planar shared memory [chunk][pixel][16 B]; out-of-image pixels (and channels past
+//                        cin) are zero-filled by the TMA unit (= the conv's zero padding); three (two for NCH = 10) tile buffers.
+//                        x is NHWC (every 16-byte pixel row of a chunk is its own TMA request: 320 per chunk) or planar-8
+//                        [n][c/8][h][w][8] (a box row is 512 contiguous bytes: 10 requests per chunk) -- the trunk's private tensors
 //   warp 1      MMA      per 128-pixel M-tile (four 32-pixel box rows) 36 tcgen05.mma (M = 128, N = 64, K = 16): a tap is a constant
 //                        pixel offset of the A operand's start address (the two box columns right of the 30 outputs compute
 //                        don't-care rows), the two 8-channel chunks of a K step are paired through the LBO stride
@@ -22,29 +24,34 @@
 
 namespace b200sr {
 namespace tc5conv {
-constexpr int TWO = 30, TH = 8, BW = 32, BH = TH + 2, NCH = 8, NTHREADS = 320;
+constexpr int TWO = 30, TH = 8, BW = 32, BH = TH + 2, NTHREADS = 320;
 constexpr int PLANE_PX = BW * BH + 8;            // + 8 zero pixels: the last taps of the second M-tile read past the box
 constexpr int PLANE = PLANE_PX * 16;             // 5,248 B
-constexpr int TILE_BUF = NCH * PLANE;            // 41,984 B
-constexpr int NBUF = 3;
-constexpr int W_SBO = 72 * 128;                  // weight image [8 row groups][72 (tap, chunk) slices][8 rows][16 B]
-constexpr int W_BYTES = 8 * W_SBO;               // 73,728 B
 constexpr int CTRL = 256;
 enum Bar { TC_FULL = 0 /*3*/, TC_EMPTY = 3 /*3*/, D_FULL = 6, D_EMPTY = 8, NBARS = 10 };
-constexpr size_t smem_bytes() { return (size_t)CTRL + NBUF * TILE_BUF + W_BYTES + 256; }
+// NCH = 8-channel chunks of the input: 8 (64 channels) or 10 (65..80 channels: the trunk's first conv on [x_i | warped feat])
+template <int NCH> struct Cfg {
+    static constexpr int TILE_BUF = NCH * PLANE;            // 41,984 / 52,480 B
+    static constexpr int NBUF = NCH <= 8 ? 3 : 2;
+    static constexpr int W_SBO = 9 * NCH * 128;             // weight image [8 row groups][9 * NCH (tap, chunk) slices][8 rows][16 B]
+    static constexpr int W_BYTES = 8 * W_SBO;               // 73,728 / 92,160 B
+    static constexpr size_t smem_bytes() { return (size_t)CTRL + NBUF * TILE_BUF + W_BYTES + 256; }
+};
 }  // namespace tc5conv
 
-__device__ __forceinline__ void tma_load_5d_conv(uint32_t dst_saddr, const void *tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+__device__ __forceinline__ void tma_load_4d_conv(uint32_t dst_saddr, const void *tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(dst_saddr), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst_saddr), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(tc5conv::NTHREADS, 1)
 conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, const uint8_t *__restrict__ wimg, int tiles_x, int tiles_y,
                        int ntiles) {
     using namespace tc5conv;
+    constexpr int TILE_BUF = Cfg<NCH>::TILE_BUF, NBUF = Cfg<NCH>::NBUF, W_SBO = Cfg<NCH>::W_SBO, W_BYTES = Cfg<NCH>::W_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *ctrl = smem_raw;
     uint8_t *tc = smem_raw + CTRL;           // NBUF x TILE_BUF
@@ -73,9 +80,13 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
     }
     __syncwarp();
     if (warp == 0) tc5::tmem_alloc(smem_u32(ctrl + 240), 128);
+    // cout = 64 G: output-channel group `grp` (its own weight image and bias slice) is fixed per CTA, the spatial tiles of a group
+    // are dealt round-robin to the group's CTAs (gridDim.x is a multiple of G)
+    const int G = a.cout >> 6, grp = (int)blockIdx.x % G, rank = (int)blockIdx.x / G, nranks = (int)gridDim.x / G;
+    wimg += (size_t)grp * W_BYTES;
     for (int i = tid; i < W_BYTES / 16; i += NTHREADS) cp_async16(wsm + i * 16, wimg + i * 16, 16);
     cp_async_commit();
-    if (tid < 64) bias_s[tid] = a.bias[tid];
+    if (tid < 64) bias_s[tid] = a.bias[grp * 64 + tid];
     for (int i = tid; i < NBUF * NCH * 8; i += NTHREADS)   // the 8 pad pixels of every plane stay zero (TMA never writes them)
         *reinterpret_cast<uint4 *>(tc + (i / 8) * PLANE + (BW * BH + i % 8) * 16) = make_uint4(0u, 0u, 0u, 0u);
     cp_async_wait<0>();
@@ -84,9 +95,9 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
     __syncthreads();
     tc5::fence_after_sync();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t *>(ctrl + 240);
-    const int nmine = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nmine = rank < ntiles ? (ntiles - 1 - rank) / nranks + 1 : 0;
     auto tile_origin = [&](int it, int &x0, int &y0, int &n) {
-        const int tile = blockIdx.x + it * gridDim.x;
+        const int tile = rank + it * nranks;
         x0 = (tile % tiles_x) * TWO;
         y0 = ((tile / tiles_x) % tiles_y) * TH;
         n = tile / (tiles_x * tiles_y);
@@ -103,7 +114,11 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
                 tc5::mbar_wait(bar(TC_EMPTY + b), ((it / NBUF) & 1) ^ 1);
                 tc5::mbar_arrive_expect_tx(bar(TC_FULL + b), NCH * BW * BH * 16);
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) tma_load_5d_conv(tc_u + b * TILE_BUF + c * PLANE, &tmap_x, bar(TC_FULL + b), 0, c, x0 - 1, y0 - 1, n);
+                for (int c = 0; c < NCH; ++c) {
+                    const uint32_t dst = tc_u + b * TILE_BUF + c * PLANE;
+                    if (a.x_planar) tma_load_4d_conv(dst, &tmap_x, bar(TC_FULL + b), 4 * (x0 - 1), y0 - 1, c, n);   // (uint32 of a row, row, plane, image)
+                    else tma_load_4d_conv(dst, &tmap_x, bar(TC_FULL + b), 8 * c, x0 - 1, y0 - 1, n);                 // (channel, x, y, image)
+                }
             }
         }
         __syncwarp();
@@ -121,10 +136,10 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
                 const uint32_t d = tmem + e * 64;
                 const uint64_t abase = a0d + (uint64_t)((b * TILE_BUF + m * 128 * 16) >> 4);
 #pragma unroll
-                for (int i = 0; i < 36; ++i) {   // (tap t = i / 4, chunks 2 (i % 4), 2 (i % 4) + 1)
-                    const int t = i >> 2, cp = i & 3, dy = t / 3, dx = t % 3;
+                for (int i = 0; i < 9 * (NCH / 2); ++i) {   // (tap t, chunks 2 cp, 2 cp + 1)
+                    const int t = i / (NCH / 2), cp = i % (NCH / 2), dy = t / 3, dx = t % 3;
                     const int aoff = 2 * cp * PLANE + (dy * BW + dx) * 16;
-                    tc5::mma_ss(d, abase + (uint64_t)(aoff >> 4), bw + (uint64_t)(16 * i), idesc, i > 0);
+                    tc5::mma_ss(d, abase + (uint64_t)(aoff >> 4), bw + (uint64_t)(8 * (t * NCH + 2 * cp)), idesc, i > 0);
                 }
                 tc5::commit(bar(D_FULL + e));
                 if (m == 1) tc5::commit(bar(TC_EMPTY + b));
@@ -148,36 +163,56 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
             const int gy = y0 + by, gx = x0 + bx;
             const bool ok = bx < TWO && gx < W && gy < H;
             const long long pix = ((long long)n * H + gy) * W + gx;
+            const long long hw = (long long)H * W, ppix = (long long)n * 8 * hw + (long long)gy * W + gx;   // planar-8: [n][q][H][W][8]
             uint4 rv[8];
-            if (res && ok) {   // residual of this pixel: in flight while the accumulator is waited for
-                const uint4 *rp = reinterpret_cast<const uint4 *>(res + pix * a.r_cs + a.r_co);
+            if (res && ok) {   // residual of this pixel (laid out like x): in flight while the accumulator is waited for
+                const uint4 *rp = reinterpret_cast<const uint4 *>(a.x_planar ? res + ppix * 8 : res + pix * a.r_cs + a.r_co + 64 * grp);
+                const long long rstep = a.x_planar ? hw : 1;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) rv[q] = __ldg(rp + q);
+                for (int q = 0; q < 8; ++q) rv[q] = __ldg(rp + q * rstep);
             }
             tc5::mbar_wait(bar(D_FULL + e), it & 1);
             tc5::fence_after_sync();
-            uint32_t v[64];
-            tc5::tmem_ld32(tmem + lane_base + e * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-            tc5::tmem_ld32(tmem + lane_base + e * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-            tc5::tmem_wait_ld();
-            tc5::fence_before_sync();
-            tc5::mbar_arrive_relaxed(bar(D_EMPTY + e));
-            if (ok) {
-                uint4 *yp = reinterpret_cast<uint4 *>(y + pix * a.y_cs + a.y_co);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float f[8];
+            for (int hh = 0; hh < 2; ++hh) {   // the accumulator row in two halves of 32 channels (register budget)
+                uint32_t v[32];
+                tc5::tmem_ld32(tmem + lane_base + e * 64 + 32 * hh, v);
+                tc5::tmem_wait_ld();
+                if (hh == 1) {
+                    tc5::fence_before_sync();
+                    tc5::mbar_arrive_relaxed(bar(D_EMPTY + e));
+                }
+                if (ok && a.shuffle == 2) {
+                    // PixelShuffle(2) in the store: channel co = 64 grp + c goes to sub-pixel (i, j) = ((c >> 1) & 1, c & 1), channel
+                    // co / 4 -- this half's 32 channels are 8 contiguous channels (16 bytes) of each of the four HR pixels
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] = apply_act(__uint_as_float(v[q * 8 + j]) + bias_s[q * 8 + j], act);
-                    if (res) {
-                        const uint32_t *rw = reinterpret_cast<const uint32_t *>(&rv[q]);
+                    for (int sub = 0; sub < 4; ++sub) {
+                        const long long hp = ((long long)n * 2 * H + 2 * gy + (sub >> 1)) * (2 * W) + 2 * gx + (sub & 1);
+                        float f[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 r2 = unpack_bf16x2(rw[j]);
-                            f[2 * j] += r2.x, f[2 * j + 1] += r2.y;
-                        }
+                        for (int j = 0; j < 8; ++j) f[j] = apply_act(__uint_as_float(v[4 * j + sub]) + bias_s[32 * hh + 4 * j + sub], act);
+                        *reinterpret_cast<uint4 *>(y + hp * a.y_cs + a.y_co + 16 * grp + 8 * hh) =
+                            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
                     }
-                    yp[q] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                } else if (ok) {
+                    uint4 *yp = reinterpret_cast<uint4 *>(a.y_planar ? y + ppix * 8 : y + pix * a.y_cs + a.y_co + 64 * grp);
+                    const long long ystep = a.y_planar ? hw : 1;
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int q = 4 * hh + q4;
+                        float f[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = apply_act(__uint_as_float(v[q4 * 8 + j]) + bias_s[q * 8 + j], act);
+                        if (res) {
+                            const uint32_t *rw = reinterpret_cast<const uint32_t *>(&rv[q]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 r2 = unpack_bf16x2(rw[j]);
+                                f[2 * j] += r2.x, f[2 * j + 1] += r2.y;
+                            }
+                        }
+                        yp[q * ystep] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                    }
                 }
             }
         }

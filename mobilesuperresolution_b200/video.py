@@ -90,19 +90,30 @@ class _ConvHandle:
             except Exception:
                 pass
 
+    def tcgen05_ok(self) -> bool:
+        """True when the tcgen05 3x3 (64..80) -> 64 kernel serves this conv in bf16 (the only kernel that takes planar-8 tensors)."""
+        return bool(_lib.lib().b200sr_conv_tcgen05_ok(self._h))
+
     def __call__(self, x: torch.Tensor, precision: str, act: int = ACT_NONE, x_coff: int = 0, out: Optional[torch.Tensor] = None,
                  y_coff: int = 0, residual: Optional[torch.Tensor] = None, shuffle: int = 1,
-                 out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-        n, h, w, xcs = x.shape
+                 out_dtype: Optional[torch.dtype] = None, x_planar: bool = False, y_planar: bool = False) -> torch.Tensor:
+        """NHWC tensors (n,h,w,c); ``x_planar`` / ``y_planar``: planar-8 tensors (n,8,h,w,8) instead (the residual follows x)."""
         assert x.is_contiguous()
+        if x_planar:
+            n, _, h, w, _ = x.shape
+            xcs = 64
+        else:
+            n, h, w, xcs = x.shape
         if out is None:
             oc = self.cout // (shuffle * shuffle)
-            out = torch.empty((n, h * shuffle, w * shuffle, oc), dtype=out_dtype or x.dtype, device=x.device)
-        ycs = out.shape[-1]
-        rcs = residual.shape[-1] if residual is not None else 0
+            shape = (n, 8, h, w, 8) if y_planar else (n, h * shuffle, w * shuffle, oc)
+            out = torch.empty(shape, dtype=out_dtype or x.dtype, device=x.device)
+        ycs = 64 if y_planar else out.shape[-1]
+        rcs = 0 if residual is None else 64 if x_planar else residual.shape[-1]
         with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().b200sr_conv_forward(
-                self._h, _ptr(x), xcs, x_coff, _ptr(out), ycs, y_coff, _ptr(residual) if residual is not None else None, rcs, 0,
+            _lib.check(_lib.lib().b200sr_conv_forward_layout(
+                self._h, _ptr(x), int(x_planar), xcs, x_coff, _ptr(out), int(y_planar), ycs, y_coff,
+                _ptr(residual) if residual is not None else None, rcs, 0,
                 n, h, w, act, shuffle, _lib.dtype_code(x.dtype), _lib.dtype_code(out.dtype), _lib.precision_code(precision),
                 _lib.current_stream_ptr(x.device)))
         return out
@@ -266,10 +277,16 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
         return flows_forward, flows_backward
 
     def _trunk(self, convs, name: str, buf: torch.Tensor, num_block: int) -> torch.Tensor:
-        t = convs[f"{name}.main.0"](buf, self.precision, ACT_LRELU, out_dtype=self._act_dtype())
+        first = convs[f"{name}.main.0"]
+        # bf16 on the tcgen05 kernel: the trunk's private 64-channel tensors live in the planar-8 layout (TMA box rows of 512
+        # contiguous bytes instead of one request per pixel and chunk); the last conv writes the NHWC features the callers read
+        planar = (self.precision != "fp32" and num_block > 0 and buf.dtype == torch.bfloat16 and first.cout == 64 and first.tcgen05_ok()
+                  and convs[f"{name}.main.2.0.conv1"].tcgen05_ok())
+        t = first(buf, self.precision, ACT_LRELU, out_dtype=self._act_dtype(), y_planar=planar)
         for k in range(num_block):
-            o = convs[f"{name}.main.2.{k}.conv1"](t, self.precision, ACT_RELU)
-            t = convs[f"{name}.main.2.{k}.conv2"](o, self.precision, ACT_NONE, residual=t)
+            o = convs[f"{name}.main.2.{k}.conv1"](t, self.precision, ACT_RELU, x_planar=planar, y_planar=planar)
+            t = convs[f"{name}.main.2.{k}.conv2"](o, self.precision, ACT_NONE, residual=t, x_planar=planar,
+                                                  y_planar=planar and k + 1 < num_block)
         return t
 
     def propagate(self, x: torch.Tensor, flows_forward: torch.Tensor, flows_backward: torch.Tensor):
@@ -282,11 +299,12 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
         nb = len(self.backward_trunk.main[2])
         cs = -(-(nf + 3) // 16) * 16
         x = x.contiguous()
-        L, st = _lib.lib(), _lib.current_stream_ptr(dev)
+        L = _lib.lib()
 
         def run(trunk: str, order, flows, flow_index):
             feats: List[Optional[torch.Tensor]] = [None] * n
             feat = None
+            st = _lib.current_stream_ptr(dev)   # the stream this direction was forked onto
             for step, i in enumerate(order):
                 buf = torch.zeros((b, h, w, cs), dtype=adt, device=dev)
                 xi = x[:, i]
@@ -300,9 +318,25 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
                 feats[i] = feat
             return feats
 
+        # the two directions are independent recurrences of small launches (one 180x320 frame is 253 tiles on 148 SMs): the
+        # forward one runs on a side stream (fork / join by events, CUDA-graph capturable) so that they fill each other's tails
+        main = torch.cuda.current_stream(dev)
+        side = self._side_stream(dev)
+        side.wait_stream(main)
         back = run("backward_trunk", range(n - 1, -1, -1), flows_backward, lambda i: i)
-        fwd = run("forward_trunk", range(0, n), flows_forward, lambda i: i - 1)
+        with torch.cuda.stream(side):
+            fwd = run("forward_trunk", range(0, n), flows_forward, lambda i: i - 1)
+        main.wait_stream(side)
+        for f in fwd:
+            f.record_stream(main)
         return back, fwd
+
+    def _side_stream(self, dev) -> "torch.cuda.Stream":
+        key = str(dev)
+        cache = self.__dict__.setdefault("_side_streams", {})
+        if key not in cache:
+            cache[key] = torch.cuda.Stream(device=dev)
+        return cache[key]
 
 
 class BasicVSR_origin(_VsrBase):

@@ -217,3 +217,84 @@ def test_conv3x3_c64_tcgen05_channel_windows(V):
     o = out.float().cpu()
     assert float((o[..., 8:72].permute(0, 3, 1, 2) - ref).abs().max()) <= 0.05
     assert float((o[..., :8] - 3).abs().max()) == 0 and float((o[..., 72:] - 3).abs().max()) == 0
+
+
+def _to_planar8(t):   # (n,h,w,64) -> (n,8,h,w,8)
+    n, h, w, _ = t.shape
+    return t.view(n, h, w, 8, 8).permute(0, 3, 1, 2, 4).contiguous()
+
+
+def _from_planar8(t):
+    n, _, h, w, _ = t.shape
+    return t.permute(0, 2, 3, 1, 4).reshape(n, h, w, 64)
+
+
+@pytest.mark.parametrize("xp,yp", [(True, True), (True, False), (False, True)])
+def test_conv3x3_c64_tcgen05_planar8(V, xp, yp):
+    """Planar-8 [n][c/8][h][w][8] input (+ residual) / output of the tcgen05 conv: bit-identical to its NHWC form."""
+    g = torch.Generator().manual_seed(5)
+    conv = nn.Conv2d(64, 64, 3, 1, 1)
+    hd = V._ConvHandle(conv, torch.device("cuda:0"))
+    assert hd.tcgen05_ok()
+    x = torch.randn(2, 27, 65, 64, generator=g).bfloat16().cuda()
+    r = torch.randn(2, 27, 65, 64, generator=g).bfloat16().cuda()
+    ref = hd(x, "bf16", V.ACT_LRELU, residual=r)
+    y = hd(_to_planar8(x) if xp else x, "bf16", V.ACT_LRELU, residual=_to_planar8(r) if xp else r, x_planar=xp, y_planar=yp)
+    y = _from_planar8(y) if yp else y
+    assert torch.equal(y, ref)
+
+
+def test_conv3x3_c67_tcgen05_first_trunk_conv(V, monkeypatch):
+    """The trunk's first conv (67 -> 64 on [x_i | warped features | pad], models/basicvsr_arch_origin.py:69-70,104): channels past
+    cin are clipped by the tensor map, so whatever the pad channels hold (NaN here) never reaches the MMA."""
+    g = torch.Generator().manual_seed(9)
+    conv = nn.Conv2d(67, 64, 3, 1, 1)
+    hd = V._ConvHandle(conv, torch.device("cuda:0"))
+    assert hd.tcgen05_ok()
+    x = torch.randn(2, 23, 41, 80, generator=g).bfloat16()
+    x[..., 67:] = float("nan")
+    xd = x.cuda()
+    y = hd(xd, "bf16", V.ACT_LRELU)
+    yp = _from_planar8(hd(xd, "bf16", V.ACT_LRELU, y_planar=True))
+    with torch.no_grad():
+        ref = F.leaky_relu(F.conv2d(x[..., :67].permute(0, 3, 1, 2).double(), conv.weight.bfloat16().double(), conv.bias.double(), padding=1), 0.1)
+    yf = y.float().cpu().permute(0, 3, 1, 2).double()
+    tol = 2.0 ** -8 * ref.abs().clamp_min(1.0) + 1e-3
+    assert bool(((yf - ref).abs() <= tol).all()), float((yf - ref).abs().max())
+    assert torch.equal(y, yp)
+
+
+def test_conv_planar8_needs_tcgen05(V, monkeypatch):
+    """Planar-8 is served by the tcgen05 kernel only: asking the other kernels for it fails loudly (no silent re-layout)."""
+    conv = nn.Conv2d(64, 64, 3, 1, 1)
+    hd = V._ConvHandle(conv, torch.device("cuda:0"))
+    x = torch.zeros(1, 8, 9, 9, 8, dtype=torch.bfloat16, device="cuda")
+    monkeypatch.setenv("B200SR_CONV_IMPL", "mma")
+    assert not hd.tcgen05_ok()
+    with pytest.raises(RuntimeError):
+        hd(x, "bf16", V.ACT_NONE, x_planar=True, y_planar=True)
+
+
+@pytest.mark.parametrize("cout,shuffle", [(256, 2), (256, 1), (128, 1)])
+def test_conv3x3_tcgen05_output_channel_groups(V, cout, shuffle, monkeypatch):
+    """upconv1 / upconv2 (64 -> 256 + PixelShuffle(2) + LeakyReLU, models/basicvsr_arch_origin.py:87-88): one CTA per group of 64
+    output channels, the shuffle folded into the store.  Against torch fp64 on the bf16 operands and the mma.sync kernel."""
+    g = torch.Generator().manual_seed(cout + shuffle)
+    conv = nn.Conv2d(64, cout, 3, 1, 1)
+    hd = V._ConvHandle(conv, torch.device("cuda:0"))
+    assert hd.tcgen05_ok()
+    x = torch.randn(2, 21, 47, 64, generator=g).bfloat16()
+    res = torch.randn(2, 21, 47, cout, generator=g).bfloat16() if shuffle == 1 else None
+    with torch.no_grad():
+        ref = F.leaky_relu(F.conv2d(x.permute(0, 3, 1, 2).double(), conv.weight.bfloat16().double(), conv.bias.double(), padding=1), 0.1)
+        ref = F.pixel_shuffle(ref, 2) if shuffle == 2 else ref + res.permute(0, 3, 1, 2).double()
+    xd, rd = x.cuda(), (res.cuda() if res is not None else None)
+    y = hd(xd, "bf16", V.ACT_LRELU, shuffle=shuffle, residual=rd)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("B200SR_CONV_IMPL", "mma")
+    y_mma = hd(xd, "bf16", V.ACT_LRELU, shuffle=shuffle, residual=rd)
+    torch.cuda.synchronize()
+    yf = y.float().cpu().permute(0, 3, 1, 2).double()
+    tol = 2.0 ** -8 * ref.abs().clamp_min(1.0) + 1e-3
+    assert bool(((yf - ref).abs() <= tol).all()), float((yf - ref).abs().max())
+    assert float((y.float() - y_mma.float()).abs().max()) <= 2.0 ** -6 * float(ref.abs().max())

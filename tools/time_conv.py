@@ -25,13 +25,18 @@ for (n, h, w) in [(1, 180, 320), (2, 180, 320), (8, 180, 320), (1, 720, 1280)]:
     x = torch.randn(n, h, w, 64, device=dev).bfloat16()
     y = torch.empty_like(x); z = torch.empty_like(x)
     flop = n * h * w * 64 * 64 * 9 * 2
-    for impl in ("tc5", "mma"):
-        os.environ["B200SR_CONV_IMPL"] = impl
+    for impl in ("tc5-planar8", "tc5", "mma"):
+        os.environ["B200SR_CONV_IMPL"] = impl[:3]
+        pl = impl.endswith("planar8")
+        if pl:
+            x, y, z = (t.view(n, 8, h, w, 8) for t in (x, y, z))   # same bytes, read as planar-8
+        else:
+            x, y, z = (t.view(n, h, w, 64) for t in (x, y, z))
         def chain():
             a, b = x, y
             for k in range(30):
-                hd(a, "bf16", video.ACT_RELU, out=z)
-                hd(z, "bf16", video.ACT_NONE, out=b, residual=a)
+                hd(a, "bf16", video.ACT_RELU, out=z, x_planar=pl, y_planar=pl)
+                hd(z, "bf16", video.ACT_NONE, out=b, residual=a, x_planar=pl, y_planar=pl)
                 a, b = b, (y if b is x else x)
         us = timeit(chain, reps=5, warm=2) / 60
         g = torch.cuda.CUDAGraph()
