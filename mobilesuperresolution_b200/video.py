@@ -272,8 +272,12 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
         x_1 = x[:, :-1].reshape(-1, c, h, w)
         x_2 = x[:, 1:].reshape(-1, c, h, w)
         self.spynet.set_precision(self.precision)
-        flows_backward = self.spynet(x_1, x_2).view(b, n - 1, 2, h, w)
-        flows_forward = self.spynet(x_2, x_1).view(b, n - 1, 2, h, w)
+        # the reference's two SPyNet calls (x_1 -> x_2, x_2 -> x_1) as ONE batch of 2 b (n-1) pairs: every op is per sample, so the
+        # flows are the same numbers, and the launch-bound coarse pyramid levels run once instead of twice
+        flows = self.spynet(torch.cat([x_1, x_2], 0), torch.cat([x_2, x_1], 0))
+        m = b * (n - 1)
+        flows_backward = flows[:m].view(b, n - 1, 2, h, w)
+        flows_forward = flows[m:].view(b, n - 1, 2, h, w)
         return flows_forward, flows_backward
 
     def _trunk(self, convs, name: str, buf: torch.Tensor, num_block: int) -> torch.Tensor:

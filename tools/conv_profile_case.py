@@ -1,0 +1,18 @@
+"""The tcgen05 3x3 64->64 convolution launches profiled in profiles/r01_conv_tc5_ncu.md: conv_hr shape 1 x 720 x 1280 (NHWC and planar-8)
+and one BasicVSR trunk frame 1 x 180 x 320 (planar-8), bf16, LeakyReLU / residual epilogues."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn as nn
+from mobilesuperresolution_b200 import video
+torch.set_grad_enabled(False)
+dev = torch.device("cuda")
+hd = video._ConvHandle(nn.Conv2d(64, 64, 3, 1, 1), dev)
+for (n, h, w) in [(1, 720, 1280), (1, 180, 320)]:
+    x = torch.randn(n, h, w, 64, device=dev).bfloat16()
+    r = torch.randn(n, h, w, 64, device=dev).bfloat16()
+    xp, rp = x.view(n, 8, h, w, 8), r.view(n, 8, h, w, 8)
+    for _ in range(3):
+        hd(x, "bf16", video.ACT_LRELU)                                   # NHWC -> NHWC (conv_hr)
+        hd(xp, "bf16", video.ACT_NONE, residual=rp, x_planar=True, y_planar=True)   # planar-8 trunk conv2 (+ residual)
+torch.cuda.synchronize()
