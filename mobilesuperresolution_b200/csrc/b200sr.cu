@@ -559,6 +559,21 @@ int b200sr_conv_create(int cin, int cout, int k, const float *w, const float *bi
             return rc;
         }
     }
+    if (k == 7 && conv7_tc5_shape_ok(cin, cout)) {
+        // [7 tap rows ky][cout/8 row groups][7 taps kx x nch chunks][8 rows][16 B]: one contiguous stage per tap row (conv7_tc5.cuh)
+        const int nch = conv7_tc5_nch(cin);
+        std::vector<uint16_t> wi((size_t)7 * (cout / 8) * 7 * nch * 64, 0);
+        for (int o = 0; o < cout; ++o)
+            for (int i = 0; i < cin; ++i)
+                for (int ky = 0; ky < 7; ++ky)
+                    for (int kx = 0; kx < 7; ++kx)
+                        wi[(((((size_t)ky * (cout / 8) + o / 8) * 7 + kx) * nch + i / 8) * 8 + o % 8) * 8 + i % 8] =
+                            f2bf(w[((size_t)o * cin + i) * 49 + ky * 7 + kx]);
+        if ((rc = upload(wi.data(), wi.size() * 2, (void **)&c->d_w_tc5))) {
+            b200sr_conv_destroy(c);
+            return rc;
+        }
+    }
     if ((rc = upload(wf.data(), wf.size() * 4, (void **)&c->d_w_f32)) || (rc = upload(wb.data(), wb.size() * 2, (void **)&c->d_w_bf16)) ||
         (rc = upload(bb.data(), bb.size() * 4, (void **)&c->d_bias))) {
         b200sr_conv_destroy(c);
@@ -588,6 +603,7 @@ int b200sr_conv_forward_layout(const b200sr_conv_t *c, const void *x, int x_layo
     if (shuffle == 2 && (c->cout % 4)) return fail(B200SR_E_INVAL, "conv_forward: PixelShuffle(2) needs cout %% 4 == 0");
     if (act < 0 || act > 2) return fail(B200SR_E_INVAL, "conv_forward: bad activation %d", act);
     const bool xp = x_layout == B200SR_TRUNK_PLANAR8, yp = y_layout == B200SR_TRUNK_PLANAR8;
+    if ((xp && c->cin % 8) || (yp && c->cout % 8)) return fail(B200SR_E_INVAL, "conv_forward: planar-8 needs channel counts that are multiples of 8");
     if ((!xp && x_layout != B200SR_TRUNK_NHWC) || (!yp && y_layout != B200SR_TRUNK_NHWC)) return fail(B200SR_E_INVAL, "conv_forward: bad layout");
     if ((!xp && x_co + c->cin > x_cs) || (!yp && y_co + (shuffle == 2 ? c->cout / 4 : c->cout) > y_cs))
         return fail(B200SR_E_INVAL, "conv_forward: channel window outside tensor");
@@ -600,14 +616,20 @@ int b200sr_conv_forward_layout(const b200sr_conv_t *c, const void *x, int x_layo
     } else {
         a.w = c->d_w_bf16, a.cinp = c->cinp_bf16, a.coutp = c->coutp_bf16;
     }
-    if (precision == B200SR_BF16 && in_dtype == B200SR_BF16 && out_dtype == B200SR_BF16 && c->d_w_tc5 && conv_tc5_enabled() &&
+    if (precision == B200SR_BF16 && in_dtype == B200SR_BF16 && out_dtype == B200SR_BF16 && c->d_w_tc5 && conv_tc5_enabled() && c->k == 7 &&
+        conv7_tc5_eligible(a)) {
+        cudaError_t e7 = launch_conv7x7_tc5(a, c->d_w_tc5, (cudaStream_t)stream);
+        if (e7 != cudaSuccess) return cuda_fail(e7, "conv_forward (tcgen05 7x7)");
+        return 0;
+    }
+    if (precision == B200SR_BF16 && in_dtype == B200SR_BF16 && out_dtype == B200SR_BF16 && c->d_w_tc5 && conv_tc5_enabled() && c->k == 3 &&
         conv_tc5_eligible(a)) {
         cudaError_t e5 = launch_conv3x3_c64_tc5(a, c->d_w_tc5, (cudaStream_t)stream);
         if (e5 != cudaSuccess) return cuda_fail(e5, "conv_forward (tcgen05 3x3 -> 64)");
         return 0;
     }
     if (xp || yp)
-        return fail(B200SR_E_UNSUPPORTED, "conv_forward: the planar-8 layout is served by the tcgen05 3x3 (64..80) -> 64 bf16 kernel only");
+        return fail(B200SR_E_UNSUPPORTED, "conv_forward: the planar-8 layout is served by the tcgen05 bf16 kernels only (3x3 64 -> 64, SPyNet 7x7 layers)");
     cudaError_t e = launch_conv(a, c->k, c->nt, in_dtype, out_dtype, precision, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "conv_forward (fp32 precision needs float32 tensors; bf16 precision: bf16|f32 in, bf16|f32 out)");
     return 0;

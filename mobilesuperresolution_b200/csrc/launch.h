@@ -43,6 +43,11 @@ cudaError_t launch_conv(const ConvArgs &a, int k, int nt, int in_dtype, int out_
 // tcgen05 3x3 64 -> 64 bf16 NHWC convolution (conv_tc5.cuh): wimg = its operand image; eligibility = channel windows 16-byte aligned
 bool conv_tc5_eligible(const ConvArgs &a);
 cudaError_t launch_conv3x3_c64_tc5(const ConvArgs &a, const uint8_t *wimg, cudaStream_t st);
+// tcgen05 7x7 bf16 convolution (conv7_tc5.cuh; SPyNet layers): wimg = [7 tap rows][stage image]
+int conv7_tc5_nch(int cin);
+bool conv7_tc5_shape_ok(int cin, int cout);
+bool conv7_tc5_eligible(const ConvArgs &a);
+cudaError_t launch_conv7x7_tc5(const ConvArgs &a, const uint8_t *wimg, cudaStream_t st);
 // video glue (video_glue.cu)
 cudaError_t launch_resize_bilinear_nchw(const void *x, int x_dtype, float *y, int n, int c, int h, int w, int oh, int ow, int align,
                                         const float *sub4, const float *mul4, cudaStream_t st);

@@ -91,25 +91,26 @@ class _ConvHandle:
                 pass
 
     def tcgen05_ok(self) -> bool:
-        """True when the tcgen05 3x3 (64..80) -> 64 kernel serves this conv in bf16 (the only kernel that takes planar-8 tensors)."""
+        """True when a tcgen05 kernel (3x3 (64..80) -> 64 k, SPyNet 7x7 layers) serves this conv in bf16 -- the only kernels that take
+        planar-8 tensors."""
         return bool(_lib.lib().b200sr_conv_tcgen05_ok(self._h))
 
     def __call__(self, x: torch.Tensor, precision: str, act: int = ACT_NONE, x_coff: int = 0, out: Optional[torch.Tensor] = None,
                  y_coff: int = 0, residual: Optional[torch.Tensor] = None, shuffle: int = 1,
                  out_dtype: Optional[torch.dtype] = None, x_planar: bool = False, y_planar: bool = False) -> torch.Tensor:
-        """NHWC tensors (n,h,w,c); ``x_planar`` / ``y_planar``: planar-8 tensors (n,8,h,w,8) instead (the residual follows x)."""
+        """NHWC tensors (n,h,w,c); ``x_planar`` / ``y_planar``: planar-8 tensors (n,c/8,h,w,8) instead (the residual follows x)."""
         assert x.is_contiguous()
         if x_planar:
             n, _, h, w, _ = x.shape
-            xcs = 64
+            xcs = self.cin
         else:
             n, h, w, xcs = x.shape
         if out is None:
             oc = self.cout // (shuffle * shuffle)
-            shape = (n, 8, h, w, 8) if y_planar else (n, h * shuffle, w * shuffle, oc)
+            shape = (n, self.cout // 8, h, w, 8) if y_planar else (n, h * shuffle, w * shuffle, oc)
             out = torch.empty(shape, dtype=out_dtype or x.dtype, device=x.device)
-        ycs = 64 if y_planar else out.shape[-1]
-        rcs = 0 if residual is None else 64 if x_planar else residual.shape[-1]
+        ycs = self.cout if y_planar else out.shape[-1]
+        rcs = 0 if residual is None else self.cout if x_planar else residual.shape[-1]
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().b200sr_conv_forward_layout(
                 self._h, _ptr(x), int(x_planar), xcs, x_coff, _ptr(out), int(y_planar), ycs, y_coff,
@@ -229,10 +230,14 @@ class SpyNet(nn.Module, _VideoPlanMixin):
                 _lib.check(L.b200sr_spynet_level_input(_ptr(refs[level]), _ptr(supps[level]), _ptr(flow) if flow is not None else None,
                                                        _ptr(inp), _lib.dtype_code(adt), _ptr(up), n, hl, wl, ph, pw, cs, st))
                 t = inp
-                for j, idx in enumerate((0, 2, 4, 6, 8)):
-                    conv = convs[f"basic_module.{level}.basic_module.{idx}"]
+                layers = [convs[f"basic_module.{level}.basic_module.{idx}"] for idx in (0, 2, 4, 6, 8)]
+                # bf16: layers 0-3 run on the tcgen05 7x7 kernel and keep their private tensors planar-8 (TMA box rows of 512
+                # contiguous bytes); the 16 -> 2 flow head reads NHWC
+                planar = self.precision != "fp32" and all(c.tcgen05_ok() for c in layers[:4])
+                for j, conv in enumerate(layers):
                     last = j == 4
-                    t = conv(t, self.precision, ACT_NONE if last else ACT_RELU, out_dtype=torch.float32 if last else adt)
+                    t = conv(t, self.precision, ACT_NONE if last else ACT_RELU, out_dtype=torch.float32 if last else adt,
+                             x_planar=planar and 1 <= j <= 3, y_planar=planar and j <= 2)
                 flow = torch.empty((n, 2, hl, wl), **f32)
                 _lib.check(L.b200sr_nhwc_plus_nchw(_ptr(t), _ptr(up), _ptr(flow), n, 2, hl, wl, 2, st))
                 ph, pw = hl, wl

@@ -298,3 +298,42 @@ def test_conv3x3_tcgen05_output_channel_groups(V, cout, shuffle, monkeypatch):
     tol = 2.0 ** -8 * ref.abs().clamp_min(1.0) + 1e-3
     assert bool(((yf - ref).abs() <= tol).all()), float((yf - ref).abs().max())
     assert float((y.float() - y_mma.float()).abs().max()) <= 2.0 ** -6 * float(ref.abs().max())
+
+
+def _to_planar(t):   # (n,h,w,c) -> (n,c/8,h,w,8)
+    n, h, w, c = t.shape
+    return t.view(n, h, w, c // 8, 8).permute(0, 3, 1, 2, 4).contiguous()
+
+
+def _from_planar(t):
+    n, q, h, w, _ = t.shape
+    return t.permute(0, 2, 3, 1, 4).reshape(n, h, w, q * 8)
+
+
+@pytest.mark.parametrize("cin,cout", [(8, 32), (32, 64), (64, 32), (32, 16)])
+@pytest.mark.parametrize("n,h,w", [(1, 6, 10), (2, 31, 53), (1, 192, 320)])
+def test_conv7x7_tcgen05_spynet_layers(V, cin, cout, n, h, w, monkeypatch):
+    """SPyNet BasicModule layers (7x7, models/spynet_arch.py:17-22) on the tcgen05 kernel with streamed filter tap rows: against torch
+    fp64 on the bf16 operands and the mma.sync kernel; NHWC and planar-8 forms agree bit for bit.  6x10 is SPyNet's coarsest level
+    (the whole image is halo), 31x53 has partial tiles in both directions, 192x320 is cfg4's finest level (several tiles per CTA)."""
+    g = torch.Generator().manual_seed(cin * 7 + cout + h)
+    conv = nn.Conv2d(cin, cout, 7, 1, 3)
+    hd = V._ConvHandle(conv, torch.device("cuda:0"))
+    assert hd.tcgen05_ok()
+    cs = max(cin, 16)   # the level input carries 8 channels in 16-channel pixels
+    x = torch.randn(n, h, w, cs, generator=g).bfloat16()
+    with torch.no_grad():
+        ref = F.relu(F.conv2d(x[..., :cin].permute(0, 3, 1, 2).double(), conv.weight.bfloat16().double(), conv.bias.double(), padding=3))
+    xd = x.cuda()
+    y = hd(xd, "bf16", V.ACT_RELU)
+    torch.cuda.synchronize()
+    if cin % 16 == 0:
+        yp = hd(_to_planar(xd), "bf16", V.ACT_RELU, x_planar=True, y_planar=True)
+        assert torch.equal(_from_planar(yp), y)
+    monkeypatch.setenv("B200SR_CONV_IMPL", "mma")
+    y_mma = hd(xd, "bf16", V.ACT_RELU)
+    torch.cuda.synchronize()
+    yf = y.float().cpu().permute(0, 3, 1, 2).double()
+    tol = 2.0 ** -8 * ref.abs().clamp_min(1.0) + 2e-3
+    assert bool(((yf - ref).abs() <= tol).all()), float((yf - ref).abs().max())
+    assert float((y.float() - y_mma.float()).abs().max()) <= 2.0 ** -6 * max(1.0, float(ref.abs().max()))

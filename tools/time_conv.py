@@ -53,3 +53,15 @@ for (n, h, w) in [(1, 180, 320), (2, 180, 320), (8, 180, 320), (1, 720, 1280)]:
         usg = a_.elapsed_time(b_) / 5 * 1e3 / 60
         print(f"{impl} {n}x{h}x{w}: eager {us:8.2f} us/conv = {flop / us / 1e6:7.1f} TFLOP/s ; graph {usg:8.2f} us/conv = {flop / usg / 1e6:7.1f} TFLOP/s", flush=True)
     x.normal_()
+
+
+print("SPyNet 7x7 layers, 28 pairs at the finest cfg4 level (192x320), bf16 NHWC")
+for (cin, cout) in [(8, 32), (32, 64), (64, 32), (32, 16)]:
+    hd7 = video._ConvHandle(nn.Conv2d(cin, cout, 7, 1, 3), dev)
+    x = torch.randn(28, 192, 320, max(cin, 16), device=dev).bfloat16()
+    flop = 28 * 192 * 320 * cin * cout * 49 * 2
+    for impl in ("tc5", "mma"):
+        os.environ["B200SR_CONV_IMPL"] = impl
+        us = timeit(lambda: hd7(x, "bf16", video.ACT_RELU), reps=5, warm=2)
+        print(f"{impl} {cin}->{cout}: {us:9.1f} us = {flop / us / 1e6:7.1f} TFLOP/s", flush=True)
+os.environ.pop("B200SR_CONV_IMPL", None)
