@@ -1,6 +1,8 @@
 // conv_tc5.cu -- launcher of the tcgen05 3x3 (64 | 65..80) -> 64 convolution (BasicVSR trunks, conv_hr).
 #include "conv_tc5.cuh"
 
+#include <cstdlib>
+
 #include "launch.h"
 #include "tma_map.h"
 
@@ -63,7 +65,9 @@ static cudaError_t launch_t(const ConvArgs &a, const CUtensorMap &map, const uin
     }
     const int tx = ceil_div(a.w_, TWO), ty = ceil_div(a.h, TH), ntiles = tx * ty * a.n;
     const int G = a.cout / 64;                       // output-channel groups: a CTA serves one (conv_tc5.cuh)
-    int ctas = sm_count() / G * G;
+    static const int cap = [] { const char *e = getenv("B200SR_CONV_CTAS"); return e ? atoi(e) : 0; }();   // developer experiment: grid cap
+    int ctas = (cap > 0 && cap < sm_count() ? cap : sm_count()) / G * G;
+    if (ctas < G) ctas = G;
     if (ctas > ntiles * G) ctas = ntiles * G;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<NCH>::smem_bytes(), cfg.stream = st;

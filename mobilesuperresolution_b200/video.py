@@ -62,6 +62,7 @@ def flow_warp_nhwc(x: torch.Tensor, flow_nchw: torch.Tensor, padding_mode: str =
 # SPyNet + BasicVSR over the C ABI
 # ======================================================================================================
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch.nn as nn
@@ -330,7 +331,7 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
         # the two directions are independent recurrences of small launches (one 180x320 frame is 253 tiles on 148 SMs): the
         # forward one runs on a side stream (fork / join by events, CUDA-graph capturable) so that they fill each other's tails
         main = torch.cuda.current_stream(dev)
-        side = self._side_stream(dev)
+        side = main if os.environ.get("B200SR_ONE_STREAM") == "1" else self._side_stream(dev)   # developer A/B switch
         side.wait_stream(main)
         back = run("backward_trunk", range(n - 1, -1, -1), flows_backward, lambda i: i)
         with torch.cuda.stream(side):

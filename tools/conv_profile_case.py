@@ -16,3 +16,11 @@ for (n, h, w) in [(1, 720, 1280), (1, 180, 320)]:
         hd(x, "bf16", video.ACT_LRELU)                                   # NHWC -> NHWC (conv_hr)
         hd(xp, "bf16", video.ACT_NONE, residual=rp, x_planar=True, y_planar=True)   # planar-8 trunk conv2 (+ residual)
 torch.cuda.synchronize()
+# SPyNet's two big 7x7 layers at cfg4's finest level, both directions batched (28 x 192 x 320), planar-8
+h32 = video._ConvHandle(nn.Conv2d(32, 64, 7, 1, 3), dev)
+h64 = video._ConvHandle(nn.Conv2d(64, 32, 7, 1, 3), dev)
+x32 = torch.randn(28, 4, 192, 320, 8, device=dev).bfloat16()
+for _ in range(3):
+    t = h32(x32, "bf16", video.ACT_RELU, x_planar=True, y_planar=True)
+    h64(t, "bf16", video.ACT_RELU, x_planar=True, y_planar=True)
+torch.cuda.synchronize()
