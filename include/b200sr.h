@@ -167,6 +167,10 @@ B200SR_API int b200sr_conv_forward_layout(const b200sr_conv_t *conv, const void 
                                           int y_layout, int y_cstride, int y_coff, const void *residual_dev, int r_cstride, int r_coff, int n,
                                           int h, int w, int act, int shuffle, int in_dtype, int out_dtype, int precision, void *stream);
 B200SR_API int b200sr_conv_tcgen05_ok(const b200sr_conv_t *conv);
+/* Grid cap of this conv's tcgen05 launches (persistent kernels, one CTA per SM by default; 0 restores that).  BasicVSR's two
+ * propagation directions (models/basicvsr_arch_origin.py:61-82) are independent chains of one-frame launches: run on two streams
+ * with half-size grids they share the SMs instead of queueing behind each other (14.7 -> 12.4 ms per 15-frame clip). */
+B200SR_API int b200sr_conv_set_max_ctas(b200sr_conv_t *conv, int max_ctas);
 
 /* F.interpolate(x, size=(oh,ow), mode='bilinear', align_corners) on NCHW, then (v - sub[c%4]) * mul[c%4]; y float32.
  * (models/spynet_arch.py:88-94 pre/post resize, normalisation :45-47; models/basicvsr_arch_origin.py:93) */

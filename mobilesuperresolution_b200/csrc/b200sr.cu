@@ -516,6 +516,7 @@ struct b200sr_conv {
     int cin = 0, cout = 0, k = 0, cinp_f32 = 0, coutp_f32 = 0, cinp_bf16 = 0, coutp_bf16 = 0, nt = 0;
     float *d_w_f32 = nullptr, *d_bias = nullptr;
     uint16_t *d_w_bf16 = nullptr;
+    int max_ctas = 0;             // grid cap of the tcgen05 kernels (0 = all SMs)
     uint8_t *d_w_tc5 = nullptr;   // tcgen05 operand image of a 3x3 64 -> 64 filter (conv_tc5.cuh)
 };
 
@@ -592,6 +593,12 @@ void b200sr_conv_destroy(b200sr_conv_t *c) {
     delete c;
 }
 
+int b200sr_conv_set_max_ctas(b200sr_conv_t *c, int max_ctas) {
+    if (!c || max_ctas < 0) return fail(B200SR_E_INVAL, "conv_set_max_ctas: bad argument");
+    c->max_ctas = max_ctas;
+    return 0;
+}
+
 int b200sr_conv_tcgen05_ok(const b200sr_conv_t *c) { return c && c->d_w_tc5 && conv_tc5_enabled() ? 1 : 0; }
 
 int b200sr_conv_forward_layout(const b200sr_conv_t *c, const void *x, int x_layout, int x_cs, int x_co, void *y, int y_layout, int y_cs,
@@ -610,7 +617,7 @@ int b200sr_conv_forward_layout(const b200sr_conv_t *c, const void *x, int x_layo
     ConvArgs a;
     a.x = x, a.y = y, a.residual = res, a.bias = c->d_bias;
     a.n = n, a.h = h, a.w_ = w, a.cin = c->cin, a.cout = c->cout, a.x_cs = x_cs, a.x_co = x_co, a.y_cs = y_cs, a.y_co = y_co, a.r_cs = r_cs,
-    a.r_co = r_co, a.act = act, a.shuffle = shuffle, a.x_planar = xp, a.y_planar = yp;
+    a.r_co = r_co, a.act = act, a.shuffle = shuffle, a.x_planar = xp, a.y_planar = yp, a.max_ctas = c->max_ctas;
     if (precision == B200SR_F32) {
         a.w = c->d_w_f32, a.cinp = c->cinp_f32, a.coutp = c->coutp_f32;
     } else {

@@ -22,6 +22,7 @@ struct ConvArgs {
     const void *w;         // packed filters (layout depends on the kernel)
     const float *bias;     // [coutp]
     int n, h, w_, cin, cinp, cout, coutp, x_cs, x_co, y_cs, y_co, r_cs, r_co, act, shuffle;
+    int max_ctas = 0;                 // tcgen05 kernels: grid cap (0 = one CTA per SM), b200sr_conv_set_max_ctas
     int x_planar = 0, y_planar = 0;   // tcgen05 kernel only: x (and the residual) / y in the planar-8 layout [n][c/8][h][w][8]
 };
 

@@ -65,7 +65,7 @@ static cudaError_t launch_t(const ConvArgs &a, const CUtensorMap &map, const uin
     }
     const int tx = ceil_div(a.w_, TWO), ty = ceil_div(a.h, TH), ntiles = tx * ty * a.n;
     const int G = a.cout / 64;                       // output-channel groups: a CTA serves one (conv_tc5.cuh)
-    static const int cap = [] { const char *e = getenv("B200SR_CONV_CTAS"); return e ? atoi(e) : 0; }();   // developer experiment: grid cap
+    const int cap = a.max_ctas;   // two concurrent streams of small launches share the SMs better with half-size grids (b200sr.h)
     int ctas = (cap > 0 && cap < sm_count() ? cap : sm_count()) / G * G;
     if (ctas < G) ctas = G;
     if (ctas > ntiles * G) ctas = ntiles * G;

@@ -28,7 +28,7 @@ constexpr int TWO = 30, TH = 8, BW = 32, BH = TH + 2, NTHREADS = 320;
 constexpr int PLANE_PX = BW * BH + 8;            // + 8 zero pixels: the last taps of the second M-tile read past the box
 constexpr int PLANE = PLANE_PX * 16;             // 5,248 B
 constexpr int CTRL = 256;
-enum Bar { TC_FULL = 0 /*3*/, TC_EMPTY = 3 /*3*/, D_FULL = 6, D_EMPTY = 8, NBARS = 10 };
+enum Bar { TC_FULL = 0 /*3*/, TC_EMPTY = 3 /*3*/, D_FULL = 6, D_EMPTY = 8, W_READY = 10, NBARS = 11 };
 // NCH = 8-channel chunks of the input: 8 (64 channels) or 10 (65..80 channels: the trunk's first conv on [x_i | warped feat])
 template <int NCH> struct Cfg {
     static constexpr int TILE_BUF = NCH * PLANE;            // 41,984 / 52,480 B
@@ -44,6 +44,12 @@ __device__ __forceinline__ void tma_load_4d_conv(uint32_t dst_saddr, const void 
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst_saddr), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+
+__device__ __forceinline__ void bulk_load_g2s(uint32_t dst_saddr, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
 }
 
 template <int NCH>
@@ -75,6 +81,7 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
             tc5::mbar_init(bar(D_FULL + e), 1);
             tc5::mbar_init(bar(D_EMPTY + e), 128);
         }
+        tc5::mbar_init(bar(W_READY), 1);
         tc5::mbar_init_fence();
         tc5::tma_prefetch_desc(&tmap_x);
     }
@@ -84,12 +91,9 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
     // are dealt round-robin to the group's CTAs (gridDim.x is a multiple of G)
     const int G = a.cout >> 6, grp = (int)blockIdx.x % G, rank = (int)blockIdx.x / G, nranks = (int)gridDim.x / G;
     wimg += (size_t)grp * W_BYTES;
-    for (int i = tid; i < W_BYTES / 16; i += NTHREADS) cp_async16(wsm + i * 16, wimg + i * 16, 16);
-    cp_async_commit();
     if (tid < 64) bias_s[tid] = a.bias[grp * 64 + tid];
     for (int i = tid; i < NBUF * NCH * 8; i += NTHREADS)   // the 8 pad pixels of every plane stay zero (TMA never writes them)
         *reinterpret_cast<uint4 *>(tc + (i / 8) * PLANE + (BW * BH + i % 8) * 16) = make_uint4(0u, 0u, 0u, 0u);
-    cp_async_wait<0>();
     tc5::fence_proxy_async();
     tc5::fence_before_sync();
     __syncthreads();
@@ -106,6 +110,9 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
     if (warp == 0) {
         // ============================== TMA producer ==============================
         if (tc5::elect_one()) {
+            // the filter image is a constant: one bulk copy, in flight while the previous kernel drains and the first tile loads
+            tc5::mbar_arrive_expect_tx(bar(W_READY), W_BYTES);
+            bulk_load_g2s(w_u, wimg, W_BYTES, bar(W_READY));
             tc5::pdl_wait();
             for (int it = 0; it < nmine; ++it) {
                 int x0, y0, n;
@@ -127,6 +134,7 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
         const bool leader = tc5::elect_one();
         const uint32_t idesc = tc5::idesc_bf16_f32(128, 64);
         const uint64_t bw = tc5::smem_desc(w_u, 128, W_SBO), a0d = tc5::smem_desc(tc_u, PLANE, 128);   // A: chunk pairs through LBO = plane stride
+        tc5::mbar_wait(bar(W_READY), 0);
         for (int g = 0; g < 2 * nmine; ++g) {
             const int it = g >> 1, m = g & 1, b = it % NBUF, e = m;
             if (m == 0) tc5::mbar_wait(bar(TC_FULL + b), (it / NBUF) & 1);
