@@ -177,7 +177,7 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
                 const uint4 *rp = reinterpret_cast<const uint4 *>(a.x_planar ? res + ppix * 8 : res + pix * a.r_cs + a.r_co + 64 * grp);
                 const long long rstep = a.x_planar ? hw : 1;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) rv[q] = __ldg(rp + q * rstep);
+                for (int q = 0; q < 8; ++q) rv[q] = rp[q * rstep];   // plain loads: y may be the residual tensor itself (in-place add)
             }
             tc5::mbar_wait(bar(D_FULL + e), it & 1);
             tc5::fence_after_sync();
