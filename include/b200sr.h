@@ -125,6 +125,22 @@ B200SR_API int b200sr_wdsr_tail(const b200sr_wdsr_t *plan, const void *trunk_dev
 B200SR_API int b200sr_wdsr_launches_per_forward(const b200sr_wdsr_t *plan);
 
 /* ------------------------------------------------------------------------------------------------
+ * Split_Block.forward_body (the fork's searchable block, models/wdsr_b.py:406-496), one fused kernel:
+ *   x1 = e*x; x2 = x - x1; x3 = x2 + sum_k p_k relu(PW_k(relu(DW_k(x1)))) + x1; y = x2 + e*x3,   k = 3, 5, 7
+ * Host arrays (float32): dw_k = weight-norm-folded depthwise filters [C][k*k] (Conv_sep.body[0], :382), dw_bias [3][C],
+ * pw = folded 1x1 filters [3][C out][C in] (Conv_sep.body[2], :387), pw_bias [3][C], mask_eff [C] = the BinaryConv2d forward
+ * weight w - (w - rounding(w, 0)) of `split` (:424, models/ops.py:18-26), prob [3] = softmax(alpha) (:487).
+ * x / y: (n, C, h, w) NCHW of `dtype` (arithmetic is fp32 FMA for both).  C in {8, 16, 24, 32}.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200sr_split b200sr_split_t;
+B200SR_API int b200sr_split_create(int channels, const float *dw3_host, const float *dw5_host, const float *dw7_host,
+                                   const float *dw_bias_host, const float *pw_host, const float *pw_bias_host,
+                                   const float *mask_eff_host, const float *prob_host, b200sr_split_t **out);
+B200SR_API void b200sr_split_destroy(b200sr_split_t *blk);
+B200SR_API int b200sr_split_forward(const b200sr_split_t *blk, const void *x_dev, void *y_dev, int n, int h, int w, int dtype,
+                                    void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * flow_warp(x, flow, 'bilinear', padding_mode, align_corners=True)   models/spynet_arch.py:98-129
  * (mmedit twin used at models/basicvsr_arch.py:74,85; basicvsr_arch_origin.py:68,79).
  * x, y: (n,c,h,w) NCHW float32 contiguous.  flow: float32, logical shape (n,h,w,2), addressed with

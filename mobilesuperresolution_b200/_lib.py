@@ -49,6 +49,9 @@ SYMBOLS = {
     "b200sr_flow_warp_nchw": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
                                       c_int, c_int, c_void_p]),
     "b200sr_flow_warp_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sr_split_create": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
+    "b200sr_split_destroy": (None, [c_void_p]),
+    "b200sr_split_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_conv_create": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, POINTER(c_void_p)]),
     "b200sr_conv_destroy": (None, [c_void_p]),
     "b200sr_conv_forward_layout": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,

@@ -510,6 +510,59 @@ int b200sr_flow_warp_nhwc(const void *x, const float *flow, void *y, int n, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Split_Block (the fork's searchable block body)
+// ---------------------------------------------------------------------------------------------------------
+struct b200sr_split {
+    int c = 0;
+    float *d_params = nullptr;
+};
+
+int b200sr_split_create(int C, const float *dw3, const float *dw5, const float *dw7, const float *dwb, const float *pw, const float *pwb,
+                        const float *e, const float *prob, b200sr_split_t **out) {
+    if (!dw3 || !dw5 || !dw7 || !dwb || !pw || !pwb || !e || !prob || !out) return fail(B200SR_E_INVAL, "split_create: null argument");
+    if (C != 8 && C != 16 && C != 24 && C != 32) return fail(B200SR_E_UNSUPPORTED, "split_create: channels=%d (8, 16, 24 or 32)", C);
+    if (b200sr_device_count() <= 0) return fail(B200SR_E_STATE, "split_create: no CUDA device (this library has no CPU fallback)");
+    std::vector<float> f((size_t)split_param_floats(C), 0.f);
+    float *q = f.data();
+    memcpy(q, dw3, sizeof(float) * C * 9), q += C * 9;
+    memcpy(q, dw5, sizeof(float) * C * 25), q += C * 25;
+    memcpy(q, dw7, sizeof(float) * C * 49), q += C * 49;
+    memcpy(q, dwb, sizeof(float) * 3 * C), q += 3 * C;
+    for (int k = 0; k < 3; ++k)            // [k][out][in] -> [k][in][out]: a thread reads one input channel's row of outputs
+        for (int o = 0; o < C; ++o)
+            for (int i = 0; i < C; ++i) q[((size_t)k * C + i) * C + o] = pw[((size_t)k * C + o) * C + i];
+    q += 3 * C * C;
+    memcpy(q, pwb, sizeof(float) * 3 * C), q += 3 * C;
+    memcpy(q, e, sizeof(float) * C), q += C;
+    memcpy(q, prob, sizeof(float) * 3);
+    b200sr_split *b = new (std::nothrow) b200sr_split();
+    if (!b) return fail(B200SR_E_INVAL, "split_create: out of memory");
+    b->c = C;
+    int rc = upload(f.data(), f.size() * 4, (void **)&b->d_params);
+    if (rc) {
+        delete b;
+        return rc;
+    }
+    *out = b;
+    return 0;
+}
+
+void b200sr_split_destroy(b200sr_split_t *b) {
+    if (!b) return;
+    if (b->d_params) cudaFree(b->d_params);
+    delete b;
+}
+
+int b200sr_split_forward(const b200sr_split_t *b, const void *x, void *y, int n, int h, int w, int dtype, void *stream) {
+    if (!b || !x || !y) return fail(B200SR_E_INVAL, "split_forward: null argument");
+    if (n <= 0 || h <= 0 || w <= 0) return fail(B200SR_E_INVAL, "split_forward: bad shape");
+    if (dtype != B200SR_F32 && dtype != B200SR_BF16) return fail(B200SR_E_INVAL, "split_forward: bad dtype %d", dtype);
+    cudaError_t e = launch_split_block(b->c, dtype, x, y, b->d_params, n, h, w, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "split_forward");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // video path
 // ---------------------------------------------------------------------------------------------------------
 struct b200sr_conv {

@@ -48,6 +48,9 @@ int conv7_tc5_nch(int cin);
 bool conv7_tc5_shape_ok(int cin, int cout);
 bool conv7_tc5_eligible(const ConvArgs &a);
 cudaError_t launch_conv7x7_tc5(const ConvArgs &a, const uint8_t *wimg, cudaStream_t st);
+// fused Split_Block body (split_block.cu): params = the packed float image of split_param_floats(C) floats, C in {8,16,24,32}
+int split_param_floats(int C);
+cudaError_t launch_split_block(int C, int dtype, const void *x, void *y, const float *params, int N, int H, int W, cudaStream_t st);
 // video glue (video_glue.cu)
 cudaError_t launch_resize_bilinear_nchw(const void *x, int x_dtype, float *y, int n, int c, int h, int w, int oh, int ow, int align,
                                         const float *sub4, const float *mul4, cudaStream_t st);

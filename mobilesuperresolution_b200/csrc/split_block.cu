@@ -1,0 +1,133 @@
+// split_block.cu -- the fork's searchable block body, Split_Block.forward_body (models/wdsr_b.py:482-496), as ONE kernel:
+//
+//   x1 = e * x                      e = BinaryConv2d(least_channel = 0) forward weight, w - (w - m), per channel (models/ops.py:18-26)
+//   x2 = x - x1
+//   x3 = x2 + sum_k p_k * relu(PW_k(relu(DW_k(x1)))) + x1        k = 3, 5, 7; DW_k depthwise k x k, PW_k 1x1 (Conv_sep, :375-402),
+//   y  = x2 + e * x3                                             both weight-normed (folded on the host); p = softmax(alpha)
+//
+// The reference runs it as 3 x (depthwise conv, ReLU, 1x1 conv, ReLU, scale, add) + 2 masks + 3 adds = ~25 kernels with a full
+// tensor round trip each; here a CTA stages a 32 x 8 pixel tile of x1 (+ 3-pixel halo, zero outside the image = the convs' padding)
+// for all C channels in shared memory and one thread carries one pixel through the whole body in registers (fp32 FFMA: this is the
+// 1e-4 parity arm as well as the bf16-storage arm).  Tensors are the reference's NCHW (depthwise convs are per plane).
+#include "common.cuh"
+#include "launch.h"
+
+namespace b200sr {
+
+namespace splitcfg {
+constexpr int TW = 32, TH = 8, HALO = 3, SW = TW + 2 * HALO, SH = TH + 2 * HALO, NTHREADS = 256;
+__host__ __device__ constexpr int dw_floats(int C) { return C * (9 + 25 + 49); }
+// parameter pack (floats): dw3[C][9] | dw5[C][25] | dw7[C][49] | dw_bias[3][C] | pw[3][C in][C out] | pw_bias[3][C] | e[C] | p[4]
+__host__ __device__ constexpr int param_floats(int C) { return dw_floats(C) + 3 * C + 3 * C * C + 3 * C + C + 4; }
+__host__ __device__ constexpr size_t smem_bytes(int C) { return (size_t)(C * SH * SW + param_floats(C)) * 4; }
+}  // namespace splitcfg
+
+template <int C, int K>
+__device__ __forceinline__ void split_branch(const float *__restrict__ xs, const float *__restrict__ dw, const float *__restrict__ dwb,
+                                             const float *__restrict__ pw, const float *__restrict__ pwb, float p, int ty, int tx,
+                                             float (&s)[C]) {
+    using namespace splitcfg;
+    constexpr int P = K / 2;
+    float t[C];
+#pragma unroll
+    for (int o = 0; o < C; ++o) t[o] = pwb[o];
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {   // one input channel at a time: depthwise tap sum -> ReLU -> rank-1 update of the C outputs
+        float acc = dwb[c];
+        const float *xp = xs + (c * SH + ty + HALO - P) * SW + tx + HALO - P;
+        const float *wp = dw + c * K * K;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) acc = fmaf(xp[ky * SW + kx], wp[ky * K + kx], acc);
+        const float d = fmaxf(acc, 0.f);
+#pragma unroll
+        for (int o4 = 0; o4 < C / 4; ++o4) {
+            const float4 wv = *reinterpret_cast<const float4 *>(pw + c * C + 4 * o4);
+            t[4 * o4 + 0] = fmaf(d, wv.x, t[4 * o4 + 0]);
+            t[4 * o4 + 1] = fmaf(d, wv.y, t[4 * o4 + 1]);
+            t[4 * o4 + 2] = fmaf(d, wv.z, t[4 * o4 + 2]);
+            t[4 * o4 + 3] = fmaf(d, wv.w, t[4 * o4 + 3]);
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < C; ++o) s[o] = s[o] + fmaxf(t[o], 0.f) * p;   // x3 = x3 + x_ * pro[i]   (models/wdsr_b.py:491-493)
+}
+
+template <int C, typename T>
+__global__ void __launch_bounds__(splitcfg::NTHREADS, 2) split_block_kernel(const T *__restrict__ x, T *__restrict__ y,
+                                                                         const float *__restrict__ params, int N, int H, int W,
+                                                                         int tiles_x, int tiles_y) {
+    using namespace splitcfg;
+    extern __shared__ __align__(16) float smem[];
+    float *prm = smem;                            // param_floats(C), 16-byte aligned sections (C % 4 == 0)
+    float *xs = smem + param_floats(C);           // [C][SH][SW]  x1 = e * x, zero outside the image
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int x0 = (tile % tiles_x) * TW, y0 = ((tile / tiles_x) % tiles_y) * TH, n = tile / (tiles_x * tiles_y);
+    for (int i = tid; i < param_floats(C) / 4; i += NTHREADS) reinterpret_cast<float4 *>(prm)[i] = reinterpret_cast<const float4 *>(params)[i];
+    const float *dw3 = prm, *dw5 = dw3 + C * 9, *dw7 = dw5 + C * 25, *dwb = dw7 + C * 49, *pw = dwb + 3 * C, *pwb = pw + 3 * C * C,
+                *e = pwb + 3 * C, *p = e + C;
+    const float *eg = params + (e - prm);
+    const long long plane = (long long)H * W;
+    const T *xn = x + (long long)n * C * plane;
+    for (int i = tid; i < C * SH * SW; i += NTHREADS) {
+        const int q = i % SW, r = (i / SW) % SH, c = i / (SW * SH);
+        const int gy = y0 - HALO + r, gx = x0 - HALO + q;
+        float v = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = to_f32<T>(xn[c * plane + (long long)gy * W + gx]) * __ldg(eg + c);
+        xs[i] = v;
+    }
+    __syncthreads();
+    const int tx = tid % TW, ty = tid / TW, gx = x0 + tx, gy = y0 + ty;
+    if (gx >= W || gy >= H) return;
+    float s[C];
+    const T *xc = xn + (long long)gy * W + gx;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float xv = to_f32<T>(xc[c * plane]);
+        s[c] = xv - xv * e[c];      // x3 = clone(x2), x2 = x - x1, x1 = e * x
+    }
+    split_branch<C, 3>(xs, dw3, dwb, pw, pwb, p[0], ty, tx, s);
+    split_branch<C, 5>(xs, dw5, dwb + C, pw + C * C, pwb + C, p[1], ty, tx, s);
+    split_branch<C, 7>(xs, dw7, dwb + 2 * C, pw + 2 * C * C, pwb + 2 * C, p[2], ty, tx, s);
+    T *yn = y + (long long)n * C * plane + (long long)gy * W + gx;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {   // x3 += x1; y = x2 + split(x3)   (x re-read: an L1 hit, cheaper than 2 C live registers)
+        const float xv = to_f32<T>(xc[c * plane]), x1 = xv * e[c], x2 = xv - x1;
+        yn[c * plane] = from_f32<T>(x2 + (s[c] + x1) * e[c]);
+    }
+}
+
+template <int C, typename T>
+static cudaError_t split_t(const void *x, void *y, const float *params, int N, int H, int W, cudaStream_t st) {
+    using namespace splitcfg;
+    auto kern = split_block_kernel<C, T>;
+    static thread_local bool set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(C));
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) set[dev] = true;
+    }
+    const int tx = ceil_div(W, TW), ty = ceil_div(H, TH);
+    kern<<<tx * ty * N, NTHREADS, smem_bytes(C), st>>>((const T *)x, (T *)y, params, N, H, W, tx, ty);
+    return cudaGetLastError();
+}
+
+int split_param_floats(int C) { return splitcfg::param_floats(C); }
+
+cudaError_t launch_split_block(int C, int dtype, const void *x, void *y, const float *params, int N, int H, int W, cudaStream_t st) {
+#define B200SR_SPLIT_CASE(CC)                                                       \
+    if (C == CC) return dtype == kF32 ? split_t<CC, float>(x, y, params, N, H, W, st) \
+                                      : split_t<CC, bf16>(x, y, params, N, H, W, st);
+    B200SR_SPLIT_CASE(8)
+    B200SR_SPLIT_CASE(16)
+    B200SR_SPLIT_CASE(24)
+    B200SR_SPLIT_CASE(32)
+#undef B200SR_SPLIT_CASE
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace b200sr

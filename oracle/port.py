@@ -92,6 +92,38 @@ def wdsr_block_masked(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
     return t + x
 
 
+def split_block(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    """The fork's searchable block body, ``Split_Block.forward_body`` (models/wdsr_b.py:482-496):
+
+        x1 = split(x); x2 = x - x1; x3 = x2 + sum_k softmax(alpha)_k * relu(PW_k(relu(DW_k(x1)))) + x1; out = x2 + split(x3)
+
+    ``split`` = BinaryConv2d(least_channel=0) (models/wdsr_b.py:424, models/ops.py:18-26); DW_k = weight-normed depthwise
+    k x k (k = 3, 5, 7), PW_k = weight-normed 1x1 (``Conv_sep`` models/wdsr_b.py:375-402); keys ``body.{3,5,7}.0.body.{0,2}.*``.
+    """
+    c = x.shape[1]
+    mw = sd[prefix + "split.weight"]
+    x1 = binary_mask_apply(x, mw, 0)
+    x2 = x - x1
+    x3 = torch.clone(x2)
+    pro = F.softmax(sd[prefix + "alpha"], dim=0)
+    for i, k in enumerate((3, 5, 7)):
+        q = f"{prefix}body.{k}.0.body."
+        wd = weight_norm_fold(sd[q + "0.weight_g"], sd[q + "0.weight_v"])
+        t = F.relu(F.conv2d(x1, wd, sd[q + "0.bias"], padding=k // 2, groups=c))
+        wp = weight_norm_fold(sd[q + "2.weight_g"], sd[q + "2.weight_v"])
+        t = F.relu(F.conv2d(t, wp, sd[q + "2.bias"]))
+        x3 = x3 + t * pro[i]
+    x3 = x3 + x1
+    return x2 + binary_mask_apply(x3, mw, 0)
+
+
+def my_aggregation_layer(sd: SD, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    """``MyAggregationLayer.forward`` eval branch (models/wdsr_b.py:539-546): identity when alpha1 >= alpha2."""
+    if float(sd[prefix + "alpha1"]) >= float(sd[prefix + "alpha2"]):
+        return x
+    return split_block(sd, prefix, x)
+
+
 def count_blocks(sd: SD, prefix: str = "body.") -> int:
     ids = {int(k[len(prefix):].split(".")[0]) for k in sd if k.startswith(prefix) and k[len(prefix)].isdigit()}
     return len(ids)
