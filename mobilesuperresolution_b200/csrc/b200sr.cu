@@ -514,7 +514,7 @@ int b200sr_flow_warp_nhwc(const void *x, const float *flow, void *y, int n, int 
 // ---------------------------------------------------------------------------------------------------------
 struct b200sr_split {
     int c = 0;
-    float *d_params = nullptr;
+    std::vector<float> params;   // packed image, passed to the kernel by value (constant bank)
 };
 
 int b200sr_split_create(int C, const float *dw3, const float *dw5, const float *dw7, const float *dwb, const float *pw, const float *pwb,
@@ -538,18 +538,12 @@ int b200sr_split_create(int C, const float *dw3, const float *dw5, const float *
     b200sr_split *b = new (std::nothrow) b200sr_split();
     if (!b) return fail(B200SR_E_INVAL, "split_create: out of memory");
     b->c = C;
-    int rc = upload(f.data(), f.size() * 4, (void **)&b->d_params);
-    if (rc) {
-        delete b;
-        return rc;
-    }
+    b->params.swap(f);
     *out = b;
     return 0;
 }
 
 void b200sr_split_destroy(b200sr_split_t *b) {
-    if (!b) return;
-    if (b->d_params) cudaFree(b->d_params);
     delete b;
 }
 
@@ -557,7 +551,7 @@ int b200sr_split_forward(const b200sr_split_t *b, const void *x, void *y, int n,
     if (!b || !x || !y) return fail(B200SR_E_INVAL, "split_forward: null argument");
     if (n <= 0 || h <= 0 || w <= 0) return fail(B200SR_E_INVAL, "split_forward: bad shape");
     if (dtype != B200SR_F32 && dtype != B200SR_BF16) return fail(B200SR_E_INVAL, "split_forward: bad dtype %d", dtype);
-    cudaError_t e = launch_split_block(b->c, dtype, x, y, b->d_params, n, h, w, (cudaStream_t)stream);
+    cudaError_t e = launch_split_block(b->c, dtype, x, y, b->params.data(), n, h, w, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "split_forward");
     return 0;
 }

@@ -48,7 +48,8 @@ int conv7_tc5_nch(int cin);
 bool conv7_tc5_shape_ok(int cin, int cout);
 bool conv7_tc5_eligible(const ConvArgs &a);
 cudaError_t launch_conv7x7_tc5(const ConvArgs &a, const uint8_t *wimg, cudaStream_t st);
-// fused Split_Block body (split_block.cu): params = the packed float image of split_param_floats(C) floats, C in {8,16,24,32}
+// fused Split_Block body (split_block.cu): params = HOST pointer to the packed float image of split_param_floats(C) floats (it
+// travels as a kernel argument), C in {8,16,24,32}
 int split_param_floats(int C);
 cudaError_t launch_split_block(int C, int dtype, const void *x, void *y, const float *params, int N, int H, int W, cudaStream_t st);
 // video glue (video_glue.cu)
