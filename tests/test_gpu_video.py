@@ -337,3 +337,29 @@ def test_conv7x7_tcgen05_spynet_layers(V, cin, cout, n, h, w, monkeypatch):
     tol = 2.0 ** -8 * ref.abs().clamp_min(1.0) + 2e-3
     assert bool(((yf - ref).abs() <= tol).all()), float((yf - ref).abs().max())
     assert float((y.float() - y_mma.float()).abs().max()) <= 2.0 ** -6 * max(1.0, float(ref.abs().max()))
+
+
+def test_basicvsr_origin_cuda_graph_two_streams(V):
+    """The whole clip forward (SPyNet batch, two propagation directions forked onto two streams, reconstruction) captures into ONE
+    CUDA graph and replays to the same result as the eager call -- no host sync, no allocation outside the capture pool."""
+    torch.manual_seed(3)
+    m = V.BasicVSR_origin(64, 2).cuda().eval().set_precision("bf16")
+    x = torch.rand(1, 4, 3, 64, 96, device="cuda")
+    with torch.no_grad():
+        eager = m(x, 256, 384).clone()
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            m(x, 256, 384)
+            st.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                y = m(x, 256, 384)
+            y.zero_()
+            g.replay()
+            st.synchronize()
+        assert torch.equal(y, eager)
+        x.copy_(torch.rand_like(x))            # new frames in the captured input buffer
+        g.replay()
+        torch.cuda.synchronize()
+        assert float((y - m(x, 256, 384)).abs().max()) == 0.0
