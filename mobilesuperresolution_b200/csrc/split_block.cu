@@ -81,7 +81,7 @@ __device__ __forceinline__ void split_branch(const float *__restrict__ xs, float
 template <int C> struct SplitParams { float v[splitcfg::param_floats(C)]; };
 
 template <int C, typename T>
-__global__ void __launch_bounds__(splitcfg::NTHREADS, 2) split_block_kernel(const T *__restrict__ x, T *__restrict__ y,
+__global__ void __launch_bounds__(splitcfg::NTHREADS, 3) split_block_kernel(const T *__restrict__ x, T *__restrict__ y,
                                                                          const __grid_constant__ SplitParams<C> prm_, int N, int H, int W,
                                                                          int tiles_x, int tiles_y) {
     using namespace splitcfg;
