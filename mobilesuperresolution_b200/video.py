@@ -463,3 +463,78 @@ class BasicVSR(_VsrBase):
         if self.num_feat != 3:
             raise RuntimeError(f"The size of tensor a ({self.num_feat}) must match the size of tensor b (3) at non-singleton dimension 1")
         raise NotImplementedError("fork BasicVSR tail (ConvTranspose2d stride 4) is not on the accelerated path; use BasicVSR_origin")
+
+
+def _transposed_s4k5_as_conv3x3(deconv: nn.ConvTranspose2d) -> nn.Conv2d:
+    """ConvTranspose2d(cin, cout, 5, stride=4) (models/mvvsr_arch.py:38) as an ordinary 3x3 convolution + PixelShuffle(4):
+    out[4y+i, 4x+j] = sum_ci x[y, x] w[ci, c, i, j]  (+ x[y-1, x] w[.., 4, j] if i == 0) (+ x[y, x-1] w[.., i, 4] if j == 0)
+    (+ x[y-1, x-1] w[.., 4, 4] if i == j == 0) -- the fifth tap of a stride-4 kernel only overlaps the next cell's first row / column.
+    Evaluated on the input zero-padded by one row and column (bottom / right) it yields all (4h+1) x (4w+1) outputs."""
+    wt = deconv.weight.detach().float().cpu()                      # (cin, cout, 5, 5)
+    cin, cout = int(wt.shape[0]), int(wt.shape[1])
+    conv = nn.Conv2d(cin, cout * 16, 3, 1, 1, bias=True)
+    w = torch.zeros(cout, 4, 4, cin, 3, 3)
+    core = wt.permute(1, 2, 3, 0)                                   # (cout, 5, 5, cin)
+    w[:, :, :, :, 1, 1] = core[:, :4, :4]
+    w[:, 0, :, :, 0, 1] = core[:, 4, :4]
+    w[:, :, 0, :, 1, 0] = core[:, :4, 4]
+    w[:, 0, 0, :, 0, 0] = core[:, 4, 4]
+    with torch.no_grad():
+        conv.weight.copy_(w.reshape(cout * 16, cin, 3, 3))
+        b = deconv.bias.detach().float().cpu() if deconv.bias is not None else torch.zeros(cout)
+        conv.bias.copy_(b.view(cout, 1).expand(cout, 16).reshape(-1))
+    return conv
+
+
+class MotionVectorVSR(_VsrBase):
+    """models/mvvsr_arch.py:10-109: BasicVSR whose flows are the codec's motion vectors carried in input channels 3:5 (SPyNet is
+    constructed -- its parameters are in the state_dict -- but never run).  ``forward(x_, height, weight)``: x_ (b,n,5,h,w) ->
+    (b,n,3,height,weight) float32.  Propagation = the BasicVSR trunks (tcgen05 convs in bf16); the tail ConvTranspose2d(2nf, 3, 5,
+    stride 4) runs as a 3x3 convolution + PixelShuffle(4) (``_transposed_s4k5_as_conv3x3``)."""
+
+    def __init__(self, num_feat=64, num_block=15, spynet_path=None):
+        super().__init__()
+        self.num_feat = num_feat
+        self.spynet = SpyNet(spynet_path)
+        self.scale = 4
+        self.backward_trunk = ConvResidualBlocks(num_feat + 3, num_feat, num_block)
+        self.forward_trunk = ConvResidualBlocks(num_feat + 3, num_feat, num_block)
+        self.fusion = nn.Conv2d(num_feat * 2, num_feat * 2, 1, 1, 0, bias=True)
+        self.upconv1 = nn.Conv2d(num_feat, num_feat * 4, 3, 1, 1, bias=True)     # unused by forward (as in the reference)
+        self.upconv2 = nn.Conv2d(num_feat, num_feat * 4, 3, 1, 1, bias=True)
+        self.conv_hr = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
+        self.conv_last = nn.ConvTranspose2d(num_feat * 2, 3, 5, stride=self.scale)
+        self.pixel_shuffle = nn.PixelShuffle(2)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+
+    def _tail(self, device) -> _ConvHandle:
+        sig = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.conv_last.parameters())
+        if getattr(self, "_tail_sig", None) != sig:
+            self._tail_handle, self._tail_sig = _ConvHandle(_transposed_s4k5_as_conv3x3(self.conv_last), device), sig
+        return self._tail_handle
+
+    def forward(self, x_: torch.Tensor, height: int = 1080, weight: int = 1920) -> torch.Tensor:
+        _lib.require_cuda_tensor(x_, "x_")
+        x = x_[:, :, :3].contiguous()
+        flows_forward = x_[:, 1:, 3:].float().contiguous()                    # mv[:, 1:]            (:65-66)
+        flows_backward = flows_forward * (-1)
+        back, fwd = self.propagate(x, flows_forward, flows_backward)
+        b, n, _, h, w = x.shape
+        dev, p = x.device, self.precision
+        convs, tail = self._convs(dev), self._tail(dev)
+        L, st = _lib.lib(), _lib.current_stream_ptr(dev)
+        out = torch.empty((b, n, 3, height, weight), dtype=torch.float32, device=dev)
+        for i in range(n):
+            o = convs["fusion"](torch.cat([back[i], fwd[i]], dim=-1), p, ACT_LRELU)
+            o = torch.nn.functional.pad(o, (0, 0, 0, 1, 0, 1))              # one zero row / column: the fifth tap's outputs
+            t = tail(o, p, ACT_NONE, out_dtype=torch.float32)               # (b, h+1, w+1, 3*16)
+            hr = t.view(b, h + 1, w + 1, 3, 4, 4).permute(0, 3, 1, 4, 2, 5).reshape(b, 3, 4 * h + 4, 4 * w + 4)
+            hr = hr[:, :, :4 * h + 1, :4 * w + 1].contiguous()              # ConvTranspose2d output size (h-1)*4 + 5
+            xi = x[:, i].float().contiguous()
+            res = torch.empty((b, 3, height, weight), dtype=torch.float32, device=dev)
+            base = torch.empty((b, 3, height, weight), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.b200sr_resize_bilinear_nchw(_ptr(hr), _lib.F32, _ptr(res), b, 3, 4 * h + 1, 4 * w + 1, height, weight, 0, None, None, st))
+                _lib.check(L.b200sr_resize_bilinear_nchw(_ptr(xi), _lib.F32, _ptr(base), b, 3, h, w, height, weight, 0, None, None, st))
+            out[:, i] = res + base
+        return out

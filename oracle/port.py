@@ -328,6 +328,25 @@ def basicvsr_origin_forward(sd: SD, x: torch.Tensor, height: int, weight: int) -
 # ----------------------------------------------------------------------------
 # parity metrics
 # ----------------------------------------------------------------------------
+def mvvsr_forward(sd: SD, x_: torch.Tensor, height: int = 1080, weight: int = 1920) -> torch.Tensor:
+    """MotionVectorVSR.forward, models/mvvsr_arch.py:56-109: flows come with the input (channels 3:5, codec motion vectors;
+    forward = mv[:, 1:], backward = -forward), BasicVSR's two propagation loops, then per frame
+    lrelu(fusion 1x1 (2nf -> 2nf)) -> ConvTranspose2d(2nf, 3, 5, stride 4) -> bilinear resize to (height, weight) + bilinear base."""
+    x, mv = x_[:, :, :3], x_[:, :, 3:]
+    ff = mv[:, 1:]
+    fb = ff * (-1)
+    num_feat = sd["backward_trunk.main.0.weight"].shape[0]
+    back, fwd = vsr_propagate(sd, x, ff, fb, num_feat)
+    outs = []
+    for i in range(x.size(1)):
+        o = F.leaky_relu(F.conv2d(torch.cat([back[i], fwd[i]], 1), sd["fusion.weight"], sd["fusion.bias"]), 0.1)
+        o = F.conv_transpose2d(o, sd["conv_last.weight"], sd["conv_last.bias"], stride=4)
+        o = F.interpolate(o, size=(height, weight), mode="bilinear")
+        o = o + F.interpolate(x[:, i], size=(height, weight), mode="bilinear", align_corners=False)
+        outs.append(o)
+    return torch.stack(outs, dim=1)
+
+
 def psnr_db(y: torch.Tensor, ref: torch.Tensor, peak: float | None = None) -> float:
     """10*log10(peak^2/MSE); peak defaults to the reference's dynamic range."""
     y, ref = y.double(), ref.double()

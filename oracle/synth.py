@@ -57,3 +57,10 @@ def synth_state_dict(shapes: Mapping[str, Sequence[int]], seed: int = 0) -> Dict
 
 def synth_input(shape: Sequence[int], seed: int = 1234, lo: float = 0.0, hi: float = 1.0) -> np.ndarray:
     return np.random.RandomState(seed).uniform(lo, hi, tuple(shape)).astype(np.float32)
+
+
+def synth_mv_clip(shape: Sequence[int], seed: int, mv_range: float = 8.0) -> np.ndarray:
+    """(b, n, 5, h, w) MotionVectorVSR input: RGB in [0,1) in channels 0:3, motion vectors in pixels (+-mv_range/2) in 3:5."""
+    x = synth_input(shape, seed)
+    x[:, :, 3:] = (x[:, :, 3:] - 0.5) * mv_range
+    return x

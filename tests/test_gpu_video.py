@@ -363,3 +363,29 @@ def test_basicvsr_origin_cuda_graph_two_streams(V):
         g.replay()
         torch.cuda.synchronize()
         assert float((y - m(x, 256, 384)).abs().max()) == 0.0
+
+
+def _mvvsr_case(name):
+    from oracle import synth
+    meta, arrs = load_golden(name)
+    sd = {k: torch.from_numpy(v) for k, v in synth.synth_state_dict(meta["shapes"], meta["seed"]).items()}
+    return meta, torch.from_numpy(arrs["y"]), sd, torch.from_numpy(synth.synth_mv_clip(meta["shape"], meta["input_seed"]))
+
+
+@pytest.mark.parametrize("name", ["mvvsr_nf64", "mvvsr_nf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_mvvsr_golden(V, name, precision):
+    """MotionVectorVSR (models/mvvsr_arch.py:56-109) against the reference's output: codec motion vectors as flows, BasicVSR trunks,
+    ConvTranspose2d(stride 4) tail as 3x3 conv + PixelShuffle(4), bilinear resize + base (size = x4 and not x4)."""
+    from oracle import port
+    meta, ref, sd, x = _mvvsr_case(name)
+    m = V.MotionVectorVSR(meta["num_feat"], meta["num_block"]).eval()
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().set_precision(precision)
+    with torch.no_grad():
+        y = m(x.cuda(), *meta["size"]).cpu()
+    assert y.shape == ref.shape
+    if precision == "fp32":
+        assert float((y - ref).abs().max()) <= 1e-4, float((y - ref).abs().max())
+    else:
+        assert port.psnr_db(y, ref) >= 50.0, port.psnr_db(y, ref)

@@ -91,3 +91,15 @@ def test_kat2_pretrained(kat):
     assert abs(float(y[0, 1, 64, 64]) - 0.467211) < 1e-5 and abs(float(y.abs().max()) - 1.530487) < 1e-5
     yc = c_oracle.basic_model_forward(sd, x.numpy(), 2)
     assert np.abs(yc - arrs["y"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["mvvsr_nf64", "mvvsr_nf16"])
+def test_mvvsr_golden(name):
+    """MotionVectorVSR (models/mvvsr_arch.py:56-109): the port against the reference-generated fixture."""
+    from oracle import synth
+    meta, arrs = load_golden(name)
+    sd = {k: torch.from_numpy(v) for k, v in synth.synth_state_dict(meta["shapes"], meta["seed"]).items()}
+    x = torch.from_numpy(synth.synth_mv_clip(meta["shape"], meta["input_seed"]))
+    with torch.no_grad():
+        y = port.mvvsr_forward(sd, x, *meta["size"])
+    assert float((y - torch.from_numpy(arrs["y"])).abs().max()) <= 1e-5

@@ -59,3 +59,10 @@ for prec in ("fp32", "bf16"):
         print(f"    as one CUDA graph: {us / 1e3:9.2f} ms/clip = {15 / us * 1e6:8.1f} frames/s, {11.23e12 / us / 1e6:7.1f} TFLOP/s")
     except Exception as e:
         print("    CUDA-graph capture of the clip forward failed:", repr(e)[:200])
+
+# MotionVectorVSR (models/mvvsr_arch.py): flows are codec motion vectors in input channels 3:5 -- no SPyNet, ConvTranspose2d tail
+m = video.MotionVectorVSR(64, 15).to(dev).eval().set_precision("bf16")
+xm = torch.rand(1, 15, 5, 180, 320, device=dev)
+xm[:, :, 3:] = (xm[:, :, 3:] - 0.5) * 8
+us = timeit(lambda: m(xm, 720, 1280), reps=3, warm=1)
+print(f"MotionVectorVSR(64,15) bf16: clip 15x180x320 -> 720x1280: {us / 1e3:9.2f} ms/clip = {15 / us * 1e6:8.1f} frames/s")
