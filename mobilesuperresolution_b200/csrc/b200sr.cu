@@ -657,7 +657,7 @@ int b200sr_conv_forward_layout(const b200sr_conv_t *c, const void *x, int x_layo
     if (shuffle == 2 && (c->cout % 4)) return fail(B200SR_E_INVAL, "conv_forward: PixelShuffle(2) needs cout %% 4 == 0");
     if (act < 0 || act > 2) return fail(B200SR_E_INVAL, "conv_forward: bad activation %d", act);
     const bool xp = x_layout == B200SR_TRUNK_PLANAR8, yp = y_layout == B200SR_TRUNK_PLANAR8;
-    if ((xp && c->cin % 8) || (yp && c->cout % 8)) return fail(B200SR_E_INVAL, "conv_forward: planar-8 needs channel counts that are multiples of 8");
+    if ((xp && c->cin % 8) || (yp && (shuffle == 2 ? c->cout % 32 : c->cout % 8))) return fail(B200SR_E_INVAL, "conv_forward: planar-8 needs channel counts that are multiples of 8");
     if ((!xp && x_layout != B200SR_TRUNK_NHWC) || (!yp && y_layout != B200SR_TRUNK_NHWC)) return fail(B200SR_E_INVAL, "conv_forward: bad layout");
     if ((!xp && x_co + c->cin > x_cs) || (!yp && y_co + (shuffle == 2 ? c->cout / 4 : c->cout) > y_cs))
         return fail(B200SR_E_INVAL, "conv_forward: channel window outside tensor");

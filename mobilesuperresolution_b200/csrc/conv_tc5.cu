@@ -42,13 +42,13 @@ static cudaError_t make_planar_map(CUtensorMap *map, const void *base, int N, in
 bool conv_tc5_eligible(const ConvArgs &a) {
     const auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (a.cout % 64 || a.cout > 256 || a.cin < 64 || a.cin > 80 || !al16(a.x) || !al16(a.y) || !al16(a.residual)) return false;
-    if (a.shuffle == 2 ? (a.residual || a.y_planar) : a.shuffle != 1) return false;
+    if (a.shuffle == 2 ? a.residual != nullptr : a.shuffle != 1) return false;
     if (a.x_planar) {
         if (a.cin != 64 || (a.residual && a.cout != 64)) return false;
     } else if (a.x_cs % 8 || a.x_co % 8 || (a.residual && (a.r_cs % 8 || a.r_co % 8))) {
         return false;
     }
-    return a.y_planar ? a.cout == 64 : (a.y_cs % 8 == 0 && a.y_co % 8 == 0);
+    return a.y_planar ? (a.shuffle == 2 ? a.cout % 32 == 0 : a.cout == 64) : (a.y_cs % 8 == 0 && a.y_co % 8 == 0);
 }
 
 template <int NCH>

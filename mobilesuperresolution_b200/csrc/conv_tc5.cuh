@@ -199,7 +199,10 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
                         float f[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) f[j] = apply_act(__uint_as_float(v[4 * j + sub]) + bias_s[32 * hh + 4 * j + sub], act);
-                        *reinterpret_cast<uint4 *>(y + hp * a.y_cs + a.y_co + 16 * grp + 8 * hh) =
+                        // NHWC: 8 of the HR pixel's channels; planar-8 [n][cout/32][2H][2W][8]: plane 2 grp + hh of the HR image
+                        bf16 *dst = a.y_planar ? y + (((long long)n * (a.cout >> 5) + 2 * grp + hh) * (4 * hw) + (hp - (long long)n * 4 * hw)) * 8
+                                               : y + hp * a.y_cs + a.y_co + 16 * grp + 8 * hh;
+                        *reinterpret_cast<uint4 *>(dst) =
                             make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
                     }
                 } else if (ok) {

@@ -112,7 +112,7 @@ class _ConvHandle:
             n, h, w, xcs = x.shape
         if out is None:
             oc = self.cout // (shuffle * shuffle)
-            shape = (n, self.cout // 8, h, w, 8) if y_planar else (n, h * shuffle, w * shuffle, oc)
+            shape = (n, oc // 8, h * shuffle, w * shuffle, 8) if y_planar else (n, h * shuffle, w * shuffle, oc)
             out = torch.empty(shape, dtype=out_dtype or x.dtype, device=x.device)
         ycs = self.cout if y_planar else out.shape[-1]
         rcs = 0 if residual is None else self.cout if x_planar else residual.shape[-1]
@@ -422,8 +422,9 @@ class BasicVSR_origin(_VsrBase):
             o = torch.cat([back[i], fwd[i]], dim=-1)
             o = convs["fusion"](o, p, ACT_LRELU)
             o = convs["upconv1"](o, p, ACT_LRELU, shuffle=2)          # lrelu(pixel_shuffle(conv)) == shuffle(lrelu(conv))
-            o = convs["upconv2"](o, p, ACT_LRELU, shuffle=2)
-            o = convs["conv_hr"](o, p, ACT_LRELU)
+            hr_planar = p != "fp32" and convs["upconv2"].tcgen05_ok() and convs["conv_hr"].tcgen05_ok() and convs["conv_hr"].cin == 64
+            o = convs["upconv2"](o, p, ACT_LRELU, shuffle=2, y_planar=hr_planar)     # 720p tensor planar-8 between the two tcgen05 convs
+            o = convs["conv_hr"](o, p, ACT_LRELU, x_planar=hr_planar)
             o = convs["conv_last"](o, p, ACT_NONE)
             direct = (height, weight) == (4 * h, 4 * w)
             hr = out[:, i] if direct else torch.empty((b, 3, 4 * h, 4 * w), dtype=torch.float32, device=dev)

@@ -389,3 +389,15 @@ def test_mvvsr_golden(V, name, precision):
         assert float((y - ref).abs().max()) <= 1e-4, float((y - ref).abs().max())
     else:
         assert port.psnr_db(y, ref) >= 50.0, port.psnr_db(y, ref)
+
+
+def test_conv3x3_tcgen05_shuffle_store_planar8(V):
+    """upconv2's PixelShuffle(2) store straight into the planar-8 layout conv_hr reads: same values as the NHWC store."""
+    g = torch.Generator().manual_seed(12)
+    conv = nn.Conv2d(64, 256, 3, 1, 1)
+    hd = V._ConvHandle(conv, torch.device("cuda:0"))
+    x = torch.randn(2, 19, 43, 64, generator=g).bfloat16().cuda()
+    ref = hd(x, "bf16", V.ACT_LRELU, shuffle=2)                       # (2, 38, 86, 64)
+    yp = hd(x, "bf16", V.ACT_LRELU, shuffle=2, y_planar=True)         # (2, 8, 38, 86, 8)
+    assert tuple(yp.shape) == (2, 8, 38, 86, 8)
+    assert torch.equal(_from_planar(yp), ref)
