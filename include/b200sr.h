@@ -188,6 +188,14 @@ B200SR_API int b200sr_conv_tcgen05_ok(const b200sr_conv_t *conv);
  * with half-size grids they share the SMs instead of queueing behind each other (14.7 -> 12.4 ms per 15-frame clip). */
 B200SR_API int b200sr_conv_set_max_ctas(b200sr_conv_t *conv, int max_ctas);
 
+/* conv_last + base of BasicVSR_origin's reconstruction in ONE kernel (models/basicvsr_arch_origin.py:90-92):
+ *   y[n,c,Y,X] = conv3x3(x)[n,c,Y,X] + F.interpolate(base, scale_factor=4, mode='bilinear', align_corners=False)[n,c,Y,X]
+ * conv = a 3x3 64 -> 3 conv; x: n x H x W x 64 bf16 (NHWC channel window or planar-8); base: float32 NCHW (3, H/4, W/4) per image,
+ * image n at base + n * base_nstride elements; y: float32 NCHW (3, H, W) per image at y + n * y_nstride.  tcgen05 only. */
+B200SR_API int b200sr_vsr_conv_last_base(const b200sr_conv_t *conv, const void *x_dev, int x_layout, int x_cstride, int x_coff,
+                                         const float *base_dev, int64_t base_nstride, float *y_dev, int64_t y_nstride, int n, int H, int W,
+                                         void *stream);
+
 /* F.interpolate(x, size=(oh,ow), mode='bilinear', align_corners) on NCHW, then (v - sub[c%4]) * mul[c%4]; y float32.
  * (models/spynet_arch.py:88-94 pre/post resize, normalisation :45-47; models/basicvsr_arch_origin.py:93) */
 B200SR_API int b200sr_resize_bilinear_nchw(const void *x_dev, int x_dtype, float *y_dev, int n, int c, int h, int w, int oh, int ow,

@@ -607,6 +607,17 @@ int b200sr_conv_create(int cin, int cout, int k, const float *w, const float *bi
             return rc;
         }
     }
+    if (cin == 64 && cout == 3 && k == 3) {
+        // "rgb" form of the tcgen05 3x3 kernel (conv_last): 16 output rows (3 used), [2 row groups][72 slices][8 rows][16 B]
+        std::vector<uint16_t> wi((size_t)2 * 72 * 64, 0);
+        for (int o = 0; o < 3; ++o)
+            for (int i = 0; i < 64; ++i)
+                for (int t = 0; t < 9; ++t) wi[(((size_t)(o / 8) * 72 + t * 8 + i / 8) * 8 + o % 8) * 8 + i % 8] = f2bf(w[((size_t)o * 64 + i) * 9 + t]);
+        if ((rc = upload(wi.data(), wi.size() * 2, (void **)&c->d_w_tc5))) {
+            b200sr_conv_destroy(c);
+            return rc;
+        }
+    }
     if (k == 7 && conv7_tc5_shape_ok(cin, cout)) {
         // [7 tap rows ky][cout/8 row groups][7 taps kx x nch chunks][8 rows][16 B]: one contiguous stage per tap row (conv7_tc5.cuh)
         const int nch = conv7_tc5_nch(cin);
@@ -686,6 +697,23 @@ int b200sr_conv_forward_layout(const b200sr_conv_t *c, const void *x, int x_layo
         return fail(B200SR_E_UNSUPPORTED, "conv_forward: the planar-8 layout is served by the tcgen05 bf16 kernels only (3x3 64 -> 64, SPyNet 7x7 layers)");
     cudaError_t e = launch_conv(a, c->k, c->nt, in_dtype, out_dtype, precision, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "conv_forward (fp32 precision needs float32 tensors; bf16 precision: bf16|f32 in, bf16|f32 out)");
+    return 0;
+}
+
+int b200sr_vsr_conv_last_base(const b200sr_conv_t *c, const void *x, int x_layout, int x_cs, int x_co, const float *base, int64_t base_nstride,
+                              float *y, int64_t y_nstride, int n, int H, int W, void *stream) {
+    if (!c || !x || !base || !y) return fail(B200SR_E_INVAL, "vsr_conv_last_base: null argument");
+    if (n <= 0 || H <= 0 || W <= 0 || H % 4 || W % 4) return fail(B200SR_E_INVAL, "vsr_conv_last_base: bad shape (H, W multiples of 4)");
+    ConvArgs a;
+    a.x = x, a.y = y, a.residual = nullptr, a.bias = c->d_bias, a.w = nullptr;
+    a.n = n, a.h = H, a.w_ = W, a.cin = c->cin, a.cinp = c->cinp_bf16, a.cout = c->cout, a.coutp = c->coutp_bf16, a.x_cs = x_cs, a.x_co = x_co,
+    a.y_cs = 0, a.y_co = 0, a.r_cs = 0, a.r_co = 0, a.act = 0, a.shuffle = 1, a.max_ctas = c->max_ctas;
+    a.x_planar = x_layout == B200SR_TRUNK_PLANAR8, a.y_planar = 0;
+    a.base = base, a.base_nstride = base_nstride, a.y_nstride = y_nstride;
+    if (!c->d_w_tc5 || c->k != 3 || !conv_tc5_enabled() || !conv_tc5_eligible(a))
+        return fail(B200SR_E_UNSUPPORTED, "vsr_conv_last_base: needs a 3x3 64 -> 3 conv, bf16 NHWC (16-byte aligned window) or planar-8 input");
+    cudaError_t e = launch_conv3x3_c64_tc5(a, c->d_w_tc5, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "vsr_conv_last_base");
     return 0;
 }
 

@@ -23,6 +23,10 @@ struct ConvArgs {
     const float *bias;     // [coutp]
     int n, h, w_, cin, cinp, cout, coutp, x_cs, x_co, y_cs, y_co, r_cs, r_co, act, shuffle;
     int max_ctas = 0;                 // tcgen05 kernels: grid cap (0 = one CTA per SM), b200sr_conv_set_max_ctas
+    // tcgen05 3x3 kernel, cout = 3 ("rgb" form, conv_last of BasicVSR_origin): y = fp32 NCHW image n at y + n * y_nstride,
+    // y += bilinear x4 upsample (align_corners = False) of the fp32 NCHW low-resolution image n at base + n * base_nstride
+    const float *base = nullptr;
+    long long base_nstride = 0, y_nstride = 0;
     int x_planar = 0, y_planar = 0;   // tcgen05 kernel only: x (and the residual) / y in the planar-8 layout [n][c/8][h][w][8]
 };
 

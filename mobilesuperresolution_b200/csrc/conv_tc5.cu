@@ -41,6 +41,9 @@ static cudaError_t make_planar_map(CUtensorMap *map, const void *base, int N, in
 
 bool conv_tc5_eligible(const ConvArgs &a) {
     const auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (a.base)   // "rgb" form: 64 -> 3, fp32 NCHW output + bilinear x4 base of an (H/4, W/4) image
+        return a.cout == 3 && a.cin == 64 && a.shuffle == 1 && !a.residual && a.act == 0 && a.h % 4 == 0 && a.w_ % 4 == 0 && al16(a.x) &&
+               (a.x_planar || (a.x_cs % 8 == 0 && a.x_co % 8 == 0));
     if (a.cout % 64 || a.cout > 256 || a.cin < 64 || a.cin > 80 || !al16(a.x) || !al16(a.y) || !al16(a.residual)) return false;
     if (a.shuffle == 2 ? a.residual != nullptr : a.shuffle != 1) return false;
     if (a.x_planar) {
@@ -51,26 +54,26 @@ bool conv_tc5_eligible(const ConvArgs &a) {
     return a.y_planar ? (a.shuffle == 2 ? a.cout % 32 == 0 : a.cout == 64) : (a.y_cs % 8 == 0 && a.y_co % 8 == 0);
 }
 
-template <int NCH>
+template <int NCH, int NOUT = 64>
 static cudaError_t launch_t(const ConvArgs &a, const CUtensorMap &map, const uint8_t *wimg, cudaStream_t st) {
     using namespace tc5conv;
-    auto kern = conv3x3_c64_tc5_kernel<NCH>;
+    auto kern = conv3x3_c64_tc5_kernel<NCH, NOUT>;
     static thread_local bool set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<NCH>::smem_bytes());
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<NCH, NOUT>::smem_bytes());
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) set[dev] = true;
     }
     const int tx = ceil_div(a.w_, TWO), ty = ceil_div(a.h, TH), ntiles = tx * ty * a.n;
-    const int G = a.cout / 64;                       // output-channel groups: a CTA serves one (conv_tc5.cuh)
+    const int G = NOUT == 64 ? a.cout / 64 : 1;      // output-channel groups: a CTA serves one (conv_tc5.cuh)
     const int cap = a.max_ctas;   // two concurrent streams of small launches share the SMs better with half-size grids (b200sr.h)
     int ctas = (cap > 0 && cap < sm_count() ? cap : sm_count()) / G * G;
     if (ctas < G) ctas = G;
     if (ctas > ntiles * G) ctas = ntiles * G;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctas), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<NCH>::smem_bytes(), cfg.stream = st;
+    cfg.gridDim = dim3(ctas), cfg.blockDim = dim3(NTHREADS), cfg.dynamicSmemBytes = Cfg<NCH, NOUT>::smem_bytes(), cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -96,6 +99,7 @@ cudaError_t launch_conv3x3_c64_tc5(const ConvArgs &a, const uint8_t *wimg, cudaS
         c.p = base, c.n = a.n, c.h = a.h, c.w = a.w_, c.cs = cs, c.cin = a.cin;
         mapp = &c.map;
     }
+    if (a.base) return launch_t<8, 16>(a, *mapp, wimg, st);
     return a.cin == 64 ? launch_t<8>(a, *mapp, wimg, st) : launch_t<10>(a, *mapp, wimg, st);
 }
 

@@ -30,11 +30,12 @@ constexpr int PLANE = PLANE_PX * 16;             // 5,248 B
 constexpr int CTRL = 256;
 enum Bar { TC_FULL = 0 /*3*/, TC_EMPTY = 3 /*3*/, D_FULL = 6, D_EMPTY = 8, W_READY = 10, NBARS = 11 };
 // NCH = 8-channel chunks of the input: 8 (64 channels) or 10 (65..80 channels: the trunk's first conv on [x_i | warped feat])
-template <int NCH> struct Cfg {
+// NOUT = output channels per CTA: 64, or 16 for the 64 -> 3 "rgb" form (conv_last + bilinear base, fp32 NCHW store)
+template <int NCH, int NOUT = 64> struct Cfg {
     static constexpr int TILE_BUF = NCH * PLANE;            // 41,984 / 52,480 B
     static constexpr int NBUF = NCH <= 8 ? 3 : 2;
-    static constexpr int W_SBO = 9 * NCH * 128;             // weight image [8 row groups][9 * NCH (tap, chunk) slices][8 rows][16 B]
-    static constexpr int W_BYTES = 8 * W_SBO;               // 73,728 / 92,160 B
+    static constexpr int W_SBO = 9 * NCH * 128;             // weight image [NOUT/8 row groups][9 * NCH (tap, chunk) slices][8 rows][16 B]
+    static constexpr int W_BYTES = (NOUT / 8) * W_SBO;      // 73,728 / 92,160 B (18,432 for NOUT = 16)
     static constexpr size_t smem_bytes() { return (size_t)CTRL + NBUF * TILE_BUF + W_BYTES + 256; }
 };
 }  // namespace tc5conv
@@ -52,12 +53,23 @@ __device__ __forceinline__ void bulk_load_g2s(uint32_t dst_saddr, const void *sr
                  : "memory");
 }
 
-template <int NCH>
+// x4 bilinear upsample (align_corners = False) of one plane of the low-resolution image at HR pixel (oy, ox): the arithmetic of
+// vsr_base_add_kernel (video_glue.cu) / F.interpolate(x_i, scale_factor=4, mode='bilinear')   models/basicvsr_arch_origin.py:91
+__device__ __forceinline__ float bilinear_x4(const float *__restrict__ p, int h, int w, int oy, int ox) {
+    const float sy = fmaxf(0.25f * ((float)oy + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.25f * ((float)ox + 0.5f) - 0.5f, 0.f);
+    const int y0 = min((int)sy, h - 1), x0 = min((int)sx, w - 1);
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    return (1.f - ly) * ((1.f - lx) * p[y0 * w + x0] + lx * p[y0 * w + x1]) + ly * ((1.f - lx) * p[y1 * w + x0] + lx * p[y1 * w + x1]);
+}
+
+template <int NCH, int NOUT>
 __global__ void __launch_bounds__(tc5conv::NTHREADS, 1)
 conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, const uint8_t *__restrict__ wimg, int tiles_x, int tiles_y,
                        int ntiles) {
     using namespace tc5conv;
-    constexpr int TILE_BUF = Cfg<NCH>::TILE_BUF, NBUF = Cfg<NCH>::NBUF, W_SBO = Cfg<NCH>::W_SBO, W_BYTES = Cfg<NCH>::W_BYTES;
+    using C = Cfg<NCH, NOUT>;
+    constexpr int TILE_BUF = C::TILE_BUF, NBUF = C::NBUF, W_SBO = C::W_SBO, W_BYTES = C::W_BYTES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *ctrl = smem_raw;
     uint8_t *tc = smem_raw + CTRL;           // NBUF x TILE_BUF
@@ -89,9 +101,9 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
     if (warp == 0) tc5::tmem_alloc(smem_u32(ctrl + 240), 128);
     // cout = 64 G: output-channel group `grp` (its own weight image and bias slice) is fixed per CTA, the spatial tiles of a group
     // are dealt round-robin to the group's CTAs (gridDim.x is a multiple of G)
-    const int G = a.cout >> 6, grp = (int)blockIdx.x % G, rank = (int)blockIdx.x / G, nranks = (int)gridDim.x / G;
+    const int G = NOUT == 64 ? a.cout >> 6 : 1, grp = (int)blockIdx.x % G, rank = (int)blockIdx.x / G, nranks = (int)gridDim.x / G;
     wimg += (size_t)grp * W_BYTES;
-    if (tid < 64) bias_s[tid] = a.bias[grp * 64 + tid];
+    if (tid < NOUT) bias_s[tid] = a.bias[grp * 64 + tid];
     for (int i = tid; i < NBUF * NCH * 8; i += NTHREADS)   // the 8 pad pixels of every plane stay zero (TMA never writes them)
         *reinterpret_cast<uint4 *>(tc + (i / 8) * PLANE + (BW * BH + i % 8) * 16) = make_uint4(0u, 0u, 0u, 0u);
     tc5::fence_proxy_async();
@@ -132,7 +144,7 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
     } else if (warp == 1) {
         // ============================== MMA issuer ==============================
         const bool leader = tc5::elect_one();
-        const uint32_t idesc = tc5::idesc_bf16_f32(128, 64);
+        const uint32_t idesc = tc5::idesc_bf16_f32(128, NOUT);
         const uint64_t bw = tc5::smem_desc(w_u, 128, W_SBO), a0d = tc5::smem_desc(tc_u, PLANE, 128);   // A: chunk pairs through LBO = plane stride
         tc5::mbar_wait(bar(W_READY), 0);
         for (int g = 0; g < 2 * nmine; ++g) {
@@ -141,7 +153,7 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
             tc5::mbar_wait(bar(D_EMPTY + e), (it & 1) ^ 1);
             tc5::fence_after_sync();
             if (leader) {
-                const uint32_t d = tmem + e * 64;
+                const uint32_t d = tmem + e * NOUT;
                 const uint64_t abase = a0d + (uint64_t)((b * TILE_BUF + m * 128 * 16) >> 4);
 #pragma unroll
                 for (int i = 0; i < 9 * (NCH / 2); ++i) {   // (tap t, chunks 2 cp, 2 cp + 1)
@@ -181,10 +193,27 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
             }
             tc5::mbar_wait(bar(D_FULL + e), it & 1);
             tc5::fence_after_sync();
+            if constexpr (NOUT == 16) {
+                // "rgb" form: 3 of the 16 accumulator columns + bias + x4 bilinear base -> fp32 NCHW (lanes = consecutive x: coalesced)
+                uint32_t v[16];
+                tc5::tmem_ld16(tmem + lane_base + e * NOUT, v);
+                tc5::tmem_wait_ld();
+                tc5::fence_before_sync();
+                tc5::mbar_arrive_relaxed(bar(D_EMPTY + e));
+                if (ok) {
+                    const int lh = H >> 2, lw = W >> 2;
+                    const float *bp = a.base + (long long)n * a.base_nstride;
+                    float *yp = reinterpret_cast<float *>(a.y) + (long long)n * a.y_nstride + (long long)gy * W + gx;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        yp[c * hw] = __uint_as_float(v[c]) + bias_s[c] + bilinear_x4(bp + (long long)c * lh * lw, lh, lw, gy, gx);
+                }
+                continue;
+            }
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {   // the accumulator row in two halves of 32 channels (register budget)
                 uint32_t v[32];
-                tc5::tmem_ld32(tmem + lane_base + e * 64 + 32 * hh, v);
+                tc5::tmem_ld32(tmem + lane_base + e * NOUT + 32 * hh, v);
                 tc5::tmem_wait_ld();
                 if (hh == 1) {
                     tc5::fence_before_sync();

@@ -423,15 +423,22 @@ class BasicVSR_origin(_VsrBase):
             o = convs["fusion"](o, p, ACT_LRELU)
             o = convs["upconv1"](o, p, ACT_LRELU, shuffle=2)          # lrelu(pixel_shuffle(conv)) == shuffle(lrelu(conv))
             hr_planar = p != "fp32" and convs["upconv2"].tcgen05_ok() and convs["conv_hr"].tcgen05_ok() and convs["conv_hr"].cin == 64
-            o = convs["upconv2"](o, p, ACT_LRELU, shuffle=2, y_planar=hr_planar)     # 720p tensor planar-8 between the two tcgen05 convs
-            o = convs["conv_hr"](o, p, ACT_LRELU, x_planar=hr_planar)
-            o = convs["conv_last"](o, p, ACT_NONE)
+            # conv_last + bilinear base in one tcgen05 launch (fp32 accumulators straight to the fp32 NCHW frame, no bf16 round trip)
+            fused_last = (hr_planar and x.dtype == torch.float32 and convs["conv_last"].tcgen05_ok() and convs["conv_last"].cout == 3
+                          and convs["conv_hr"].cout == 64)
+            o = convs["upconv2"](o, p, ACT_LRELU, shuffle=2, y_planar=hr_planar)     # 720p tensors planar-8 between the tcgen05 convs
+            o = convs["conv_hr"](o, p, ACT_LRELU, x_planar=hr_planar, y_planar=fused_last)
             direct = (height, weight) == (4 * h, 4 * w)
             hr = out[:, i] if direct else torch.empty((b, 3, 4 * h, 4 * w), dtype=torch.float32, device=dev)
             xi = x[:, i]
             with torch.cuda.device(dev):
-                _lib.check(L.b200sr_vsr_base_add(_ptr(o), _lib.dtype_code(o.dtype), o.shape[-1], _ptr(xi), _lib.dtype_code(x.dtype), x.stride(0),
-                                                 _ptr(hr), hr.stride(0), b, h, w, st))
+                if fused_last:
+                    _lib.check(L.b200sr_vsr_conv_last_base(convs["conv_last"]._h, _ptr(o), 1, 64, 0, _ptr(xi), x.stride(0), _ptr(hr), hr.stride(0),
+                                                           b, 4 * h, 4 * w, st))
+                else:
+                    o = convs["conv_last"](o, p, ACT_NONE)
+                    _lib.check(L.b200sr_vsr_base_add(_ptr(o), _lib.dtype_code(o.dtype), o.shape[-1], _ptr(xi), _lib.dtype_code(x.dtype), x.stride(0),
+                                                     _ptr(hr), hr.stride(0), b, h, w, st))
                 if not direct:   # F.interpolate(out, size=(height, weight), mode='bilinear'), :93
                     res = torch.empty((b, 3, height, weight), dtype=torch.float32, device=dev)
                     _lib.check(L.b200sr_resize_bilinear_nchw(_ptr(hr), _lib.F32, _ptr(res), b, 3, 4 * h, 4 * w, height, weight, 0, None, None, st))

@@ -401,3 +401,33 @@ def test_conv3x3_tcgen05_shuffle_store_planar8(V):
     yp = hd(x, "bf16", V.ACT_LRELU, shuffle=2, y_planar=True)         # (2, 8, 38, 86, 8)
     assert tuple(yp.shape) == (2, 8, 38, 86, 8)
     assert torch.equal(_from_planar(yp), ref)
+
+
+@pytest.mark.parametrize("planar", [False, True])
+def test_conv_last_plus_base_fused_tcgen05(V, planar):
+    """conv_last (3x3, 64 -> 3) + F.interpolate(x_i, scale_factor=4, bilinear, align_corners=False) in one launch
+    (models/basicvsr_arch_origin.py:90-92): fp32 NCHW result written into a strided batch slot, against torch fp64."""
+    import ctypes
+    from mobilesuperresolution_b200 import _lib
+    g = torch.Generator().manual_seed(44)
+    conv = nn.Conv2d(64, 3, 3, 1, 1)
+    hd = V._ConvHandle(conv, torch.device("cuda:0"))
+    b, h, w = 2, 9, 13
+    x = torch.randn(b, 4 * h, 4 * w, 64, generator=g).bfloat16()
+    lr = torch.rand(b, 3, 3, h, w, generator=g)                         # (b, n, 3, h, w) clip: frame 1 is the base
+    with torch.no_grad():
+        ref = F.conv2d(x.permute(0, 3, 1, 2).double(), conv.weight.bfloat16().double(), conv.bias.double(), padding=1) + \
+            F.interpolate(lr[:, 1].double(), scale_factor=4, mode="bilinear", align_corners=False)
+    xd = x.cuda()
+    xin = _to_planar(xd) if planar else xd
+    lrd = lr.cuda()
+    out = torch.full((b, 3, 3, 4 * h, 4 * w), 9.0, device="cuda")
+    base = lrd[:, 1]
+    slot = out[:, 2]
+    _lib.check(_lib.lib().b200sr_vsr_conv_last_base(hd._h, ctypes.c_void_p(xin.data_ptr()), int(planar), 64, 0, ctypes.c_void_p(base.data_ptr()),
+                                                    lrd.stride(0), ctypes.c_void_p(slot.data_ptr()), out.stride(0), b, 4 * h, 4 * w,
+                                                    _lib.current_stream_ptr(xd.device)))
+    torch.cuda.synchronize()
+    o = out.cpu()
+    assert float((o[:, 2].double() - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))
+    assert float((o[:, :2] - 9).abs().max()) == 0
