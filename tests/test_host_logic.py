@@ -67,6 +67,28 @@ def test_abi_error_codes_without_device(sr):
     L.b200sr_wdsr_destroy(h)
 
 
+def test_abi_error_codes_conv_and_split_without_device(sr):
+    """Argument errors of the video / Split_Block entry points come back as codes (never exceptions, never a device touch)."""
+    from mobilesuperresolution_b200 import _lib
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    z = np.zeros(4096, np.float32)
+    p = z.ctypes.data_as(ctypes.c_void_p)
+    assert L.b200sr_conv_create(8, 8, 5, p, p, ctypes.byref(h)) == -4 and b"k in" in L.b200sr_last_error()
+    assert L.b200sr_conv_create(8, 8, 3, None, p, ctypes.byref(h)) == -1
+    assert L.b200sr_split_create(12, p, p, p, p, p, p, p, p, ctypes.byref(h)) == -4 and b"channels=12" in L.b200sr_last_error()
+    assert L.b200sr_split_create(24, p, p, p, p, p, p, p, None, ctypes.byref(h)) == -1
+    assert L.b200sr_split_forward(None, p, p, 1, 8, 8, 0, None) == -1
+    assert L.b200sr_conv_forward_layout(None, p, 0, 8, 0, p, 0, 8, 0, None, 0, 0, 1, 8, 8, 0, 1, 1, 1, 1, None) == -1
+    assert L.b200sr_vsr_conv_last_base(None, p, 0, 64, 0, p, 0, p, 0, 1, 8, 8, None) == -1
+    assert L.b200sr_conv_set_max_ctas(None, 4) == -1
+    assert L.b200sr_conv_tcgen05_ok(None) == 0
+    if L.b200sr_device_count() == 0:
+        assert L.b200sr_conv_create(64, 64, 3, p, p, ctypes.byref(h)) == -2 and b"no CPU fallback" in L.b200sr_last_error()
+        big = np.zeros(24 * 49 + 3 * 24 * 24, np.float32).ctypes.data_as(ctypes.c_void_p)
+        assert L.b200sr_split_create(24, big, big, big, big, big, big, big, big, ctypes.byref(h)) == -2
+
+
 def test_no_cpu_fallback(sr):
     m = sr.BASIC_MODEL(P(2, 1)).eval()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
