@@ -7,7 +7,8 @@ from mobilesuperresolution_b200 import video
 torch.set_grad_enabled(False)
 dev = torch.device("cuda")
 m = video.BasicVSR_origin(64, 30).to(dev).eval().set_precision("bf16")
-x = torch.rand(1, 3, 3, 180, 320, device=dev)
+nf = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+x = torch.rand(1, nf, 3, 180, 320, device=dev)
 y = m(x, 720, 1280)
 torch.cuda.synchronize()
 print(tuple(y.shape), float(y.abs().mean()))
