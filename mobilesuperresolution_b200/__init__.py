@@ -6,6 +6,7 @@ hand-written CUDA reached through the C ABI in ``include/b200sr.h``.  No Triton,
 from .masks import BinaryConv2d, rounding  # noqa: F401
 from .wdsr import BASIC_MODEL, NAS_MODEL, AggregationLayer, Block, Model, WdsrPlan  # noqa: F401
 from .split import Conv_sep, MyAggregationLayer, Split_Block  # noqa: F401
+from .graph import Graphed  # noqa: F401
 
 __version__ = "0.1.0"
 

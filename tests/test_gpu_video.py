@@ -431,3 +431,25 @@ def test_conv_last_plus_base_fused_tcgen05(V, planar):
     o = out.cpu()
     assert float((o[:, 2].double() - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max()))
     assert float((o[:, :2] - 9).abs().max()) == 0
+
+
+def test_graphed_helper_wdsr_and_clip(V):
+    """mobilesuperresolution_b200.Graphed: a forward replayed as one CUDA graph returns the eager result for new inputs."""
+    import types
+    import mobilesuperresolution_b200 as sr
+    torch.manual_seed(5)
+    p = types.SimpleNamespace(image_mean=0.5, num_channels=3, scale=4, num_blocks=3, num_residual_units=24, width_search=False, pretrained=False)
+    m = sr.BASIC_MODEL(p).cuda().eval().set_precision("bf16")
+    x = torch.rand(2, 3, 48, 64, device="cuda").bfloat16()
+    with torch.no_grad():
+        g = sr.Graphed(m, x)
+        x2 = torch.rand_like(x.float()).bfloat16()
+        assert torch.equal(g(x2), m(x2))
+        vsr = V.BasicVSR_origin(64, 1).cuda().eval().set_precision("bf16")
+        clip = torch.rand(1, 3, 3, 64, 64, device="cuda")
+        gv = sr.Graphed(vsr, clip, 256, 256)
+        clip2 = torch.rand_like(clip)
+        y = gv(clip2, clone=True)
+        assert torch.equal(y, vsr(clip2, 256, 256))
+        with pytest.raises(RuntimeError):
+            gv(torch.rand(1, 2, 3, 64, 64, device="cuda"))
