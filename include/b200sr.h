@@ -38,6 +38,9 @@ extern "C" {
 /* element types of activation tensors, and arithmetic precisions */
 #define B200SR_F32 0  /* float32 storage; true-fp32 FMA arithmetic                                  */
 #define B200SR_BF16 1 /* bfloat16 storage; bf16 tensor-core operands, fp32 accumulate/bias/residual */
+#define B200SR_U8 2   /* y_dtype of b200sr_wdsr_forward* / b200sr_wdsr_tail only (bf16 precision, tcgen05 tail): the 8-bit frame
+                       * (sr * 255).round().clamp(0, 255) of common/metrics.py:12 written by the tail epilogue -- a quarter of the
+                       * float32 output bytes over PCIe */
 
 /* flow_warp padding modes (models/spynet_arch.py:98 `padding_mode`) */
 #define B200SR_PAD_ZEROS 0

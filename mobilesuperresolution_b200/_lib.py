@@ -14,7 +14,7 @@ import torch  # noqa: F401  (loads libcudart.so.12 first so the library binds to
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libb200sr.so")
 
-F32, BF16 = 0, 1
+F32, BF16, U8 = 0, 1, 2
 PAD_ZEROS, PAD_BORDER = 0, 1
 
 
@@ -104,6 +104,8 @@ def dtype_code(dt: torch.dtype) -> int:
         return F32
     if dt == torch.bfloat16:
         return BF16
+    if dt == torch.uint8:
+        return U8          # output frames of the WDSR forward only (b200sr.h B200SR_U8)
     raise TypeError(f"b200sr: unsupported tensor dtype {dt} (float32 or bfloat16)")
 
 

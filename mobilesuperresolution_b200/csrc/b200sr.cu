@@ -55,7 +55,7 @@ uint16_t f2bf(float f) {  // round-to-nearest-even, same as __float2bfloat16_rn 
     return (uint16_t)(u >> 16);
 }
 
-size_t esize(int dtype) { return dtype == B200SR_F32 ? 4 : 2; }
+size_t esize(int dtype) { return dtype == B200SR_F32 ? 4 : dtype == B200SR_U8 ? 1 : 2; }
 
 // B200SR_CONV_IMPL = mma keeps the video path's 3x3 64 -> 64 convolutions on the mma.sync kernel (developer A/B switch, read per call)
 bool conv_tc5_enabled() {
@@ -441,6 +441,8 @@ int b200sr_wdsr_tail(const b200sr_wdsr_t *p, const void *trunk, const void *x, i
     int rc = check_common(p, n, h, w, precision, "wdsr_tail");
     if (rc) return rc;
     if (!trunk || !x || !y) return fail(B200SR_E_INVAL, "wdsr_tail: null tensor");
+    if (y_dtype == B200SR_U8 && (precision != B200SR_BF16 || !p->tc5_path()))
+        return fail(B200SR_E_UNSUPPORTED, "wdsr_tail: the 8-bit frame output is written by the tcgen05 tail only (bf16 precision, trunk of 24 channels)");
     const float out_add = p->add_mean ? p->mean : 0.f;
     if (precision == B200SR_F32)
         CU(launch_tail_f32(p->cp, p->scale, x_dtype, y_dtype, (const float *)trunk, x, y, p->d_tail_f32, n, h, w, p->mean,

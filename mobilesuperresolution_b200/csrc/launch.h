@@ -6,7 +6,7 @@
 namespace b200sr {
 
 // precision / dtype codes mirror include/b200sr.h
-constexpr int kF32 = 0, kBF16 = 1;
+constexpr int kF32 = 0, kBF16 = 1, kU8 = 2;   // kU8: output of the tcgen05 tail only
 
 int sm_count();  // cached multiprocessor count of the current device
 

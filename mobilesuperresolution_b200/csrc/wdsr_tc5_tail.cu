@@ -47,6 +47,8 @@ static cudaError_t tail_tc5_io(int xd, int yd, const void *trunk, const void *x,
     if (xd == kF32 && yd == kBF16) return tail_tc5_t<float, bf16, S>(trunk, x, y, wimg, N, H, W, mean, out_add, st);
     if (xd == kBF16 && yd == kF32) return tail_tc5_t<bf16, float, S>(trunk, x, y, wimg, N, H, W, mean, out_add, st);
     if (xd == kBF16 && yd == kBF16) return tail_tc5_t<bf16, bf16, S>(trunk, x, y, wimg, N, H, W, mean, out_add, st);
+    if (xd == kF32 && yd == kU8) return tail_tc5_t<float, uint8_t, S>(trunk, x, y, wimg, N, H, W, mean, out_add, st);
+    if (xd == kBF16 && yd == kU8) return tail_tc5_t<bf16, uint8_t, S>(trunk, x, y, wimg, N, H, W, mean, out_add, st);
     return cudaErrorInvalidValue;
 }
 

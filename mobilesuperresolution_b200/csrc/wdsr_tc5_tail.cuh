@@ -228,7 +228,18 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
                                 r[j] = __uint_as_float(v[ch]) + bias[ch] + out_add;
                             }
                         }
-                        if constexpr (S == 4 && sizeof(TOUT) == 2) {
+                        if constexpr (sizeof(TOUT) == 1) {
+                            // 8-bit frame: (sr * 255).round().clamp(0, 255)   common/metrics.py:12 (round half to even, like torch.round)
+                            uint32_t pk = 0;
+#pragma unroll
+                            for (int j = 0; j < S; ++j) pk |= (uint32_t)min(max(__float2int_rn(r[j] * 255.f), 0), 255) << (8 * j);
+                            if constexpr (S == 4) *reinterpret_cast<uint32_t *>(o) = pk;
+                            else if constexpr (S == 2) *reinterpret_cast<uint16_t *>(o) = (uint16_t)pk;
+                            else {
+#pragma unroll
+                                for (int j = 0; j < S; ++j) o[j] = (TOUT)((pk >> (8 * j)) & 255u);
+                            }
+                        } else if constexpr (S == 4 && sizeof(TOUT) == 2) {
                             *reinterpret_cast<uint2 *>(o) = make_uint2(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]));
                         } else if constexpr (S == 4 && sizeof(TOUT) == 4) {
                             *reinterpret_cast<float4 *>(o) = make_float4(r[0], r[1], r[2], r[3]);

@@ -361,6 +361,13 @@ class _WdsrNet(nn.Module, _PlanCacheMixin):
         _lib.require_cuda_tensor(x, "input")
         return self._get_plan(x.device).forward(x, self.precision)
 
+    def forward_u8(self, x: torch.Tensor) -> torch.Tensor:
+        """The forward with the 8-bit frame ``(sr * 255).round().clamp(0, 255)`` (common/metrics.py:12, what the reference's
+        evaluation turns every output into before PSNR / PNG) written straight from the tail kernel's epilogue: uint8 (N,3,sH,sW),
+        a quarter of the float32 bytes to bring back over PCIe.  bf16 precision on the tcgen05 path only (raises otherwise)."""
+        _lib.require_cuda_tensor(x, "input")
+        return self._get_plan(x.device).forward(x, self.precision, out_dtype=torch.uint8)
+
     def launches_per_forward(self) -> int:
         return self._plan.launches_per_forward()
 

@@ -306,3 +306,27 @@ def test_back_to_back_forwards_do_not_race(G):
             yb = m(xb)
             torch.cuda.synchronize()
             assert torch.equal(ya, ra) and torch.equal(yb, rb)
+
+
+@pytest.mark.gpu
+def test_forward_u8_matches_quantised_forward():
+    """The 8-bit frame written by the tcgen05 tail epilogue == (sr * 255).round().clamp(0, 255) of the same forward's float output
+    (common/metrics.py:12), and only the tcgen05 bf16 path offers it (fp32 precision raises: no silent conversion pass)."""
+    import types
+    import mobilesuperresolution_b200 as sr
+    torch.manual_seed(11)
+    for scale in (2, 4):
+        p = types.SimpleNamespace(image_mean=0.5, num_channels=3, scale=scale, num_blocks=2, num_residual_units=24, width_search=False,
+                                  pretrained=False)
+        m = sr.BASIC_MODEL(p).cuda().eval().set_precision("bf16")
+        x = torch.rand(2, 3, 40, 72, device="cuda")
+        with torch.no_grad():
+            plan = m.prepare()
+            yf = plan.forward(x, "bf16", out_dtype=torch.float32)          # same arithmetic, float32 store
+            yu = m.forward_u8(x)
+        assert yu.dtype == torch.uint8 and tuple(yu.shape) == (2, 3, 40 * scale, 72 * scale)
+        ref = (yf * 255).round().clamp(0, 255)
+        d = (yu.float() - ref).abs()
+        assert float(d.max()) <= 1.0 and float((d > 0).float().mean()) < 1e-3      # ties at x.5 may round differently after the fp32 mul
+    with pytest.raises(RuntimeError):
+        m.set_precision("fp32").forward_u8(x)
