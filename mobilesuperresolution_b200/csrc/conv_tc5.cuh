@@ -1,20 +1,26 @@
-// conv_tc5.cuh -- 3x3 "same" convolution, 64 -> 64 channels, bf16 NHWC, on tcgen05: the BasicVSR propagation trunks
-// (ConvResidualBlocks: 30 x [conv-ReLU-conv + x] per frame and direction, models/basicvsr_arch_origin.py:98-137) and conv_hr.
+// conv_tc5.cuh -- 3x3 "same" convolution from 64 (or 65..80) bf16 channels, on tcgen05: the BasicVSR propagation trunks
+// (ConvResidualBlocks: 30 x [conv-ReLU-conv + x] per frame and direction, models/basicvsr_arch_origin.py:98-137), the upsampler
+// convs upconv1 / upconv2 (64 -> 256 + PixelShuffle(2), :87-88), conv_hr (:89) and conv_last + bilinear base (:90-92).
 //
 //   y[n, oy, ox, co] = act( bias[co] + sum_{ky,kx,ci} x[n, oy+ky-1, ox+kx-1, ci] * w[co][ci][ky][kx] ) (+ residual)
 //
 // Same producer -> MMA -> epilogue chain as the WDSR tail (wdsr_tc5_tail.cuh), no builders: an implicit GEMM with pixels as M.
-//   warp 0      TMA      NCH cp.async.bulk.tensor.4d per tile (one per 8-channel chunk) of a 32 x 10 pixel box (30 x 8 outputs +
+//   warp 0      TMA      the filter image by ONE cp.async.bulk (a constant: in flight while the previous kernel drains), then NCH
+//                        cp.async.bulk.tensor.4d per tile (one per 8-channel chunk) of a 32 x 10 pixel box (30 x 8 outputs +
 //                        1-pixel halo) into chunk-planar shared memory [chunk][pixel][16 B]; out-of-image pixels (and channels past
 //                        cin) are zero-filled by the TMA unit (= the conv's zero padding); three (two for NCH = 10) tile buffers.
 //                        x is NHWC (every 16-byte pixel row of a chunk is its own TMA request: 320 per chunk) or planar-8
 //                        [n][c/8][h][w][8] (a box row is 512 contiguous bytes: 10 requests per chunk) -- the trunk's private tensors
-//   warp 1      MMA      per 128-pixel M-tile (four 32-pixel box rows) 36 tcgen05.mma (M = 128, N = 64, K = 16): a tap is a constant
-//                        pixel offset of the A operand's start address (the two box columns right of the 30 outputs compute
-//                        don't-care rows), the two 8-channel chunks of a K step are paired through the LBO stride
-//   warps 2-5 / 6-9      epilogue of the tile's first / second M-tile: tcgen05.ld -> + bias -> activation -> (+ residual) -> 128-byte
-//                        NHWC pixel stores.  Activations may live inside wider NHWC tensors (channel stride / offset).
-// The generic mma.sync kernel (conv.cuh) ran these convolutions at ~110 TFLOP/s; they are 77 % of a BasicVSR clip's FLOPs.
+//   warp 1      MMA      per 128-pixel M-tile (four 32-pixel box rows) 9 * NCH / 2 tcgen05.mma (M = 128, N = NOUT, K = 16): a tap is a
+//                        constant pixel offset of the A operand's start address (the two box columns right of the 30 outputs
+//                        compute don't-care rows), the two 8-channel chunks of a K step are paired through the LBO stride
+//   warps 2-5 / 6-9      epilogue of the tile's first / second M-tile: tcgen05.ld -> + bias -> activation -> (+ residual) -> bf16
+//                        stores: NHWC pixel rows (channel windows of wider tensors allowed), planar-8 planes, or PixelShuffle(2)
+//                        folded into either.  cout = 64 G: a CTA serves one group of 64 output channels (own filter image).
+//                        NOUT = 16 ("rgb" form, 64 -> 3): 3 accumulator columns + bias + x4 bilinear base -> fp32 NCHW frame.
+// The generic mma.sync kernel (conv.cuh) ran these convolutions at ~110-139 TFLOP/s; they are 90 % of a BasicVSR clip's FLOPs.
+// Measured (profiles/r01_conv_tc5_ncu.md): 925 TFLOP/s at 720 x 1280 = 66 % of the sustained bf16 peak -- an SS MMA with N = 64
+// reads 6 KB of operands from shared memory for 32 clk of tensor work, so ~2/3 of peak is this operand shape's ceiling.
 #pragma once
 #include <cuda.h>
 
