@@ -30,14 +30,17 @@
 
 namespace b200sr {
 namespace tc5conv {
-constexpr int TWO = 30, TH = 8, BW = 32, BH = TH + 2, NTHREADS = 320;
-constexpr int PLANE_PX = BW * BH + 8;            // + 8 zero pixels: the last taps of the second M-tile read past the box
-constexpr int PLANE = PLANE_PX * 16;             // 5,248 B
+constexpr int TWO = 30, BW = 32, NTHREADS = 320;
 constexpr int CTRL = 256;
 enum Bar { TC_FULL = 0 /*3*/, TC_EMPTY = 3 /*3*/, D_FULL = 6, D_EMPTY = 8, W_READY = 10, NBARS = 11 };
 // NCH = 8-channel chunks of the input: 8 (64 channels) or 10 (65..80 channels: the trunk's first conv on [x_i | warped feat])
 // NOUT = output channels per CTA: 64, or 16 for the 64 -> 3 "rgb" form (conv_last + bilinear base, fp32 NCHW store)
-template <int NCH, int NOUT = 64> struct Cfg {
+// MT = 128-pixel M-tiles per tile: 2 (30 x 8 outputs), or 1 (30 x 4) for launches of only a few tiles per CTA -- one 180 x 320 frame
+//      on a 74-CTA grid is 3.4 rounds of 30 x 8 tiles (4 are paid for) but 6.7 rounds of 30 x 4 tiles (7 half-size ones)
+template <int NCH, int NOUT = 64, int MT = 2> struct Cfg {
+    static constexpr int TH = 4 * MT, BH = TH + 2;
+    static constexpr int PLANE_PX = BW * BH + 8;            // + 8 zero pixels: the last taps of the last M-tile read past the box
+    static constexpr int PLANE = PLANE_PX * 16;             // 5,248 B (3,200 for MT = 1)
     static constexpr int TILE_BUF = NCH * PLANE;            // 41,984 / 52,480 B
     static constexpr int NBUF = NCH <= 8 ? 3 : 2;
     static constexpr int W_SBO = 9 * NCH * 128;             // weight image [NOUT/8 row groups][9 * NCH (tap, chunk) slices][8 rows][16 B]
@@ -69,13 +72,13 @@ __device__ __forceinline__ float bilinear_x4(const float *__restrict__ p, int h,
     return (1.f - ly) * ((1.f - lx) * p[y0 * w + x0] + lx * p[y0 * w + x1]) + ly * ((1.f - lx) * p[y1 * w + x0] + lx * p[y1 * w + x1]);
 }
 
-template <int NCH, int NOUT>
+template <int NCH, int NOUT, int MT>
 __global__ void __launch_bounds__(tc5conv::NTHREADS, 1)
 conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, const uint8_t *__restrict__ wimg, int tiles_x, int tiles_y,
                        int ntiles) {
     using namespace tc5conv;
-    using C = Cfg<NCH, NOUT>;
-    constexpr int TILE_BUF = C::TILE_BUF, NBUF = C::NBUF, W_SBO = C::W_SBO, W_BYTES = C::W_BYTES;
+    using C = Cfg<NCH, NOUT, MT>;
+    constexpr int TILE_BUF = C::TILE_BUF, NBUF = C::NBUF, W_SBO = C::W_SBO, W_BYTES = C::W_BYTES, TH = C::TH, BH = C::BH, PLANE = C::PLANE;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *ctrl = smem_raw;
     uint8_t *tc = smem_raw + CTRL;           // NBUF x TILE_BUF
@@ -153,10 +156,11 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
         const uint32_t idesc = tc5::idesc_bf16_f32(128, NOUT);
         const uint64_t bw = tc5::smem_desc(w_u, 128, W_SBO), a0d = tc5::smem_desc(tc_u, PLANE, 128);   // A: chunk pairs through LBO = plane stride
         tc5::mbar_wait(bar(W_READY), 0);
-        for (int g = 0; g < 2 * nmine; ++g) {
-            const int it = g >> 1, m = g & 1, b = it % NBUF, e = m;
+        // M-tiles are numbered j = MT * it + m across the CTA's tiles; accumulator (and epilogue warpgroup) e = j & 1, k-th use = j >> 1
+        for (int j = 0; j < MT * nmine; ++j) {
+            const int it = j / MT, m = j % MT, b = it % NBUF, e = j & 1;
             if (m == 0) tc5::mbar_wait(bar(TC_FULL + b), (it / NBUF) & 1);
-            tc5::mbar_wait(bar(D_EMPTY + e), (it & 1) ^ 1);
+            tc5::mbar_wait(bar(D_EMPTY + e), ((j >> 1) & 1) ^ 1);
             tc5::fence_after_sync();
             if (leader) {
                 const uint32_t d = tmem + e * NOUT;
@@ -168,11 +172,14 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
                     tc5::mma_ss(d, abase + (uint64_t)(aoff >> 4), bw + (uint64_t)(8 * (t * NCH + 2 * cp)), idesc, i > 0);
                 }
                 tc5::commit(bar(D_FULL + e));
-                if (m == 1) tc5::commit(bar(TC_EMPTY + b));
+                if (m == MT - 1) tc5::commit(bar(TC_EMPTY + b));
             }
             __syncwarp();
         }
-        if (nmine > 0) tc5::mbar_wait(bar(D_FULL + 1), (nmine - 1) & 1);  // every MMA retired
+        if (nmine > 0) {   // every MMA retired
+            const int jl = MT * nmine - 1;
+            tc5::mbar_wait(bar(D_FULL + (jl & 1)), (jl >> 1) & 1);
+        }
     } else {
         // ============================== epilogue: M-tile e of every tile ==============================
         const int e = (warp - 2) >> 2;
@@ -182,10 +189,11 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
         const bf16 *res = reinterpret_cast<const bf16 *>(a.residual);
         const int act = a.act;
         tc5::pdl_wait();
-        for (int it = 0; it < nmine; ++it) {
+        for (int j = e; j < MT * nmine; j += 2) {
+            const int it = j / MT, m = j % MT;
             int x0, y0, n;
             tile_origin(it, x0, y0, n);
-            const int p = e * 128 + row, by = p >> 5, bx = p & 31;
+            const int p = m * 128 + row, by = p >> 5, bx = p & 31;
             const int gy = y0 + by, gx = x0 + bx;
             const bool ok = bx < TWO && gx < W && gy < H;
             const long long pix = ((long long)n * H + gy) * W + gx;
@@ -197,7 +205,7 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
 #pragma unroll
                 for (int q = 0; q < 8; ++q) rv[q] = rp[q * rstep];   // plain loads: y may be the residual tensor itself (in-place add)
             }
-            tc5::mbar_wait(bar(D_FULL + e), it & 1);
+            tc5::mbar_wait(bar(D_FULL + e), (j >> 1) & 1);
             tc5::fence_after_sync();
             if constexpr (NOUT == 16) {
                 // "rgb" form: 3 of the 16 accumulator columns + bias + x4 bilinear base -> fp32 NCHW (lanes = consecutive x: coalesced)

@@ -163,12 +163,14 @@ def test_cfg4_basicvsr_clip_properties(V):
     assert port.psnr_db(y2[:1].cpu(), yf.cpu()) >= 50.0
 
 
+@pytest.mark.parametrize("mt", ["1", "2"])
 @pytest.mark.parametrize("n,h,w", [(1, 8, 30), (2, 19, 37), (1, 180, 320), (3, 33, 61)])
 @pytest.mark.parametrize("act,with_res", [(0, True), (1, False), (2, True)])
-def test_conv3x3_c64_tcgen05(V, n, h, w, act, with_res, monkeypatch):
+def test_conv3x3_c64_tcgen05(V, n, h, w, act, with_res, mt, monkeypatch):
     """The tcgen05 form of the BasicVSR trunk convolution (3x3, 64 -> 64, bf16 NHWC; models/basicvsr_arch_origin.py:115-137):
     against torch fp32 on the bf16-rounded operands, and against the mma.sync kernel it replaces (B200SR_CONV_IMPL=mma).
     Exercises partial tiles in x and y, several images per launch and the image border (TMA zero fill = the conv's zero padding)."""
+    monkeypatch.setenv("B200SR_CONV_MT", mt)      # both tile heights (30 x 4 and 30 x 8 outputs); the launcher picks by tiles per CTA
     g = torch.Generator().manual_seed(n * 1000 + h * 10 + w + act)
     conv = nn.Conv2d(64, 64, 3, 1, 1)
     with torch.no_grad():
