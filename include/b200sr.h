@@ -156,6 +156,11 @@ B200SR_API int b200sr_flow_warp_nchw(const float *x_dev, const float *flow_dev, 
 B200SR_API int b200sr_flow_warp_nhwc(const void *x_dev, const float *flow_nchw_dev, void *y_dev, int n, int c, int h, int w,
                           int padding_mode, int dtype, void *stream);
 
+/* The same warp written into channels [y_coff, y_coff + c) of a wider NHWC tensor of y_cstride channels: the warped features land
+ * directly inside the trunk's input (torch.cat([x_i, feat_prop], 1), models/basicvsr_arch_origin.py:69,81) -- no copy. */
+B200SR_API int b200sr_flow_warp_nhwc_into(const void *x_dev, const float *flow_nchw_dev, void *y_dev, int y_cstride, int y_coff, int n, int c,
+                                          int h, int w, int padding_mode, int dtype, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Video path building blocks (SPyNet + BasicVSR).  The Python mirror (mobilesuperresolution_b200/video.py)
  * sequences these exactly as the reference's forward does:

@@ -511,6 +511,17 @@ int b200sr_flow_warp_nhwc(const void *x, const float *flow, void *y, int n, int 
     return 0;
 }
 
+int b200sr_flow_warp_nhwc_into(const void *x, const float *flow, void *y, int y_cs, int y_co, int n, int c, int h, int w, int padding_mode,
+                               int dtype, void *stream) {
+    if (!x || !flow || !y) return fail(B200SR_E_INVAL, "flow_warp_nhwc_into: null tensor");
+    if (padding_mode != B200SR_PAD_ZEROS && padding_mode != B200SR_PAD_BORDER)
+        return fail(B200SR_E_UNSUPPORTED, "flow_warp_nhwc_into: padding_mode %d", padding_mode);
+    if (y_cs < c || y_co < 0 || y_co + c > y_cs) return fail(B200SR_E_INVAL, "flow_warp_nhwc_into: channel window outside tensor");
+    cudaError_t e = launch_flow_warp_nhwc(x, flow, y, n, c, h, w, padding_mode == B200SR_PAD_BORDER, dtype, (cudaStream_t)stream, y_cs, y_co);
+    if (e != cudaSuccess) return cuda_fail(e, "flow_warp_nhwc_into (c, y_cstride, y_coff multiples of 8 (bf16) / 4 (f32); c*esize/16 in {1,2,3,4,6,8,16})");
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Split_Block (the fork's searchable block body)
 // ---------------------------------------------------------------------------------------------------------

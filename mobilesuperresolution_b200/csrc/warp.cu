@@ -119,7 +119,7 @@ cudaError_t launch_flow_warp_nchw(const float *x, const float *flow, long long f
 template <typename T, int Q>
 __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const T *__restrict__ x, const float *__restrict__ flow,
                                                              T *__restrict__ y, int N, int C, int H, int W, int border,
-                                                             int tiles_x, int tiles_y) {
+                                                             int tiles_x, int tiles_y, int y_cs, int y_co) {
     constexpr int VEC = 16 / sizeof(T);
     constexpr bool kPow2 = (Q & (Q - 1)) == 0 && Q <= 32;
     constexpr int PPS = kPow2 ? 32 / Q : 1;            // pixels per step
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const T *__restrict
         const int cy0 = min(max(b.y0, 0), H - 1), cy1 = min(max(b.y0 + 1, 0), H - 1);
         const int o00 = cy0 * W + cx0, o01 = cy0 * W + cx1, o10 = cy1 * W + cx0, o11 = cy1 * W + cx1;   // < 2^31: per-image pixel index
         const T *xi = x + (long long)n * H * W * C;
-        T *yrow = y + (((long long)n * H + yh) * W + (long long)tx * WTX) * C;
+        T *yrow = y + (((long long)n * H + yh) * W + (long long)tx * WTX) * y_cs + y_co;   // y may be a channel window of a wider tensor
         const int npx = min(WTX, W - tx * WTX);
 #pragma unroll 2
         for (int s0 = 0; s0 < 32; s0 += PPS) {
@@ -195,47 +195,46 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const T *__restrict
                     o.z = pack_bf16x2(acc[4], acc[5]);
                     o.w = pack_bf16x2(acc[6], acc[7]);
                 }
-                __stcs(reinterpret_cast<uint4 *>(yrow + (long long)src * C + q * VEC), o);
+                __stcs(reinterpret_cast<uint4 *>(yrow + (long long)src * y_cs + q * VEC), o);
             }
         }
     }
 }
 
 template <typename T, int Q>
-static cudaError_t warp_nhwc_t(const void *x, const float *flow, void *y, int n, int c, int h, int w, int border,
+static cudaError_t warp_nhwc_t(const void *x, const float *flow, void *y, int n, int c, int h, int w, int border, int y_cs, int y_co,
                                cudaStream_t st) {
     const int tx = ceil_div(w, WTX), ty = ceil_div(h, WTY);
     long long blocks = (long long)n * tx * ty;
     const long long cap = (long long)sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    flow_warp_nhwc_kernel<T, Q><<<(unsigned)blocks, 256, 0, st>>>((const T *)x, flow, (T *)y, n, c, h, w, border, tx, ty);
+    flow_warp_nhwc_kernel<T, Q><<<(unsigned)blocks, 256, 0, st>>>((const T *)x, flow, (T *)y, n, c, h, w, border, tx, ty, y_cs, y_co);
     return cudaGetLastError();
 }
 
 template <typename T>
-static cudaError_t warp_nhwc_q(int Q, const void *x, const float *flow, void *y, int n, int c, int h, int w, int border,
+static cudaError_t warp_nhwc_q(int Q, const void *x, const float *flow, void *y, int n, int c, int h, int w, int border, int y_cs, int y_co,
                                cudaStream_t st) {
     switch (Q) {
-        case 1: return warp_nhwc_t<T, 1>(x, flow, y, n, c, h, w, border, st);
-        case 2: return warp_nhwc_t<T, 2>(x, flow, y, n, c, h, w, border, st);
-        case 3: return warp_nhwc_t<T, 3>(x, flow, y, n, c, h, w, border, st);
-        case 4: return warp_nhwc_t<T, 4>(x, flow, y, n, c, h, w, border, st);
-        case 6: return warp_nhwc_t<T, 6>(x, flow, y, n, c, h, w, border, st);
-        case 8: return warp_nhwc_t<T, 8>(x, flow, y, n, c, h, w, border, st);
-        case 16: return warp_nhwc_t<T, 16>(x, flow, y, n, c, h, w, border, st);
+        case 1: return warp_nhwc_t<T, 1>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
+        case 2: return warp_nhwc_t<T, 2>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
+        case 3: return warp_nhwc_t<T, 3>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
+        case 4: return warp_nhwc_t<T, 4>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
+        case 6: return warp_nhwc_t<T, 6>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
+        case 8: return warp_nhwc_t<T, 8>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
+        case 16: return warp_nhwc_t<T, 16>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
     }
     return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_flow_warp_nhwc(const void *x, const float *flow_nchw, void *y, int n, int c, int h, int w, int border,
-                                  int dtype, cudaStream_t st) {
+                                  int dtype, cudaStream_t st, int y_cs, int y_co) {
     if ((long long)n * h * w == 0) return cudaSuccess;
-    if (dtype == kF32) {
-        if (c % 4) return cudaErrorInvalidValue;
-        return warp_nhwc_q<float>(c / 4, x, flow_nchw, y, n, c, h, w, border, st);
-    }
-    if (c % 8) return cudaErrorInvalidValue;
-    return warp_nhwc_q<bf16>(c / 8, x, flow_nchw, y, n, c, h, w, border, st);
+    if (y_cs <= 0) y_cs = c, y_co = 0;
+    const int vec = dtype == kF32 ? 4 : 8;     // the window must keep the 16-byte stores aligned
+    if (c % vec || y_cs % vec || y_co % vec || y_co + c > y_cs) return cudaErrorInvalidValue;
+    if (dtype == kF32) return warp_nhwc_q<float>(c / 4, x, flow_nchw, y, n, c, h, w, border, y_cs, y_co, st);
+    return warp_nhwc_q<bf16>(c / 8, x, flow_nchw, y, n, c, h, w, border, y_cs, y_co, st);
 }
 
 }  // namespace b200sr

@@ -43,16 +43,19 @@ def flow_warp(x: torch.Tensor, flow: torch.Tensor, interp_mode: str = "bilinear"
     return y
 
 
-def flow_warp_nhwc(x: torch.Tensor, flow_nchw: torch.Tensor, padding_mode: str = "zeros") -> torch.Tensor:
-    """Internal-layout warp: ``x`` (n,h,w,c) float32|bfloat16 contiguous, ``flow_nchw`` (n,2,h,w) float32."""
+def flow_warp_nhwc(x: torch.Tensor, flow_nchw: torch.Tensor, padding_mode: str = "zeros", out: Optional[torch.Tensor] = None,
+                   out_coff: int = 0) -> torch.Tensor:
+    """Internal-layout warp: ``x`` (n,h,w,c) float32|bfloat16 contiguous, ``flow_nchw`` (n,2,h,w) float32.  ``out``: write into
+    channels [out_coff, out_coff + c) of this wider (n,h,w,C) tensor instead of a new one (a concatenation without the copy)."""
     _lib.require_cuda_tensor(x, "x")
     assert x.is_contiguous() and flow_nchw.is_contiguous() and flow_nchw.dtype == torch.float32
     n, h, w, c = x.shape
     assert tuple(flow_nchw.shape) == (n, 2, h, w)
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if out is None else out
+    assert y.is_contiguous() and y.dtype == x.dtype and tuple(y.shape[:3]) == (n, h, w)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().b200sr_flow_warp_nhwc(
-            _ptr(x), _ptr(flow_nchw), _ptr(y), n, c, h, w,
+        _lib.check(_lib.lib().b200sr_flow_warp_nhwc_into(
+            _ptr(x), _ptr(flow_nchw), _ptr(y), y.shape[-1], out_coff, n, c, h, w,
             _lib.PAD_BORDER if padding_mode == "border" else _lib.PAD_ZEROS, _lib.dtype_code(x.dtype),
             _lib.current_stream_ptr(x.device)))
     return y
@@ -144,9 +147,25 @@ class _VideoPlanMixin:
         own = [(n, m) for n, m in self.named_modules() if isinstance(m, nn.Conv2d) and not n.startswith("spynet.")]
         sig = (str(device),) + tuple((p.data_ptr(), p._version) for _, m in own for p in m.parameters())
         if getattr(self, "_conv_sig", None) != sig:
-            self._conv_cache = {n: _ConvHandle(m, device) for n, m in own}
+            rot = self._feat_first()
+            self._conv_cache = {n: _ConvHandle(_rotate_in_channels(m, 3) if rot and n.endswith("_trunk.main.0") else m, device)
+                                for n, m in own}
             self._conv_sig = sig
         return self._conv_cache
+
+    def _feat_first(self) -> bool:
+        """BasicVSR trunks: keep the trunk input as [feat | x_i] (see propagate) when num_feat is a multiple of 8."""
+        return getattr(self, "num_feat", 0) > 0 and self.num_feat % 8 == 0
+
+
+def _rotate_in_channels(conv: nn.Conv2d, k: int) -> nn.Conv2d:
+    """The same convolution for an input whose first ``k`` channels were moved to the end."""
+    r = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, bias=conv.bias is not None)
+    with torch.no_grad():
+        r.weight.copy_(torch.cat([conv.weight[:, k:], conv.weight[:, :k]], 1))
+        if conv.bias is not None:
+            r.bias.copy_(conv.bias)
+    return r
 
 
 class BasicModule(nn.Module):
@@ -344,6 +363,12 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
         x = x.contiguous()
         L = _lib.lib()
 
+        # trunk input = cat([x_i, feat]) (:69,81).  When the feature count keeps the stores 16-byte aligned the buffer holds
+        # [feat | x_i | 0] instead -- the first conv's handle was built with its input channels rotated the same way (_convs) -- so that
+        # flow_warp writes the warped features in place
+        feat_first = self._feat_first()
+        xco = nf if feat_first else 0
+
         def run(trunk: str, order, flows, flow_index):
             feats: List[Optional[torch.Tensor]] = [None] * n
             feat = None
@@ -353,10 +378,13 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
                 xi = x[:, i]
                 with torch.cuda.device(dev):
                     _lib.check(L.b200sr_nchw3_to_nhwc(_ptr(xi), _lib.dtype_code(x.dtype), x.stride(0), _ptr(buf), _lib.dtype_code(adt),
-                                                      b, h, w, cs, 0, st))
+                                                      b, h, w, cs, xco, st))
                 if step > 0:
                     fl = flows[:, flow_index(i)].contiguous()
-                    buf[..., 3:3 + nf] = flow_warp_nhwc(feat, fl)
+                    if feat_first:
+                        flow_warp_nhwc(feat, fl, out=buf)          # straight into channels [0, nf) of the trunk input
+                    else:
+                        buf[..., 3:3 + nf] = flow_warp_nhwc(feat, fl)
                 feat = self._trunk(convs, trunk, buf, nb)
                 feats[i] = feat
             return feats
