@@ -64,5 +64,5 @@ for prec in ("fp32", "bf16"):
 m = video.MotionVectorVSR(64, 15).to(dev).eval().set_precision("bf16")
 xm = torch.rand(1, 15, 5, 180, 320, device=dev)
 xm[:, :, 3:] = (xm[:, :, 3:] - 0.5) * 8
-us = timeit(lambda: m(xm, 720, 1280), reps=3, warm=1)
+us = timeit(lambda: m(xm, 720, 1280), reps=5, warm=3)
 print(f"MotionVectorVSR(64,15) bf16: clip 15x180x320 -> 720x1280: {us / 1e3:9.2f} ms/clip = {15 / us * 1e6:8.1f} frames/s")
