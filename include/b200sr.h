@@ -196,6 +196,14 @@ B200SR_API int b200sr_conv_tcgen05_ok(const b200sr_conv_t *conv);
  * with half-size grids they share the SMs instead of queueing behind each other (14.7 -> 12.4 ms per 15-frame clip). */
 B200SR_API int b200sr_conv_set_max_ctas(b200sr_conv_t *conv, int max_ctas);
 
+/* ConvResidualBlocks.forward (models/basicvsr_arch_origin.py:98-137) as one host call on the tcgen05 kernels, bf16:
+ *   t = lrelu(first(buf));  for k: o = relu(conv1_k(t)); t = t + conv2_k(o);  out = t
+ * blocks = {conv1_0, conv2_0, conv1_1, ...} (2 * num_block handles, 3x3 64 -> 64); first: 3x3 (64..80) -> 64 on the NHWC trunk input
+ * `buf` (n,h,w,buf_cstride); t, o: planar-8 scratch tensors of n*h*w*64 bf16 each; out: NHWC (n,h,w,64).  2 * num_block + 1 launches
+ * on `stream`, no synchronisation.  Fails (B200SR_E_UNSUPPORTED) if a conv is not served by the tcgen05 kernel. */
+B200SR_API int b200sr_vsr_trunk_forward(const b200sr_conv_t *first, const b200sr_conv_t *const *blocks, int num_block, const void *buf_dev,
+                                        int buf_cstride, void *t_dev, void *o_dev, void *out_dev, int n, int h, int w, void *stream);
+
 /* conv_last + base of BasicVSR_origin's reconstruction in ONE kernel (models/basicvsr_arch_origin.py:90-92):
  *   y[n,c,Y,X] = conv3x3(x)[n,c,Y,X] + F.interpolate(base, scale_factor=4, mode='bilinear', align_corners=False)[n,c,Y,X]
  * conv = a 3x3 64 -> 3 conv; x: n x H x W x 64 bf16 (NHWC channel window or planar-8); base: float32 NCHW (3, H/4, W/4) per image,

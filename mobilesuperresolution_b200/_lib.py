@@ -58,6 +58,7 @@ SYMBOLS = {
     "b200sr_conv_forward_layout": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
                                            c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_conv_tcgen05_ok": (c_int, [c_void_p]),
+    "b200sr_vsr_trunk_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b200sr_vsr_conv_last_base": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                                           c_void_p]),
     "b200sr_conv_set_max_ctas": (c_int, [c_void_p, c_int]),

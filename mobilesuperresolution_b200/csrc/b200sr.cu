@@ -730,6 +730,21 @@ int b200sr_vsr_conv_last_base(const b200sr_conv_t *c, const void *x, int x_layou
     return 0;
 }
 
+int b200sr_vsr_trunk_forward(const b200sr_conv_t *first, const b200sr_conv_t *const *blocks, int num_block, const void *buf, int buf_cs,
+                             void *t, void *o, void *out, int n, int h, int w, void *stream) {
+    if (!first || !blocks || num_block < 1 || !buf || !t || !o || !out) return fail(B200SR_E_INVAL, "vsr_trunk_forward: bad argument");
+    const int P = B200SR_TRUNK_PLANAR8, N_ = B200SR_TRUNK_NHWC, bf = B200SR_BF16;
+    int rc = b200sr_conv_forward_layout(first, buf, N_, buf_cs, 0, t, P, 64, 0, nullptr, 0, 0, n, h, w, B200SR_ACT_LRELU01, 1, bf, bf, bf, stream);
+    for (int k = 0; k < num_block && !rc; ++k) {
+        rc = b200sr_conv_forward_layout(blocks[2 * k], t, P, 64, 0, o, P, 64, 0, nullptr, 0, 0, n, h, w, B200SR_ACT_RELU, 1, bf, bf, bf, stream);
+        if (rc) break;
+        const bool last = k + 1 == num_block;   // conv2 adds its residual in place (y = t + conv(o)); the last one writes the NHWC features
+        rc = b200sr_conv_forward_layout(blocks[2 * k + 1], o, P, 64, 0, last ? out : t, last ? N_ : P, 64, 0, t, 64, 0, n, h, w,
+                                        B200SR_ACT_NONE, 1, bf, bf, bf, stream);
+    }
+    return rc;
+}
+
 int b200sr_conv_forward(const b200sr_conv_t *c, const void *x, int x_cs, int x_co, void *y, int y_cs, int y_co, const void *res, int r_cs,
                         int r_co, int n, int h, int w, int act, int shuffle, int in_dtype, int out_dtype, int precision, void *stream) {
     return b200sr_conv_forward_layout(c, x, B200SR_TRUNK_NHWC, x_cs, x_co, y, B200SR_TRUNK_NHWC, y_cs, y_co, res, r_cs, r_co, n, h, w, act,

@@ -321,34 +321,20 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
                 o = convs[f"{name}.main.2.{k}.conv1"](t, self.precision, ACT_RELU)
                 t = convs[f"{name}.main.2.{k}.conv2"](o, self.precision, ACT_NONE, residual=t)
             return t
-        # 2 * num_block + 1 dependent launches of a few microseconds each: keep the host side as lean as the device side -- one
-        # device guard and stream lookup, raw ABI calls, two planar-8 buffers (conv2 adds its residual in place: y = t + conv(o))
+        # 2 * num_block + 1 dependent launches of a few microseconds each: the host side is ONE ABI call (b200sr_vsr_trunk_forward
+        # sequences them in C), two planar-8 buffers (conv2 adds its residual in place: y = t + conv(o))
         n, h, w, cs = buf.shape
         dev = buf.device
         t = torch.empty((n, 8, h, w, 8), dtype=torch.bfloat16, device=dev)
         o = torch.empty_like(t)
         out = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=dev)
-        fwd = _lib.lib().b200sr_conv_forward_layout
-        pb, pt, po, pout = buf.data_ptr(), t.data_ptr(), o.data_ptr(), out.data_ptr()
-        bf = _lib.BF16
         hkey = "__handles__:" + name   # lives and dies with this set of conv handles
         if hkey not in convs:
-            convs[hkey] = [(convs[f"{name}.main.2.{k}.conv1"]._h, convs[f"{name}.main.2.{k}.conv2"]._h) for k in range(num_block)]
-        handles = convs[hkey]
+            hs = [convs[f"{name}.main.2.{k}.{c}"]._h for k in range(num_block) for c in ("conv1", "conv2")]
+            convs[hkey] = (ctypes.c_void_p * len(hs))(*[h.value for h in hs])
         with torch.cuda.device(dev):
-            st = _lib.current_stream_ptr(dev)
-            rc = fwd(first._h, pb, 0, cs, 0, pt, 1, 64, 0, None, 0, 0, n, h, w, ACT_LRELU, 1, bf, bf, bf, st)
-            for k, (h1, h2) in enumerate(handles):
-                if rc:
-                    break
-                rc = fwd(h1, pt, 1, 64, 0, po, 1, 64, 0, None, 0, 0, n, h, w, ACT_RELU, 1, bf, bf, bf, st)
-                if rc:
-                    break
-                if k + 1 < num_block:
-                    rc = fwd(h2, po, 1, 64, 0, pt, 1, 64, 0, pt, 64, 0, n, h, w, ACT_NONE, 1, bf, bf, bf, st)
-                else:   # the features the callers (flow_warp, fusion) read are NHWC
-                    rc = fwd(h2, po, 1, 64, 0, pout, 0, 64, 0, pt, 64, 0, n, h, w, ACT_NONE, 1, bf, bf, bf, st)
-            _lib.check(rc)
+            _lib.check(_lib.lib().b200sr_vsr_trunk_forward(first._h, convs[hkey], num_block, buf.data_ptr(), cs, t.data_ptr(), o.data_ptr(),
+                                                           out.data_ptr(), n, h, w, _lib.current_stream_ptr(dev)))
         return out
 
     def propagate(self, x: torch.Tensor, flows_forward: torch.Tensor, flows_backward: torch.Tensor):
