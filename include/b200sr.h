@@ -184,7 +184,7 @@ B200SR_API int b200sr_conv_forward(const b200sr_conv_t *conv, const void *x_dev,
  * [n][channels/8][h][w][8] bf16 (channel count a multiple of 8, no channel window), is what the BasicVSR propagation trunks
  * (ConvResidualBlocks, models/basicvsr_arch_origin.py:98-137) and SPyNet's BasicModule (models/spynet_arch.py:17-22) keep
  * their private tensors in: only the tcgen05 kernels take it -- 3x3 (64..80) -> 64 k (k <= 4, PixelShuffle(2) store for the
- * upsampler convs) and 7x7 (8|16 -> 32, 32 -> 64, 64 -> 32, 32 -> 16) -- in bf16 precision with bf16 tensors; anything else
+ * upsampler convs), 1x1 128 -> 64 k (NHWC input) and 7x7 (8|16 -> 32, 32 -> 64, 64 -> 32, 32 -> 16) -- in bf16 precision with bf16 tensors; anything else
  * returns B200SR_E_UNSUPPORTED.  The residual is laid out like x.  b200sr_conv_tcgen05_ok() != 0 says such a kernel exists
  * for this conv's shape (developer switch B200SR_CONV_IMPL=mma turns them off). */
 B200SR_API int b200sr_conv_forward_layout(const b200sr_conv_t *conv, const void *x_dev, int x_layout, int x_cstride, int x_coff, void *y_dev,

@@ -620,6 +620,17 @@ int b200sr_conv_create(int cin, int cout, int k, const float *w, const float *bi
             return rc;
         }
     }
+    if (cin == 128 && cout % 64 == 0 && cout <= 256 && k == 1) {
+        // 1x1 form of the tcgen05 kernel (fusion conv): per group of 64 outputs [8 row groups][16 chunk slices][8 rows][16 B]
+        const size_t img = (size_t)8 * 16 * 64;
+        std::vector<uint16_t> wi(img * (cout / 64), 0);
+        for (int o = 0; o < cout; ++o)
+            for (int i = 0; i < 128; ++i) wi[(o / 64) * img + (((size_t)(o % 64 / 8) * 16 + i / 8) * 8 + o % 8) * 8 + i % 8] = f2bf(w[(size_t)o * 128 + i]);
+        if ((rc = upload(wi.data(), wi.size() * 2, (void **)&c->d_w_tc5))) {
+            b200sr_conv_destroy(c);
+            return rc;
+        }
+    }
     if (cin == 64 && cout == 3 && k == 3) {
         // "rgb" form of the tcgen05 3x3 kernel (conv_last): 16 output rows (3 used), [2 row groups][72 slices][8 rows][16 B]
         std::vector<uint16_t> wi((size_t)2 * 72 * 64, 0);
@@ -688,7 +699,7 @@ int b200sr_conv_forward_layout(const b200sr_conv_t *c, const void *x, int x_layo
     ConvArgs a;
     a.x = x, a.y = y, a.residual = res, a.bias = c->d_bias;
     a.n = n, a.h = h, a.w_ = w, a.cin = c->cin, a.cout = c->cout, a.x_cs = x_cs, a.x_co = x_co, a.y_cs = y_cs, a.y_co = y_co, a.r_cs = r_cs,
-    a.r_co = r_co, a.act = act, a.shuffle = shuffle, a.x_planar = xp, a.y_planar = yp, a.max_ctas = c->max_ctas;
+    a.r_co = r_co, a.act = act, a.shuffle = shuffle, a.x_planar = xp, a.y_planar = yp, a.max_ctas = c->max_ctas, a.ks = c->k;
     if (precision == B200SR_F32) {
         a.w = c->d_w_f32, a.cinp = c->cinp_f32, a.coutp = c->coutp_f32;
     } else {
@@ -700,8 +711,8 @@ int b200sr_conv_forward_layout(const b200sr_conv_t *c, const void *x, int x_layo
         if (e7 != cudaSuccess) return cuda_fail(e7, "conv_forward (tcgen05 7x7)");
         return 0;
     }
-    if (precision == B200SR_BF16 && in_dtype == B200SR_BF16 && out_dtype == B200SR_BF16 && c->d_w_tc5 && conv_tc5_enabled() && c->k == 3 &&
-        conv_tc5_eligible(a)) {
+    if (precision == B200SR_BF16 && in_dtype == B200SR_BF16 && out_dtype == B200SR_BF16 && c->d_w_tc5 && conv_tc5_enabled() &&
+        (c->k == 3 || c->k == 1) && conv_tc5_eligible(a)) {
         cudaError_t e5 = launch_conv3x3_c64_tc5(a, c->d_w_tc5, (cudaStream_t)stream);
         if (e5 != cudaSuccess) return cuda_fail(e5, "conv_forward (tcgen05 3x3 -> 64)");
         return 0;

@@ -22,6 +22,7 @@ struct ConvArgs {
     const void *w;         // packed filters (layout depends on the kernel)
     const float *bias;     // [coutp]
     int n, h, w_, cin, cinp, cout, coutp, x_cs, x_co, y_cs, y_co, r_cs, r_co, act, shuffle;
+    int ks = 3;                       // filter size (the tcgen05 launcher picks its instantiation by it)
     int max_ctas = 0;                 // tcgen05 kernels: grid cap (0 = one CTA per SM), b200sr_conv_set_max_ctas
     // tcgen05 3x3 kernel, cout = 3 ("rgb" form, conv_last of BasicVSR_origin): y = fp32 NCHW image n at y + n * y_nstride,
     // y += bilinear x4 upsample (align_corners = False) of the fp32 NCHW low-resolution image n at base + n * base_nstride

@@ -41,6 +41,11 @@ static cudaError_t make_planar_map(CUtensorMap *map, const void *base, int N, in
 
 bool conv_tc5_eligible(const ConvArgs &a) {
     const auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (a.ks == 1)   // 1x1 form: 128 -> 64 k (the fusion conv on cat([backward, forward] features)), NHWC input
+        return a.cin == 128 && a.cout % 64 == 0 && a.cout <= 256 && a.shuffle == 1 && !a.base && !a.x_planar && al16(a.x) && al16(a.y) &&
+               al16(a.residual) && a.x_cs % 8 == 0 && a.x_co % 8 == 0 && (!a.residual || (a.r_cs % 8 == 0 && a.r_co % 8 == 0)) &&
+               (a.y_planar ? a.cout == 64 : (a.y_cs % 8 == 0 && a.y_co % 8 == 0));
+    if (a.ks != 3) return false;
     if (a.base)   // "rgb" form: 64 -> 3, fp32 NCHW output + bilinear x4 base of an (H/4, W/4) image
         return a.cout == 3 && a.cin == 64 && a.shuffle == 1 && !a.residual && a.act == 0 && a.h % 4 == 0 && a.w_ % 4 == 0 && al16(a.x) &&
                (a.x_planar || (a.x_cs % 8 == 0 && a.x_co % 8 == 0));
@@ -59,11 +64,11 @@ static int grid_ctas(const ConvArgs &a, int G) {
     return (cap > 0 && cap < sm_count() ? cap : sm_count()) / G * G;
 }
 
-template <int NCH, int NOUT, int MT>
+template <int NCH, int NOUT, int MT, int KS = 3>
 static cudaError_t launch_t(const ConvArgs &a, const CUtensorMap &map, const uint8_t *wimg, cudaStream_t st) {
     using namespace tc5conv;
-    using C = Cfg<NCH, NOUT, MT>;
-    auto kern = conv3x3_c64_tc5_kernel<NCH, NOUT, MT>;
+    using C = Cfg<NCH, NOUT, MT, KS>;
+    auto kern = conv3x3_c64_tc5_kernel<NCH, NOUT, MT, KS>;
     static thread_local bool set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -72,7 +77,7 @@ static cudaError_t launch_t(const ConvArgs &a, const CUtensorMap &map, const uin
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) set[dev] = true;
     }
-    const int tx = ceil_div(a.w_, TWO), ty = ceil_div(a.h, C::TH), ntiles = tx * ty * a.n;
+    const int tx = ceil_div(a.w_, C::TWO), ty = ceil_div(a.h, C::TH), ntiles = tx * ty * a.n;
     const int G = NOUT == 64 ? a.cout / 64 : 1;      // output-channel groups: a CTA serves one (conv_tc5.cuh)
     int ctas = grid_ctas(a, G);
     if (ctas < G) ctas = G;
@@ -92,11 +97,11 @@ cudaError_t launch_conv3x3_c64_tc5(const ConvArgs &a, const uint8_t *wimg, cudaS
     const int G = a.base ? 1 : a.cout / 64;
     int ctas = grid_ctas(a, G) / G;
     if (ctas < 1) ctas = 1;
-    const long long tiles8 = (long long)ceil_div(a.w_, TWO) * ceil_div(a.h, 8) * a.n;
+    const long long tiles8 = (long long)ceil_div(a.w_, 30) * ceil_div(a.h, 8) * a.n;
     const char *mt_env = getenv("B200SR_CONV_MT");   // developer / test switch (read per call): force 1 or 2 M-tiles per tile
     const int force_mt = mt_env ? atoi(mt_env) : 0;
-    const int mt = a.cin != 64 || a.base ? 2 : (force_mt == 1 || force_mt == 2) ? force_mt : (tiles8 < 6ll * ctas ? 1 : 2);
-    const int bh = 4 * mt + 2;
+    const int mt = a.cin != 64 || a.base || a.ks != 3 ? 2 : (force_mt == 1 || force_mt == 2) ? force_mt : (tiles8 < 6ll * ctas ? 1 : 2);
+    const int bh = 4 * mt + 2 * (a.ks / 2);
     // the recurrent trunks cycle through a handful of activation buffers: tensor maps are cached per (pointer, geometry)
     struct MapKey { const void *p; int n, h, w, cs, cin, bh; CUtensorMap map; };
     constexpr int NCACHE = 32;
@@ -114,6 +119,7 @@ cudaError_t launch_conv3x3_c64_tc5(const ConvArgs &a, const uint8_t *wimg, cudaS
         c.p = base, c.n = a.n, c.h = a.h, c.w = a.w_, c.cs = cs, c.cin = a.cin, c.bh = bh;
         mapp = &c.map;
     }
+    if (a.ks == 1) return launch_t<16, 64, 2, 1>(a, *mapp, wimg, st);
     if (a.base) return launch_t<8, 16, 2>(a, *mapp, wimg, st);
     if (a.cin != 64) return launch_t<10, 64, 2>(a, *mapp, wimg, st);
     return mt == 1 ? launch_t<8, 64, 1>(a, *mapp, wimg, st) : launch_t<8, 64, 2>(a, *mapp, wimg, st);

@@ -30,20 +30,22 @@
 
 namespace b200sr {
 namespace tc5conv {
-constexpr int TWO = 30, BW = 32, NTHREADS = 320;
+constexpr int BW = 32, NTHREADS = 320;
 constexpr int CTRL = 256;
 enum Bar { TC_FULL = 0 /*3*/, TC_EMPTY = 3 /*3*/, D_FULL = 6, D_EMPTY = 8, W_READY = 10, NBARS = 11 };
 // NCH = 8-channel chunks of the input: 8 (64 channels) or 10 (65..80 channels: the trunk's first conv on [x_i | warped feat])
 // NOUT = output channels per CTA: 64, or 16 for the 64 -> 3 "rgb" form (conv_last + bilinear base, fp32 NCHW store)
 // MT = 128-pixel M-tiles per tile: 2 (30 x 8 outputs), or 1 (30 x 4) for launches of only a few tiles per CTA -- one 180 x 320 frame
 //      on a 74-CTA grid is 3.4 rounds of 30 x 8 tiles (4 are paid for) but 6.7 rounds of 30 x 4 tiles (7 half-size ones)
-template <int NCH, int NOUT = 64, int MT = 2> struct Cfg {
-    static constexpr int TH = 4 * MT, BH = TH + 2;
+// KS = 3 (3x3, 30 outputs per 32-pixel box row) or 1 (1x1: no halo, no don't-care columns; NCH = 16 for the 128 -> 64 k fusion conv)
+template <int NCH, int NOUT = 64, int MT = 2, int KS = 3> struct Cfg {
+    static constexpr int HALO = KS / 2, TAPS = KS * KS, TWO = BW - 2 * HALO;
+    static constexpr int TH = 4 * MT, BH = TH + 2 * HALO;
     static constexpr int PLANE_PX = BW * BH + 8;            // + 8 zero pixels: the last taps of the last M-tile read past the box
     static constexpr int PLANE = PLANE_PX * 16;             // 5,248 B (3,200 for MT = 1)
     static constexpr int TILE_BUF = NCH * PLANE;            // 41,984 / 52,480 B
     static constexpr int NBUF = NCH <= 8 ? 3 : 2;
-    static constexpr int W_SBO = 9 * NCH * 128;             // weight image [NOUT/8 row groups][9 * NCH (tap, chunk) slices][8 rows][16 B]
+    static constexpr int W_SBO = TAPS * NCH * 128;          // weight image [NOUT/8 row groups][TAPS * NCH (tap, chunk) slices][8 rows][16 B]
     static constexpr int W_BYTES = (NOUT / 8) * W_SBO;      // 73,728 / 92,160 B (18,432 for NOUT = 16)
     static constexpr size_t smem_bytes() { return (size_t)CTRL + NBUF * TILE_BUF + W_BYTES + 256; }
 };
@@ -72,13 +74,14 @@ __device__ __forceinline__ float bilinear_x4(const float *__restrict__ p, int h,
     return (1.f - ly) * ((1.f - lx) * p[y0 * w + x0] + lx * p[y0 * w + x1]) + ly * ((1.f - lx) * p[y1 * w + x0] + lx * p[y1 * w + x1]);
 }
 
-template <int NCH, int NOUT, int MT>
+template <int NCH, int NOUT, int MT, int KS>
 __global__ void __launch_bounds__(tc5conv::NTHREADS, 1)
 conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, const uint8_t *__restrict__ wimg, int tiles_x, int tiles_y,
                        int ntiles) {
     using namespace tc5conv;
-    using C = Cfg<NCH, NOUT, MT>;
+    using C = Cfg<NCH, NOUT, MT, KS>;
     constexpr int TILE_BUF = C::TILE_BUF, NBUF = C::NBUF, W_SBO = C::W_SBO, W_BYTES = C::W_BYTES, TH = C::TH, BH = C::BH, PLANE = C::PLANE;
+    constexpr int HALO = C::HALO, TAPS = C::TAPS, TWO = C::TWO;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *ctrl = smem_raw;
     uint8_t *tc = smem_raw + CTRL;           // NBUF x TILE_BUF
@@ -144,8 +147,8 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     const uint32_t dst = tc_u + b * TILE_BUF + c * PLANE;
-                    if (a.x_planar) tma_load_4d_conv(dst, &tmap_x, bar(TC_FULL + b), 4 * (x0 - 1), y0 - 1, c, n);   // (uint32 of a row, row, plane, image)
-                    else tma_load_4d_conv(dst, &tmap_x, bar(TC_FULL + b), 8 * c, x0 - 1, y0 - 1, n);                 // (channel, x, y, image)
+                    if (a.x_planar) tma_load_4d_conv(dst, &tmap_x, bar(TC_FULL + b), 4 * (x0 - HALO), y0 - HALO, c, n);   // (uint32 of a row, row, plane, image)
+                    else tma_load_4d_conv(dst, &tmap_x, bar(TC_FULL + b), 8 * c, x0 - HALO, y0 - HALO, n);                 // (channel, x, y, image)
                 }
             }
         }
@@ -166,8 +169,8 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
                 const uint32_t d = tmem + e * NOUT;
                 const uint64_t abase = a0d + (uint64_t)((b * TILE_BUF + m * 128 * 16) >> 4);
 #pragma unroll
-                for (int i = 0; i < 9 * (NCH / 2); ++i) {   // (tap t, chunks 2 cp, 2 cp + 1)
-                    const int t = i / (NCH / 2), cp = i % (NCH / 2), dy = t / 3, dx = t % 3;
+                for (int i = 0; i < TAPS * (NCH / 2); ++i) {   // (tap t, chunks 2 cp, 2 cp + 1)
+                    const int t = i / (NCH / 2), cp = i % (NCH / 2), dy = t / KS, dx = t % KS;
                     const int aoff = 2 * cp * PLANE + (dy * BW + dx) * 16;
                     tc5::mma_ss(d, abase + (uint64_t)(aoff >> 4), bw + (uint64_t)(8 * (t * NCH + 2 * cp)), idesc, i > 0);
                 }

@@ -455,3 +455,27 @@ def test_graphed_helper_wdsr_and_clip(V):
         assert torch.equal(y, vsr(clip2, 256, 256))
         with pytest.raises(RuntimeError):
             gv(torch.rand(1, 2, 3, 64, 64, device="cuda"))
+
+
+@pytest.mark.parametrize("cout", [64, 128])
+@pytest.mark.parametrize("n,h,w", [(1, 5, 9), (2, 37, 70), (1, 180, 320)])
+def test_conv1x1_c128_tcgen05_fusion(V, cout, n, h, w, monkeypatch):
+    """The fusion conv (1x1, 2 nf -> nf | 2 nf on cat([backward, forward]), models/basicvsr_arch_origin.py:84, mvvsr_arch.py:33) on the 1x1
+    form of the tcgen05 kernel: against torch fp64 on the bf16 operands and the mma.sync kernel."""
+    g = torch.Generator().manual_seed(cout + h)
+    conv = nn.Conv2d(128, cout, 1, 1, 0)
+    hd = V._ConvHandle(conv, torch.device("cuda:0"))
+    assert hd.tcgen05_ok()
+    x = torch.randn(n, h, w, 128, generator=g).bfloat16()
+    with torch.no_grad():
+        ref = F.leaky_relu(F.conv2d(x.permute(0, 3, 1, 2).double(), conv.weight.bfloat16().double(), conv.bias.double()), 0.1)
+    xd = x.cuda()
+    y = hd(xd, "bf16", V.ACT_LRELU)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("B200SR_CONV_IMPL", "mma")
+    y_mma = hd(xd, "bf16", V.ACT_LRELU)
+    torch.cuda.synchronize()
+    yf = y.float().cpu().permute(0, 3, 1, 2).double()
+    tol = 2.0 ** -8 * ref.abs().clamp_min(1.0) + 1e-3
+    assert bool(((yf - ref).abs() <= tol).all()), float((yf - ref).abs().max())
+    assert float((y.float() - y_mma.float()).abs().max()) <= 2.0 ** -6 * max(1.0, float(ref.abs().max()))
