@@ -24,3 +24,9 @@ for _ in range(3):
     t = h32(x32, "bf16", video.ACT_RELU, x_planar=True, y_planar=True)
     h64(t, "bf16", video.ACT_RELU, x_planar=True, y_planar=True)
 torch.cuda.synchronize()
+# one trunk frame as the propagation launches it: planar-8, + residual, 74-CTA grid (two directions share the GPU), 30x4-output tiles
+hd.set_max_ctas(74)
+x = torch.randn(1, 8, 180, 320, 8, device=dev).bfloat16(); r = torch.randn_like(x.float()).bfloat16()
+for _ in range(3):
+    hd(x, "bf16", video.ACT_NONE, residual=r, x_planar=True, y_planar=True)
+torch.cuda.synchronize()
