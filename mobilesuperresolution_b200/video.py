@@ -1,7 +1,9 @@
-"""Video path: ``flow_warp`` (and, below, SPyNet / BasicVSR) over the B200 C ABI.
+"""Video path over the B200 C ABI: ``flow_warp``, ``SpyNet``, ``BasicVSR_origin`` / ``BasicVSR`` (fork) / ``MotionVectorVSR``.
 
-Mirrors models/spynet_arch.py (the in-repo twin of the un-vendored ``mmedit`` functions the BasicVSR
-files import).
+Mirrors models/spynet_arch.py (the in-repo twin of the un-vendored ``mmedit`` functions the BasicVSR files import),
+models/basicvsr_arch_origin.py, models/basicvsr_arch.py and models/mvvsr_arch.py: same constructors, ``forward`` signatures and
+``state_dict`` keys.  In bf16 precision the convolutions run on the tcgen05 kernels (csrc/conv_tc5.cuh, conv7_tc5.cuh) with the
+tensors between consecutive convolutions kept planar-8; fp32 precision is the true-fp32 FFMA parity arm (1e-4 gate).
 """
 from __future__ import annotations
 
