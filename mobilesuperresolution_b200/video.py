@@ -383,6 +383,8 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
         side = main if os.environ.get("B200SR_ONE_STREAM") == "1" else self._side_stream(dev)   # developer A/B switch
         # ... each on half of the SMs (grids of the one-frame trunk launches capped): 14.7 -> 12.4 ms per 15-frame clip
         half = 0 if side is main or os.environ.get("B200SR_TRUNK_FULL_GRID") == "1" else torch.cuda.get_device_properties(dev).multi_processor_count // 2
+        if half and os.environ.get("B200SR_TRUNK_CTAS"):     # developer experiment: another grid cap for the one-frame trunk launches
+            half = int(os.environ["B200SR_TRUNK_CTAS"])
         for name, c in convs.items():
             if name.startswith(("backward_trunk.", "forward_trunk.")):
                 c.set_max_ctas(half)
