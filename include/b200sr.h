@@ -126,6 +126,12 @@ B200SR_API int b200sr_wdsr_tail(const b200sr_wdsr_t *plan, const void *trunk_dev
                      int y_dtype, int n, int h, int w, int precision, void *stream);
 /* kernels launched by the last b200sr_wdsr_forward* call on this plan (bench "gpu_launches") */
 B200SR_API int b200sr_wdsr_launches_per_forward(const b200sr_wdsr_t *plan);
+/* Host-only introspection (no device needed): the shared-memory operand image the row-streaming tcgen05 block kernel consumes
+ * for one Block (models/basic_wdsr_b.py:96-144) with folded filters w1 (m1, c), w2 (m2, m1), w3 (c, m2, 3, 3) -- the layout of
+ * csrc/wdsr_rs_layout.cuh, including the A-operand slice table of the 3x3.  tests/ replays the kernel's data flow on it.
+ * *bytes receives the image size; the image is written when img_host != NULL and cap >= *bytes. */
+B200SR_API int b200sr_wdsr_pack_block_image(int c, int m1, int m2, const float *w1, const float *b1, const float *w2, const float *b2,
+                                 const float *w3, const float *b3, void *img_host, size_t cap, size_t *bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * Split_Block.forward_body (the fork's searchable block, models/wdsr_b.py:406-496), one fused kernel:
@@ -133,7 +139,8 @@ B200SR_API int b200sr_wdsr_launches_per_forward(const b200sr_wdsr_t *plan);
  * Host arrays (float32): dw_k = weight-norm-folded depthwise filters [C][k*k] (Conv_sep.body[0], :382), dw_bias [3][C],
  * pw = folded 1x1 filters [3][C out][C in] (Conv_sep.body[2], :387), pw_bias [3][C], mask_eff [C] = the BinaryConv2d forward
  * weight w - (w - rounding(w, 0)) of `split` (:424, models/ops.py:18-26), prob [3] = softmax(alpha) (:487).
- * x / y: (n, C, h, w) NCHW of `dtype` (arithmetic is fp32 FMA for both).  C in {8, 16, 24, 32}.
+ * x / y: (n, C, h, w) NCHW of `dtype` (arithmetic is fp32 FMA for both).  C in {8, 16, 24, 32}.  y must not alias x
+ * (B200SR_E_INVAL): a CTA reads a 3-pixel halo of x that neighbouring CTAs would overwrite.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct b200sr_split b200sr_split_t;
 B200SR_API int b200sr_split_create(int channels, const float *dw3_host, const float *dw5_host, const float *dw7_host,

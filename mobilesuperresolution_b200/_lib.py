@@ -46,6 +46,7 @@ SYMBOLS = {
     "b200sr_wdsr_block": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_wdsr_tail": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_wdsr_launches_per_forward": (c_int, [c_void_p]),
+    "b200sr_wdsr_pack_block_image": (c_int, [c_int, c_int, c_int] + [c_void_p] * 6 + [c_void_p, c_size_t, POINTER(c_size_t)]),
     "b200sr_flow_warp_nchw": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_int,
                                       c_int, c_int, c_void_p]),
     "b200sr_flow_warp_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -18,6 +18,7 @@
 #include "wdsr_bf16.cuh"
 #include "wdsr_f32.cuh"
 #include "wdsr_tc5_layout.cuh"
+#include "wdsr_rs_pack.h"
 #include "wdsr_tc5_head.cuh"
 #include "wdsr_tc5_tail.cuh"
 
@@ -84,7 +85,8 @@ struct b200sr_wdsr {
     std::vector<float *> d_blk_f32;
     std::vector<uint8_t *> d_blk_bf16;
     std::vector<uint8_t *> d_blk_tc5;  // tcgen05 operand images (nullptr where the block is not eligible)
-    int block_impl = 0;                // 0 = mma.sync kernel, 1 = tcgen05 sequential form, 2 = tcgen05 pipelined form
+    std::vector<uint8_t *> d_blk_rs;   // row-streaming tcgen05 operand images (wdsr_rs.cuh), same eligibility
+    int block_impl = 0;                // 0 = mma.sync kernel, 1 = tcgen05 sequential form, 2 = tcgen05 tile form, 3 = tcgen05 row-streaming form
     float *d_tail_f32 = nullptr;
     uint8_t *d_tail_bf16 = nullptr;
     uint8_t *d_head_tc5 = nullptr;   // tcgen05 head image (trunk padded to 24 channels)
@@ -93,7 +95,7 @@ struct b200sr_wdsr {
     // The bf16 forward is one of two uniform paths: head/block/tail all tcgen05 on a planar-8 trunk [N][3][H][W][8] (tma_map.h), or
     // all mma.sync (+ the sequential tcgen05 reference block) on an NHWC trunk.  Never a mixture: the kernels disagree on the layout.
     bool tc5_path() const {
-        if (cp != 24 || block_impl != 2 || !tail_impl || !d_head_tc5 || !d_tail_tc5) return false;
+        if (cp != 24 || block_impl < 2 || !tail_impl || !d_head_tc5 || !d_tail_tc5) return false;
         for (auto b : d_blk_tc5)
             if (!b) return false;
         return true;
@@ -106,7 +108,9 @@ struct b200sr_wdsr {
         for (auto p : d_blk_bf16) cudaFree(p);
         for (auto p : d_blk_tc5)
             if (p) cudaFree(p);
-        d_blk_f32.clear(), d_blk_bf16.clear(), d_blk_tc5.clear();
+        for (auto p : d_blk_rs)
+            if (p) cudaFree(p);
+        d_blk_f32.clear(), d_blk_bf16.clear(), d_blk_tc5.clear(), d_blk_rs.clear();
         if (d_tail_f32) cudaFree(d_tail_f32), d_tail_f32 = nullptr;
         if (d_tail_bf16) cudaFree(d_tail_bf16), d_tail_bf16 = nullptr;
         if (d_tail_tc5) cudaFree(d_tail_tc5), d_tail_tc5 = nullptr;
@@ -301,15 +305,23 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
             uint8_t *d = nullptr;
             if ((rc = upload(img.data(), img.size(), (void **)&d))) return rc;
             p->d_blk_tc5.push_back(d);
+            std::vector<uint8_t> rimg;   // row-streaming form: same w1 / w2 images, the 3x3 with dy stacked in N (wdsr_rs_pack.h)
+            pack_block_rs(rimg, C, M1, M2, M1P, k.w1.data(), k.b1.data(), k.w2.data(), k.b2.data(), k.w3.data(), k.b3.data());
+            d = nullptr;
+            if ((rc = upload(rimg.data(), rimg.size(), (void **)&d))) return rc;
+            p->d_blk_rs.push_back(d);
         } else {
             p->d_blk_tc5.push_back(nullptr);
+            p->d_blk_rs.push_back(nullptr);
         }
     }
     {
         // default: the tcgen05 kernel wherever a block is eligible (trunk padded to 24, M2 <= 24), the mma.sync kernel
-        // elsewhere.  B200SR_BLOCK_IMPL = mma | tc5seq | tc5 is a developer switch (A/B timing, reference form).
+        // elsewhere.  B200SR_BLOCK_IMPL = mma | tc5seq | tc5 | rs is a developer switch (A/B timing, reference form):
+        // tc5 = the tile form (wdsr_tc5p.cuh, the default), rs = the row-streaming form (wdsr_rs.cuh): parity-green and within
+        // +-7 % of the tile form (cfg2 28.4 vs 25.9 us, 1080p 74-82 vs 80 us per launch; DESIGN.md 4.1b says what bounds both).
         const char *e = getenv("B200SR_BLOCK_IMPL");
-        p->block_impl = !e ? 2 : !strcmp(e, "mma") ? 0 : !strcmp(e, "tc5seq") ? 1 : 2;
+        p->block_impl = !e ? 2 : !strcmp(e, "mma") ? 0 : !strcmp(e, "tc5seq") ? 1 : !strcmp(e, "rs") ? 3 : 2;
     }
     const int NO = p->no;
     {   // tail fp32: Wt[9][CP][NOP4] | Ws[75][NOP4] | bias[NOP4]
@@ -391,6 +403,21 @@ int b200sr_wdsr_trunk_layout(const b200sr_wdsr_t *p, int precision) {
 }
 int b200sr_wdsr_launches_per_forward(const b200sr_wdsr_t *p) { return p ? p->launches : 0; }
 
+int b200sr_wdsr_pack_block_image(int c, int m1, int m2, const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                                 const float *b3, void *img_host, size_t cap, size_t *bytes) {
+    if (!w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !bytes) return fail(B200SR_E_INVAL, "pack_block_image: null argument");
+    if (c < 1 || c > 24 || m1 < 1 || m1 > 144 || m2 < 1 || m2 > 24)
+        return fail(B200SR_E_UNSUPPORTED, "pack_block_image: (c=%d, m1=%d, m2=%d) outside [1,24]x[1,144]x[1,24]", c, m1, m2);
+    std::vector<uint8_t> img;
+    pack_block_rs(img, c, m1, m2, round_up(m1, 16), w1, b1, w2, b2, w3, b3);
+    *bytes = img.size();
+    if (img_host) {
+        if (cap < img.size()) return fail(B200SR_E_WORKSPACE, "pack_block_image: buffer %zu < %zu bytes", cap, img.size());
+        memcpy(img_host, img.data(), img.size());
+    }
+    return 0;
+}
+
 size_t b200sr_wdsr_workspace_bytes(const b200sr_wdsr_t *p, int n, int h, int w, int precision) {
     if (!p || n <= 0 || h <= 0 || w <= 0) return 0;
     const size_t trunk = round_up((int)(((size_t)n * h * w * p->cp * esize(precision) + 255) / 256), 1) * (size_t)256;
@@ -427,6 +454,8 @@ int b200sr_wdsr_block(const b200sr_wdsr_t *p, int i, const void *tin, void *tout
     if (precision == B200SR_F32)
         CU(launch_block_f32(p->cp, p->m2p_f32[i], (const float *)tin, (float *)tout, p->d_blk_f32[i], p->m1p[i], n, h, w,
                             (cudaStream_t)stream));
+    else if (p->tc5_path() && p->block_impl == 3 && block_rs_eligible(n, h, w))
+        CU(launch_block_rs(tin, tout, p->d_blk_rs[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
     else if (p->tc5_path())
         CU(launch_block_tc5(1, tin, tout, p->d_blk_tc5[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
     else if (p->block_impl == 1 && p->d_blk_tc5[i] && p->m2[i] > 16)   // sequential tcgen05 reference form (NHWC trunk, all 27 w3 slices; developer switch)
@@ -562,6 +591,7 @@ void b200sr_split_destroy(b200sr_split_t *b) {
 
 int b200sr_split_forward(const b200sr_split_t *b, const void *x, void *y, int n, int h, int w, int dtype, void *stream) {
     if (!b || !x || !y) return fail(B200SR_E_INVAL, "split_forward: null argument");
+    if (x == y) return fail(B200SR_E_INVAL, "split_forward: x and y must be distinct buffers (a CTA reads a 3-pixel halo that its neighbours overwrite)");
     if (n <= 0 || h <= 0 || w <= 0) return fail(B200SR_E_INVAL, "split_forward: bad shape");
     if (dtype != B200SR_F32 && dtype != B200SR_BF16) return fail(B200SR_E_INVAL, "split_forward: bad dtype %d", dtype);
     cudaError_t e = launch_split_block(b->c, dtype, x, y, b->params.data(), n, h, w, (cudaStream_t)stream);

@@ -8,12 +8,8 @@ template <int K, typename T>
 static cudaError_t conv_f32_t(const ConvArgs &a, cudaStream_t st) {
     auto kern = conv_f32_kernel<K, T>;
     constexpr size_t smem = conv_f32_smem<K>();
-    static thread_local bool set = false;
-    if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        set = true;
-    }
+    static thread_local SmemOptIn optin;   // per device (launch.h)
+    if (cudaError_t e = optin.ensure(kern, smem); e != cudaSuccess) return e;
     const int tx = ceil_div(a.w_, 16), ty = ceil_div(a.h, 8);
     kern<<<dim3(tx * ty * a.n, a.coutp / 32), 256, smem, st>>>(a, tx, ty);
     return cudaGetLastError();
@@ -23,12 +19,8 @@ template <int K, int NT, typename TIN, typename TOUT>
 static cudaError_t conv_bf16_t(const ConvArgs &a, cudaStream_t st) {
     auto kern = conv_bf16_kernel<K, NT, TIN, TOUT>;
     constexpr size_t smem = conv_bf16_smem<K, NT>();
-    static thread_local bool set = false;
-    if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        set = true;
-    }
+    static thread_local SmemOptIn optin;   // per device (launch.h)
+    if (cudaError_t e = optin.ensure(kern, smem); e != cudaSuccess) return e;
     const int tx = ceil_div(a.w_, 16), ty = ceil_div(a.h, 8);
     kern<<<dim3(tx * ty * a.n, a.coutp / (8 * NT)), 128, smem, st>>>(a, tx, ty);
     return cudaGetLastError();

@@ -10,6 +10,21 @@ constexpr int kF32 = 0, kBF16 = 1, kU8 = 2;   // kU8: output of the tcgen05 tail
 
 int sm_count();  // cached multiprocessor count of the current device
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: the opt-in is tracked per (kernel instantiation, device),
+// so a host thread that drives a second GPU opts in there too.  One static instance per call site (template instantiation).
+struct SmemOptIn {
+    size_t set[64] = {};
+    template <typename K> cudaError_t ensure(K kern, size_t smem) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64 && set[dev] >= smem) return cudaSuccess;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess && dev >= 0 && dev < 64) set[dev] = smem;
+        return e;
+    }
+};
+
 // tile geometry chosen by the launchers (exposed for tests/bench reporting)
 struct TileInfo { int tw, th, tiles, ctas; };
 
@@ -22,6 +37,9 @@ cudaError_t launch_block_bf16(int CP, int M2P, const void *in, void *out, const 
 // tcgen05 form of the fused block (CP == 24, M2 <= 24): variant 0 = sequential reference form, 1 = pipelined
 cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8_t *wimg, int M1P, int M2, int N, int H, int W,
                              cudaStream_t st);
+// row-streaming tcgen05 form of the fused block (wdsr_rs.cuh; planar-8 trunk, CP == 24, M2 <= 24, M1P <= 144)
+bool block_rs_eligible(int N, int H, int W);
+cudaError_t launch_block_rs(const void *in, void *out, const uint8_t *wimg, int M1P, int M2, int N, int H, int W, cudaStream_t st);
 // tcgen05 form of the head (bf16 trunk padded to 24 channels)
 cudaError_t launch_head_tc5(int x_dtype, const void *x, void *trunk, const uint8_t *wimg, int N, int H, int W, float mean, cudaStream_t st);
 // tcgen05 form of the fused tail (trunk padded to 24 channels)

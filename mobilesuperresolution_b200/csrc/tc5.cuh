@@ -134,6 +134,12 @@ __device__ __forceinline__ void tma_load_plane(uint32_t dst_saddr, const void *t
         ::"r"(dst_saddr), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(4 * x), "r"(y), "r"(plane), "r"(n)
         : "memory");
 }
+// plain (non-tensor) bulk copy global -> shared, completion counted in bytes on an mbarrier; addresses and size multiples of 16
+__device__ __forceinline__ void bulk_load_g2s(uint32_t dst_saddr, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
@@ -151,6 +157,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // (tcgen05.wait::ld / ::st retired, shared-memory values consumed).
 __device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.relaxed.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+// the executing thread's prior cp.async copies, once complete, arrive on the mbarrier (the arrival is pre-counted in its init count)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;

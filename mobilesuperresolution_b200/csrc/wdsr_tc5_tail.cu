@@ -27,12 +27,8 @@ static cudaError_t tail_tc5_t(const void *trunk, const void *x, void *y, const u
     }
     auto kern = wdsr_tail_tc5_kernel<TIN, TOUT, S>;
     const size_t smem = smem_bytes(NOP);
-    static thread_local bool set = false;
-    if (!set) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        set = true;
-    }
+    static thread_local SmemOptIn optin;   // per device (launch.h)
+    if ((e = optin.ensure(kern, smem)) != cudaSuccess) return e;
     const int tx = ceil_div(W, TW), ty = ceil_div(H, TH), ntiles = tx * ty * N;
     int ctas = sm_count();
     if (ctas > ntiles) ctas = ntiles;
@@ -68,12 +64,8 @@ static cudaError_t head_tc5_t(const void *x, void *trunk, const uint8_t *wimg, i
     using namespace tc5head;
     auto kern = wdsr_head_tc5_kernel<TIN>;
     const size_t smem = smem_bytes();
-    static thread_local bool set = false;
-    if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        set = true;
-    }
+    static thread_local SmemOptIn optin;   // per device (launch.h); ~30 KB needs no opt-in today, kept for symmetry
+    if (cudaError_t e = optin.ensure(kern, smem); e != cudaSuccess) return e;
     const int tx = ceil_div(W, TW), ty = ceil_div(H, TH), ntiles = tx * ty * N;
     int ctas = CTAS_PER_SM * sm_count();
     if (ctas > ntiles) ctas = ntiles;

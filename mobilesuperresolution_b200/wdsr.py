@@ -18,6 +18,7 @@ is never called.  Inference only (``torch.no_grad`` semantics); there is no CPU 
 from __future__ import annotations
 
 import ctypes
+import os
 import math
 import warnings
 from typing import List, Optional, Sequence, Tuple
@@ -121,6 +122,9 @@ class WdsrPlan:
         s = self.scale
         if out is None:
             out = torch.empty((n, 3, s * h, s * w), dtype=out_dtype, device=x.device)
+        elif tuple(out.shape) != (n, 3, s * h, s * w) or out.device != x.device or not out.is_contiguous():
+            raise RuntimeError(f"out must be a contiguous {(n, 3, s * h, s * w)} tensor on {x.device}, got "
+                               f"{tuple(out.shape)} on {out.device} (contiguous={out.is_contiguous()})")
         if n == 0 or h == 0 or w == 0:
             return out
         ws = self.workspace(n, h, w, prec)
@@ -202,10 +206,20 @@ class WdsrPlan:
 # ------------------------------------------------------------------------------------------------------
 class _PlanCacheMixin:
     """Folded-weight cache: rebuilt when any parameter is modified in place (``_version``), re-assigned
-    (``data_ptr``) or the module moves device -- the reference re-folds on every forward, so mutating
-    ``weight_g`` after construction must change the output here too (hard part 7)."""
+    (``data_ptr``), the module moves device, or a plain attribute folded into the plan (``image_mean``, ``scale``)
+    changes -- the reference re-folds on every forward, so mutating ``weight_g`` after construction must change
+    the output here too (hard part 7).
+
+    Two things the signature cannot see, by contract:
+      * writes through ``.data`` (``p.data.copy_()``, ``p.data.clamp_()``, EMA swaps) do NOT bump ``_version``:
+        call ``invalidate()`` after them;
+      * ``freeze()`` skips the per-forward signature walk (153 parameters for the 16-block net, ~30 us of Python
+        that a 100 us forward notices) until ``invalidate()`` / ``unfreeze()``: the serving form.
+    ``B200SR_DEBUG_REFOLD=1`` re-folds on every forward like the reference does (slow; for chasing stale-plan bugs).
+    """
 
     precision: str = "fp32"
+    _frozen: bool = False
 
     def set_precision(self, precision: str):
         _lib.precision_code(precision)
@@ -213,11 +227,30 @@ class _PlanCacheMixin:
         return self
 
     def _signature(self, device):
-        return (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (str(device), getattr(self, "image_mean", None), getattr(self, "scale", None)) + \
+            tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def invalidate(self):
+        """Drop the folded plan: the next forward (or ``prepare()``) folds and uploads again."""
+        self._plan_sig = None
+        self._frozen = False
+        return self
+
+    def freeze(self, device=None):
+        """Prepare now and stop checking the parameters on every forward (until ``invalidate()`` / ``unfreeze()``)."""
+        self.prepare(device)
+        self._frozen = True
+        return self
+
+    def unfreeze(self):
+        self._frozen = False
+        return self
 
     def _get_plan(self, device) -> WdsrPlan:
+        if self._frozen and getattr(self, "_plan", None) is not None and self._plan.device == device:
+            return self._plan
         sig = self._signature(device)
-        if getattr(self, "_plan_sig", None) != sig:
+        if getattr(self, "_plan_sig", None) != sig or os.environ.get("B200SR_DEBUG_REFOLD") == "1":
             self._plan = self._build_plan(device)
             self._plan_sig = sig
         return self._plan
@@ -345,7 +378,9 @@ class AggregationLayer(Block):
         return x, speed_accu + self.beta2.detach().to(speed_accu.device) * speed_curr
 
     def get_num_channels(self):
-        ch = [m.in_channels for m in self.body.children() if isinstance(m, nn.Conv2d) and not isinstance(m, BinaryConv2d)]
+        # models/wdsr_b.py:366-372 appends in_channels of EVERY nn.Conv2d child, and BinaryConv2d is one: with
+        # width_search=True the reference returns [nru, m1, m1, m2, m2, nru] -- reproduced
+        ch = [m.in_channels for m in self.body.children() if isinstance(m, nn.Conv2d)]
         return ch + [ch[0]]
 
 
