@@ -157,6 +157,122 @@ def l2_flusher(device):
     return flush
 
 
+P1_WIDTHS = [(9, 91, 14), (9, 94, 10), (9, 107, 12), (9, 110, 13), (9, 115, 12), (9, 94, 12), (9, 115, 17), (9, 116, 16)]
+
+
+def _graph_us(module, x, *fargs, reps=10, warm=2):
+    """One forward as a CUDA graph (the serving form, mobilesuperresolution_b200.Graphed): microseconds per replay, CUDA events
+    on the replaying stream."""
+    import mobilesuperresolution_b200 as sr
+    g = sr.Graphed(module, x, *fargs, warmup=warm)
+    st = torch.cuda.current_stream()
+    for _ in range(2):
+        g(x)
+    st.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st)
+    for _ in range(reps):
+        g.graph.replay()
+    b.record(st)
+    st.synchronize()
+    return a.elapsed_time(b) / reps * 1e3, g
+
+
+def north_star_configs(dev, rank, world, peaks, shard):
+    """The other configurations BASELINE.json's north star is judged on (SURVEY.md 8d ceilings), each through the public module as
+    one CUDA graph, inputs resident, CUDA-event timed; per-rank work is fixed (weak), times are the max over ranks.  Side numbers:
+    cfg2 stays the headline."""
+    import tempfile
+    import mobilesuperresolution_b200 as sr
+    from mobilesuperresolution_b200 import video
+    out = {}
+    dv = str(dev) if world > 1 else "cpu"
+
+    def P(scale):
+        return types.SimpleNamespace(image_mean=0.5, num_channels=3, scale=scale, num_blocks=NB, num_residual_units=NRU,
+                                     width_search=False, pretrained=False)
+
+    def reduce_us(us):
+        return shard.max_over_ranks(us, dv)
+
+    with torch.no_grad():
+        # -- dense WDSR-B x4 360p -> 1440p (the north-star target: >= 60 % of the 16.3 k frames/s ceiling)
+        torch.manual_seed(0)
+        m = sr.BASIC_MODEL(P(4)).eval().to(dev).set_precision("bf16")
+        ceil_fps = 1.0 / max(370224 * 230400 / (peaks["bf16_tflops_sustained"] * 1e12), 1740 * 230400 / (peaks["hbm_gbs"] * 1e9))
+        for b in (1, 8):
+            x = torch.rand(b, 3, 360, 640, device=dev).bfloat16()
+            us, g = _graph_us(m, x)
+            us = reduce_us(us)
+            out[f"dense_360p_b{b}"] = {"us_per_frame": us / b, "frames_per_s": world * b / us * 1e6, "frames_per_s_per_gpu": b / us * 1e6,
+                                       "ceiling_frames_per_s_per_gpu": ceil_fps, "frac_of_ceiling": b / us * 1e6 / ceil_fps,
+                                       "out_mpix_s": world * b * 1440 * 2560 / us}
+            del g
+        # -- cfg3: searched widths P1 (pixelshuffle.onnx, SURVEY App. E) at x4, 360p frames
+        f = tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False)
+        f.write(repr((list(range(len(P1_WIDTHS))), [list(w) for w in P1_WIDTHS])) + "\n")
+        f.close()
+        mp = sr.Model(4, f.name).eval().to(dev).set_precision("bf16")
+        os.unlink(f.name)
+        ceil_p1 = 1.0 / max(70284 * 230400 / (peaks["bf16_tflops_sustained"] * 1e12), 432 * 230400 / (peaks["hbm_gbs"] * 1e9))
+        for b in (1, 8):
+            x = torch.rand(b, 3, 360, 640, device=dev).bfloat16()
+            us, g = _graph_us(mp, x)
+            us = reduce_us(us)
+            out[f"cfg3_P1_b{b}"] = {"us_per_frame": us / b, "frames_per_s": world * b / us * 1e6, "frames_per_s_per_gpu": b / us * 1e6,
+                                    "ceiling_frames_per_s_per_gpu": ceil_p1, "frac_of_ceiling": b / us * 1e6 / ceil_p1}
+            del g
+        # -- cfg5: WDSR-B x2 1080p -> 2160p, frames sharded over the ranks (4 frames per rank, no collective)
+        torch.manual_seed(0)
+        m2 = sr.BASIC_MODEL(P(2)).eval().to(dev).set_precision("bf16")
+        lo, hi = shard.shard_slice(4 * world, rank, world)
+        x = torch.rand(hi - lo, 3, 1080, 1920, device=dev).bfloat16()
+        us, g = _graph_us(m2, x, reps=5)
+        us = reduce_us(us)
+        ceil5 = 1.0 / max(349272 * 2073600 / (peaks["bf16_tflops_sustained"] * 1e12), 1668 * 2073600 / (peaks["hbm_gbs"] * 1e9))
+        out["cfg5_1080p_x2"] = {"frames_total": 4 * world, "frames_per_rank": hi - lo, "ms_per_frame_per_gpu": us / (hi - lo) / 1e3,
+                                "frames_per_s": 4 * world / us * 1e6, "frames_per_s_per_gpu": (hi - lo) / us * 1e6,
+                                "ceiling_frames_per_s_per_gpu": ceil5, "frac_of_ceiling": (hi - lo) / us * 1e6 / ceil5,
+                                "out_mpix_s": 4 * world * 2160 * 3840 / us}
+        del g, x
+        # -- cfg4: BasicVSR_origin(64, 30), one 15-frame 180x320 clip per rank -> 720x1280 (11.23 TFLOP per clip)
+        mv = video.BasicVSR_origin(64, 30).to(dev).eval().set_precision("bf16")
+        clip = torch.rand(1, 15, 3, 180, 320, device=dev)
+        us, g = _graph_us(mv, clip, 720, 1280, reps=5, warm=1)
+        us = reduce_us(us)
+        roof_ms = 11.23e12 / (peaks["bf16_tflops_sustained"] * 1e12) * 1e3
+        out["cfg4_clip15"] = {"ms_per_clip": us / 1e3, "frames_per_s": world * 15 / us * 1e6, "tflops_per_gpu": 11.23e12 / us / 1e6,
+                              "roofline_ms_per_clip": roof_ms, "frac_of_roofline": roof_ms / (us / 1e3)}
+        del g
+        # -- sustained leg: the headline forward replayed back to back for >= 3 s (power-limited steady state), clocks sampled
+        torch.manual_seed(0)
+        mh = sr.BASIC_MODEL(params()).eval().to(dev).set_precision("bf16")
+        xh = torch.rand(BATCH, 3, LR, LR, device=dev).bfloat16()
+        us1, g = _graph_us(mh, xh, reps=20)
+        n_rep = max(100, int(3.2e6 / us1))
+        idx = int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[dev.index]) if "CUDA_VISIBLE_DEVICES" in os.environ else dev.index
+        sampler = ClockSampler(idx, period_s=0.02)
+        st = torch.cuda.current_stream()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        shard.barrier()
+        st.synchronize()
+        sampler.start()
+        a.record(st)
+        for _ in range(n_rep):
+            g.graph.replay()
+        b.record(st)
+        st.synchronize()
+        clk = sampler.stop()
+        ms = shard.max_over_ranks(a.elapsed_time(b), dv)
+        out["sustained_cfg2"] = {"seconds": ms / 1e3, "replays": n_rep, "ms_per_step": ms / n_rep, "ms_per_step_burst": us1 / 1e3,
+                                 "value": world * n_rep * BATCH * (LR * SCALE) ** 2 / 1e6 / (ms / 1e3), "unit": "Mpix/s",
+                                 "l2": "not flushed (back-to-back replays; the 3.5 MB input and 57 MB output are overwritten every step)",
+                                 "clocks": clk}
+        del g
+    out["how"] = "each configuration as one CUDA graph of the public module's forward (Graphed), resident inputs, CUDA events, max over ranks"
+    return out
+
+
 def run_b200(args, rank, local_rank, world):
     import mobilesuperresolution_b200 as sr
     from mobilesuperresolution_b200 import shard
@@ -231,9 +347,19 @@ def run_b200(args, rank, local_rank, world):
     lr_px = BATCH * LR * LR
     ach_tflops = lr_px * FLOP_PER_LR_PX_BLOCK / (blk_ms * 1e-3) / 1e12
     ach_gbs = lr_px * BYTES_PER_LR_PX_BLOCK / (blk_ms * 1e-3) / 1e9
-    roofline = {"kernel": "wdsr_block_tc5p_kernel (tcgen05 fused residual block)", "bound": "tensor", "achieved": ach_tflops,
-                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach_tflops / peaks["bf16_tflops_sustained"],
-                "traffic": NCU_DRAM_BYTES_PER_BLOCK_LAUNCH, "traffic_source": "profiles/r01_block_tcgen05_v2_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)", "peak_source": peaks["source"] + " (sustained bf16 GEMM; kernel timed inside a 16-launch loop)",
+    # The kernel is timed ALONE (16 launches, ~0.4 ms of GPU work at boost clocks): the peak that applies is the BURST bf16
+    # figure of MEASURED_PEAKS.json; the sustained one is carried next to it.  The block sits on the ridge, so the roofline time
+    # is max(FLOP / peak, bytes / HBM) and `roof_frac` = T_roof / T_measured.
+    t_tensor = lr_px * FLOP_PER_LR_PX_BLOCK / (peaks["bf16_tflops"] * 1e12)
+    t_hbm = lr_px * BYTES_PER_LR_PX_BLOCK / (peaks["hbm_gbs"] * 1e9)
+    roofline = {"kernel": f"fused residual block ({os.environ.get('B200SR_BLOCK_IMPL', 'tc5')}: "
+                          f"{'wdsr_block_rs_kernel' if os.environ.get('B200SR_BLOCK_IMPL') == 'rs' else 'wdsr_block_tc5p_kernel'}, tcgen05)",
+                "bound": "tensor", "achieved": ach_tflops,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tflops / peaks["bf16_tflops"],
+                "peak_sustained": peaks["bf16_tflops_sustained"], "frac_sustained": ach_tflops / peaks["bf16_tflops_sustained"],
+                "roof_frac": max(t_tensor, t_hbm) / (blk_ms * 1e-3),
+                "traffic": NCU_DRAM_BYTES_PER_BLOCK_LAUNCH, "traffic_source": "profiles/r01_block_tcgen05_v2_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)",
+                "peak_source": peaks["source"] + " (burst bf16 GEMM: the kernel is timed alone, 16 launches between two events; the sustained figure is peak_sustained)",
                 "us_per_launch": blk_ms * 1e3, "algorithmic_flop_per_launch": lr_px * FLOP_PER_LR_PX_BLOCK,
                 "algorithmic_bytes_per_launch": lr_px * BYTES_PER_LR_PX_BLOCK,
                 "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"]},
@@ -290,6 +416,32 @@ def run_b200(args, rank, local_rank, world):
               "how": "same call with y_dtype = B200SR_U8: 8-bit frames from the tail epilogue (extra information, not the headline e2e)",
               "checksum": float(yu_h[0][:1].float().sum())}
 
+    # ---- host ceiling of the end-to-end number: every rank copies its step's output bytes device -> pinned host, all ranks at once
+    #      (plain cudaMemcpyAsync, what forward_host issues); the aggregate GB/s is what e2e can reach at most at this N.
+    shard.barrier()
+    torch.cuda.synchronize()
+    reps_c = 10
+    ys_h[0].copy_(ys_d[0], non_blocking=True)
+    torch.cuda.synchronize()
+    shard.barrier()
+    t0 = time.perf_counter()
+    for i in range(reps_c):
+        ys_h[i % depth].copy_(ys_d[i % depth], non_blocking=True)
+    torch.cuda.synchronize()
+    d2h_s = shard.max_over_ranks(time.perf_counter() - t0, str(dev) if world > 1 else "cpu")
+    d2h_gbs = world * reps_c * ys_h[0].numel() * 2 / d2h_s / 1e9
+    e2e["host_ceiling_gbs"] = d2h_gbs
+    e2e["host_ceiling_mpix_s"] = d2h_gbs * 1e9 / (3 * 2) / 1e6                 # 3 channels x 2 bytes per output pixel
+    e2e["frac_of_host_ceiling"] = e2e["value"] / e2e["host_ceiling_mpix_s"]
+    e2e["limiter"] = (f"device->host copy of the bf16 output ({ys_h[0].numel() * 2 / 1e6:.1f} MB per step and GPU): {world} concurrent pinned "
+                      f"cudaMemcpyAsync reach {d2h_gbs:.1f} GB/s in aggregate on this box")
+    try:
+        e2e["cpu_affinity"] = sorted(os.sched_getaffinity(0))[:1] + [len(os.sched_getaffinity(0))]
+    except Exception:
+        pass
+
+    extras = north_star_configs(dev, rank, world, peaks, shard) if not args.no_extras else None
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, sec, cores = cpu_forward_rate(16, 3, 1)
@@ -304,7 +456,7 @@ def run_b200(args, rank, local_rank, world):
                            "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},
                 "frames_per_s": world * BATCH / (ms_per_step / 1e3), "wall_ms_per_step_incl_flush": t_wall / K * 1e3,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "e2e_checksum": checksum, "e2e_u8_frames": e2e_u8}
+                "e2e_checksum": checksum, "e2e_u8_frames": e2e_u8, "north_star": extras}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -318,6 +470,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the north-star side configs (dense 360p, cfg3, cfg4, cfg5, sustained leg)")
     args = ap.parse_args()
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

@@ -149,6 +149,18 @@ B200SR_API int b200sr_split_create(int channels, const float *dw3_host, const fl
 B200SR_API void b200sr_split_destroy(b200sr_split_t *blk);
 B200SR_API int b200sr_split_forward(const b200sr_split_t *blk, const void *x_dev, void *y_dev, int n, int h, int w, int dtype,
                                     void *stream);
+/* Per-channel multiplier applied to x before everything else (host array [C]; NULL = all ones): NAS_MODEL.forward's
+ * `y = self.mask(y)` in front of every block (models/wdsr_b.py:116-119), fused into the block kernel. */
+B200SR_API int b200sr_split_set_premask(b200sr_split_t *blk, const float *premask_host);
+
+/* The fork's NAS_MODEL.forward (models/wdsr_b.py:105-137) in one call: head -> the KEPT MyAggregationLayer blocks (depth gates
+ * resolved by the host, models/wdsr_b.py:539-546; each with the global mask as its pre-mask) -> tail + skip + PixelShuffle (+ mean).
+ * `plan` is a b200sr_wdsr_t created with num_blocks = 0 whose head / tail filters carry the global mask (head: nothing to fold,
+ * the first block's pre-mask applies it; tail: input channels scaled by the mask).  x / y as in b200sr_wdsr_forward. */
+B200SR_API size_t b200sr_nas_workspace_bytes(const b200sr_wdsr_t *plan, int n, int h, int w, int precision);
+B200SR_API int b200sr_nas_forward(const b200sr_wdsr_t *plan, const b200sr_split_t *const *blocks, int num_blocks, const void *x_dev,
+                                  int x_dtype, void *y_dev, int y_dtype, int n, int h, int w, int precision, void *workspace_dev,
+                                  size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * flow_warp(x, flow, 'bilinear', padding_mode, align_corners=True)   models/spynet_arch.py:98-129
@@ -218,6 +230,13 @@ B200SR_API int b200sr_vsr_trunk_forward(const b200sr_conv_t *first, const b200sr
 B200SR_API int b200sr_vsr_conv_last_base(const b200sr_conv_t *conv, const void *x_dev, int x_layout, int x_cstride, int x_coff,
                                          const float *base_dev, int64_t base_nstride, float *y_dev, int64_t y_nstride, int n, int H, int W,
                                          void *stream);
+
+/* Tail of the fork's BasicVSR / MotionVectorVSR (models/basicvsr_arch.py:96-102, models/mvvsr_arch.py:98-104) behind conv_last =
+ * ConvTranspose2d(2nf, 3, 5, stride 4) evaluated as a 3x3 convolution with 3 x 16 output channels on the (h+1) x (w+1) zero-extended
+ * features: t_dev NHWC (n, h+1, w+1, t_cstride >= 48).  PixelShuffle(4) + crop to (4h+1) x (4w+1) + bilinear resize to (oh, ow) +
+ * bilinear base of the 3-channel NCHW frame img_dev (n, 3, h, w), all align_corners=False, in one pass; y float32 NCHW (n, 3, oh, ow). */
+B200SR_API int b200sr_vsr_deconv_tail(const void *t_dev, int t_dtype, int t_cstride, const void *img_dev, int img_dtype, int64_t img_nstride,
+                                      float *y_dev, int64_t y_nstride, int n, int h, int w, int oh, int ow, void *stream);
 
 /* F.interpolate(x, size=(oh,ow), mode='bilinear', align_corners) on NCHW, then (v - sub[c%4]) * mul[c%4]; y float32.
  * (models/spynet_arch.py:88-94 pre/post resize, normalisation :45-47; models/basicvsr_arch_origin.py:93) */

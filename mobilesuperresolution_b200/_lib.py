@@ -53,6 +53,10 @@ SYMBOLS = {
     "b200sr_split_create": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
     "b200sr_split_destroy": (None, [c_void_p]),
     "b200sr_split_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sr_split_set_premask": (c_int, [c_void_p, c_void_p]),
+    "b200sr_nas_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int, c_int]),
+    "b200sr_nas_forward": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                   c_size_t, c_void_p]),
     "b200sr_flow_warp_nhwc_into": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_conv_create": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, POINTER(c_void_p)]),
     "b200sr_conv_destroy": (None, [c_void_p]),
@@ -67,6 +71,7 @@ SYMBOLS = {
                                     c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_resize_bilinear_nchw": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                             c_void_p]),
+    "b200sr_vsr_deconv_tail": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_avg_pool2_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_spynet_level_input": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_void_p]),

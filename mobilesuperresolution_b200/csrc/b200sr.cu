@@ -576,7 +576,8 @@ int b200sr_split_create(int C, const float *dw3, const float *dw5, const float *
     q += 3 * C * C;
     memcpy(q, pwb, sizeof(float) * 3 * C), q += 3 * C;
     memcpy(q, e, sizeof(float) * C), q += C;
-    memcpy(q, prob, sizeof(float) * 3);
+    memcpy(q, prob, sizeof(float) * 3), q += 4;
+    for (int c = 0; c < C; ++c) q[c] = 1.f;   // pre-mask: none (b200sr_split_set_premask)
     b200sr_split *b = new (std::nothrow) b200sr_split();
     if (!b) return fail(B200SR_E_INVAL, "split_create: out of memory");
     b->c = C;
@@ -587,6 +588,53 @@ int b200sr_split_create(int C, const float *dw3, const float *dw5, const float *
 
 void b200sr_split_destroy(b200sr_split_t *b) {
     delete b;
+}
+
+int b200sr_split_set_premask(b200sr_split_t *b, const float *g) {
+    if (!b) return fail(B200SR_E_INVAL, "split_set_premask: null block");
+    float *q = b->params.data() + b->params.size() - b->c;
+    for (int c = 0; c < b->c; ++c) q[c] = g ? g[c] : 1.f;
+    return 0;
+}
+
+size_t b200sr_nas_workspace_bytes(const b200sr_wdsr_t *p, int n, int h, int w, int precision) {
+    if (!p || n <= 0 || h <= 0 || w <= 0) return 0;
+    const size_t es = esize(precision), px = (size_t)n * h * w;
+    const size_t trunk = ((px * p->cp * es + 255) / 256) * 256, nchw = ((px * p->cin * es + 255) / 256) * 256;
+    return trunk + 2 * nchw;
+}
+
+int b200sr_nas_forward(const b200sr_wdsr_t *p, const b200sr_split_t *const *blocks, int nblocks, const void *x, int x_dtype, void *y,
+                       int y_dtype, int n, int h, int w, int precision, void *ws, size_t ws_bytes, void *stream) {
+    int rc = check_common(p, n, h, w, precision, "nas_forward");
+    if (rc) return rc;
+    if (!x || !y || !ws || (nblocks > 0 && !blocks)) return fail(B200SR_E_INVAL, "nas_forward: null tensor/workspace");
+    if (p->nb != 0) return fail(B200SR_E_STATE, "nas_forward: the plan must hold head / tail / skip only (0 classic blocks)");
+    for (int i = 0; i < nblocks; ++i)
+        if (!blocks[i] || blocks[i]->c != p->cin) return fail(B200SR_E_INVAL, "nas_forward: block %d is null or not %d channels wide", i, p->cin);
+    const size_t need = b200sr_nas_workspace_bytes(p, n, h, w, precision);
+    if (ws_bytes < need) return fail(B200SR_E_WORKSPACE, "nas_forward: workspace %zu < %zu bytes", ws_bytes, need);
+    const size_t es = esize(precision), px = (size_t)n * h * w;
+    const size_t trunk_b = ((px * p->cp * es + 255) / 256) * 256, nchw_b = ((px * p->cin * es + 255) / 256) * 256;
+    uint8_t *trunk = (uint8_t *)ws, *a = trunk + trunk_b, *b = a + nchw_b;
+    const int tl = b200sr_wdsr_trunk_layout(p, precision);   // 0 NHWC, 1 planar-8
+    cudaStream_t st = (cudaStream_t)stream;
+    int launches = 0;
+    if ((rc = b200sr_wdsr_head(p, x, x_dtype, trunk, n, h, w, precision, stream))) return rc;
+    ++launches;
+    if (nblocks > 0) {   // the Split_Block kernel works on NCHW planes (depthwise convolutions): two layout changes per forward
+        CU(launch_trunk_convert(trunk, tl, a, 2, precision, n, p->cin, p->cp, h, w, st));
+        for (int i = 0; i < nblocks; ++i) {
+            CU(launch_split_block(p->cin, precision, a, b, blocks[i]->params.data(), n, h, w, st));
+            uint8_t *t = a;
+            a = b, b = t;
+        }
+        CU(launch_trunk_convert(a, 2, trunk, tl, precision, n, p->cin, p->cp, h, w, st));
+        launches += nblocks + 2;
+    }
+    if ((rc = b200sr_wdsr_tail(p, trunk, x, x_dtype, y, y_dtype, n, h, w, precision, stream))) return rc;
+    p->launches = launches + 1;
+    return 0;
 }
 
 int b200sr_split_forward(const b200sr_split_t *b, const void *x, void *y, int n, int h, int w, int dtype, void *stream) {
@@ -798,6 +846,13 @@ int b200sr_resize_bilinear_nchw(const void *x, int x_dtype, float *y, int n, int
     if (h <= 0 || w <= 0 || oh <= 0 || ow <= 0) return fail(B200SR_E_INVAL, "resize_bilinear: bad shape");
     const float z[4] = {0, 0, 0, 0}, o[4] = {1, 1, 1, 1};
     CU(launch_resize_bilinear_nchw(x, x_dtype, y, n, c, h, w, oh, ow, align, sub4 ? sub4 : z, mul4 ? mul4 : o, (cudaStream_t)stream));
+    return 0;
+}
+int b200sr_vsr_deconv_tail(const void *t, int t_dtype, int t_cstride, const void *img, int img_dtype, int64_t img_nstride, float *y,
+                           int64_t y_nstride, int n, int h, int w, int oh, int ow, void *stream) {
+    if (!t || !img || !y) return fail(B200SR_E_INVAL, "vsr_deconv_tail: null tensor");
+    if (n < 0 || h <= 0 || w <= 0 || oh <= 0 || ow <= 0 || t_cstride < 48) return fail(B200SR_E_INVAL, "vsr_deconv_tail: bad shape");
+    CU(launch_deconv_tail_resize_add(t, t_dtype, t_cstride, img, img_dtype, img_nstride, y, y_nstride, n, h, w, oh, ow, (cudaStream_t)stream));
     return 0;
 }
 int b200sr_avg_pool2_nchw(const float *x, float *y, int n, int c, int h, int w, void *stream) {

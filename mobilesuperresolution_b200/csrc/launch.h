@@ -70,6 +70,10 @@ cudaError_t launch_conv7x7_tc5(const ConvArgs &a, const uint8_t *wimg, cudaStrea
 // travels as a kernel argument), C in {8,16,24,32}
 int split_param_floats(int C);
 cudaError_t launch_split_block(int C, int dtype, const void *x, void *y, const float *params, int N, int H, int W, cudaStream_t st);
+// trunk layout conversion (video_glue.cu): layouts 0 = NHWC, 1 = planar-8, 2 = NCHW (c of cp channels)
+cudaError_t launch_trunk_convert(const void *src, int src_layout, void *dst, int dst_layout, int dtype, int n, int c, int cp, int h, int w, cudaStream_t st);
+cudaError_t launch_deconv_tail_resize_add(const void *t, int t_dtype, int cs, const void *img, int img_dtype, long long img_nstride, float *y,
+                                          long long y_nstride, int n, int h, int w, int oh, int ow, cudaStream_t st);
 // video glue (video_glue.cu)
 cudaError_t launch_resize_bilinear_nchw(const void *x, int x_dtype, float *y, int n, int c, int h, int w, int oh, int ow, int align,
                                         const float *sub4, const float *mul4, cudaStream_t st);

@@ -19,8 +19,10 @@ namespace b200sr {
 namespace splitcfg {
 constexpr int TW = 32, TH = 8, HALO = 3, SW = TW + 2 * HALO, SH = TH + 2 * HALO, NTHREADS = 256;
 __host__ __device__ constexpr int dw_floats(int C) { return C * (9 + 25 + 49); }
-// parameter pack (floats): dw3[C][9] | dw5[C][25] | dw7[C][49] | dw_bias[3][C] | pw[3][C in][C out] | pw_bias[3][C] | e[C] | p[4]
-__host__ __device__ constexpr int param_floats(int C) { return dw_floats(C) + 3 * C + 3 * C * C + 3 * C + C + 4; }
+// parameter pack (floats): dw3[C][9] | dw5[C][25] | dw7[C][49] | dw_bias[3][C] | pw[3][C in][C out] | pw_bias[3][C] | e[C] | p[4] | g[C]
+// g = per-channel multiplier applied to x FIRST (all ones for a stand-alone Split_Block): NAS_MODEL.forward runs `y = self.mask(y)` in
+// front of every block (models/wdsr_b.py:116-119), a BinaryConv2d multiply that is fused here instead of costing a tensor round trip
+__host__ __device__ constexpr int param_floats(int C) { return dw_floats(C) + 3 * C + 3 * C * C + 3 * C + C + 4 + C; }
 __host__ __device__ constexpr size_t smem_bytes(int C) { return (size_t)(C * SH * SW + C * TW * TH) * 4; }
 }  // namespace splitcfg
 
@@ -93,14 +95,14 @@ __global__ void __launch_bounds__(splitcfg::NTHREADS, 3) split_block_kernel(cons
     const int x0 = (tile % tiles_x) * TW, y0 = ((tile / tiles_x) % tiles_y) * TH, n = tile / (tiles_x * tiles_y);
     const float *prm = prm_.v;
     const float *dw3 = prm, *dw5 = dw3 + C * 9, *dw7 = dw5 + C * 25, *dwb = dw7 + C * 49, *pw = dwb + 3 * C, *pwb = pw + 3 * C * C,
-                *e = pwb + 3 * C, *p = e + C;
+                *e = pwb + 3 * C, *p = e + C, *gmask = p + 4;
     const long long plane = (long long)H * W;
     const T *xn = x + (long long)n * C * plane;
     for (int i = tid; i < C * SH * SW; i += NTHREADS) {
         const int q = i % SW, r = (i / SW) % SH, c = i / (SW * SH);
         const int gy = y0 - HALO + r, gx = x0 - HALO + q;
         float v = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = to_f32<T>(xn[c * plane + (long long)gy * W + gx]) * e[c];
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = (to_f32<T>(xn[c * plane + (long long)gy * W + gx]) * gmask[c]) * e[c];
         xs[i] = v;
     }
     const int tx = tid % TW, ty = tid / TW, gx = x0 + tx, gy = y0 + ty;
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(splitcfg::NTHREADS, 3) split_block_kernel(cons
     const T *xc = xn + (long long)(ok ? gy : 0) * W + (ok ? gx : 0);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const float xv = to_f32<T>(xc[c * plane]);
+        const float xv = to_f32<T>(xc[c * plane]) * gmask[c];
         s[c] = xv - xv * e[c];      // x3 = clone(x2), x2 = x - x1, x1 = e * x
     }
     split_branch<C, 3>(xs, ds, dw3, dwb, pw, pwb, p[0], tid, s);
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(splitcfg::NTHREADS, 3) split_block_kernel(cons
     T *yn = y + (long long)n * C * plane + (long long)gy * W + gx;
 #pragma unroll
     for (int c = 0; c < C; ++c) {   // x3 += x1; y = x2 + split(x3)   (x re-read: an L1 hit, cheaper than 2 C live registers)
-        const float xv = to_f32<T>(xc[c * plane]), x1 = xv * e[c], x2 = xv - x1;
+        const float xv = to_f32<T>(xc[c * plane]) * gmask[c], x1 = xv * e[c], x2 = xv - x1;
         yn[c * plane] = from_f32<T>(x2 + (s[c] + x1) * e[c]);
     }
 }

@@ -228,4 +228,88 @@ cudaError_t launch_vsr_base_add(const void *a, int a_dtype, int cs, const void *
     return cudaGetLastError();
 }
 
+// Tail of the fork's BasicVSR / MotionVectorVSR after conv_last = ConvTranspose2d(2nf, 3, 5, stride 4) evaluated as a 3x3 convolution with
+// 48 output channels on the (h+1) x (w+1) zero-extended features (video.py _transposed_s4k5_as_conv3x3):
+//   hr[n,c,yy,xx]  = t[n, yy/4, xx/4, 16 c + 4 (yy%4) + xx%4]           (PixelShuffle(4), cropped to (4h+1) x (4w+1))
+//   y[n,c,Y,X]     = bilinear(hr -> (OH,OW))[Y,X] + bilinear(x_i -> (OH,OW))[Y,X]      models/mvvsr_arch.py:100-104, models/basicvsr_arch.py:98-102
+// (both F.interpolate calls use align_corners=False) -- shuffle, crop, both resizes and the add in one pass, no intermediate tensor.
+template <typename TT, typename TIMG>
+__global__ void __launch_bounds__(256) deconv_tail_resize_add_kernel(const TT *__restrict__ t, int CS, const TIMG *__restrict__ img, long long img_nstride,
+                                                                     float *__restrict__ y, long long y_nstride, int N, int h, int w, int OH, int OW) {
+    const int HH = 4 * h + 1, WH = 4 * w + 1, TWp = w + 1;
+    const float sh = resize_scale(HH, OH, false), sw = resize_scale(WH, OW, false), bh = resize_scale(h, OH, false), bw = resize_scale(w, OW, false);
+    const long long total = (long long)N * 3 * OH * OW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % OW), oy = (int)((i / OW) % OH), c = (int)((i / ((long long)OW * OH)) % 3), n = (int)(i / ((long long)OW * OH * 3));
+        int y0, y1, x0, x1;
+        float ly, lx;
+        src_index(sh, oy, HH, false, y0, y1, ly);
+        src_index(sw, ox, WH, false, x0, x1, lx);
+        const TT *tn = t + (long long)n * (h + 1) * TWp * CS + 16 * c;
+        auto hr = [&](int yy, int xx) { return to_f32<TT>(tn[((long long)(yy >> 2) * TWp + (xx >> 2)) * CS + 4 * (yy & 3) + (xx & 3)]); };
+        const float res = (1.f - ly) * ((1.f - lx) * hr(y0, x0) + lx * hr(y0, x1)) + ly * ((1.f - lx) * hr(y1, x0) + lx * hr(y1, x1));
+        src_index(bh, oy, h, false, y0, y1, ly);
+        src_index(bw, ox, w, false, x0, x1, lx);
+        const TIMG *p = img + n * img_nstride + (long long)c * h * w;
+        const float base = (1.f - ly) * ((1.f - lx) * to_f32<TIMG>(p[y0 * w + x0]) + lx * to_f32<TIMG>(p[y0 * w + x1])) +
+                           ly * ((1.f - lx) * to_f32<TIMG>(p[y1 * w + x0]) + lx * to_f32<TIMG>(p[y1 * w + x1]));
+        y[n * y_nstride + ((long long)c * OH + oy) * OW + ox] = res + base;
+    }
+}
+cudaError_t launch_deconv_tail_resize_add(const void *t, int t_dtype, int cs, const void *img, int img_dtype, long long img_nstride, float *y,
+                                          long long y_nstride, int n, int h, int w, int oh, int ow, cudaStream_t st) {
+    const long long total = (long long)n * 3 * oh * ow;
+    if (total == 0) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+#define B200SR_DT_CASE(TD, ID, TT, TI) \
+    if (t_dtype == TD && img_dtype == ID) { deconv_tail_resize_add_kernel<TT, TI><<<(unsigned)blocks, 256, 0, st>>>((const TT *)t, cs, (const TI *)img, img_nstride, y, y_nstride, n, h, w, oh, ow); return cudaGetLastError(); }
+    B200SR_DT_CASE(kF32, kF32, float, float)
+    B200SR_DT_CASE(kF32, kBF16, float, bf16)
+    B200SR_DT_CASE(kBF16, kF32, bf16, float)
+    B200SR_DT_CASE(kBF16, kBF16, bf16, bf16)
+#undef B200SR_DT_CASE
+    return cudaErrorInvalidValue;
+}
+
+// Trunk layout conversion between the WDSR head / tail kernels' trunk (NHWC or planar-8, cp channels) and the NCHW tensors of the
+// fork's Split_Block kernel (c channels): one thread moves the 8 channels of one pixel and chunk.  layout: 0 = NHWC [n][h][w][cp],
+// 1 = planar-8 [n][cp/8][h][w][8], 2 = NCHW [n][c][h][w] (channels >= c of the padded side read as / are written as zero).
+template <typename T>
+__global__ void __launch_bounds__(256) trunk_convert_kernel(const T *__restrict__ src, int sl, T *__restrict__ dst, int dl, int N, int C, int CP, int H, int W) {
+    const int nch = CP / 8;
+    const long long total = (long long)N * H * W * nch, plane = (long long)H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long px = i % plane;                 // consecutive threads = consecutive pixels (coalesced on the planar / NCHW side)
+        const int ch = (int)((i / plane) % nch);
+        const long long n = i / (plane * nch);
+        T v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = 8 * ch + j;
+            if (sl == 2) v[j] = c < C ? src[(n * C + c) * plane + px] : from_f32<T>(0.f);
+            else if (sl == 1) v[j] = src[((n * nch + ch) * plane + px) * 8 + j];
+            else v[j] = src[(n * plane + px) * CP + c];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = 8 * ch + j;
+            if (dl == 2) { if (c < C) dst[(n * C + c) * plane + px] = v[j]; }
+            else if (dl == 1) dst[((n * nch + ch) * plane + px) * 8 + j] = v[j];
+            else dst[(n * plane + px) * CP + c] = v[j];
+        }
+    }
+}
+cudaError_t launch_trunk_convert(const void *src, int src_layout, void *dst, int dst_layout, int dtype, int n, int c, int cp, int h, int w, cudaStream_t st) {
+    if (cp % 8 != 0 || c > cp || src_layout == dst_layout) return cudaErrorInvalidValue;
+    const long long total = (long long)n * h * w * (cp / 8);
+    if (total == 0) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    if (dtype == kF32) trunk_convert_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float *)src, src_layout, (float *)dst, dst_layout, n, c, cp, h, w);
+    else if (dtype == kBF16) trunk_convert_kernel<bf16><<<(unsigned)blocks, 256, 0, st>>>((const bf16 *)src, src_layout, (bf16 *)dst, dst_layout, n, c, cp, h, w);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
 }  // namespace b200sr

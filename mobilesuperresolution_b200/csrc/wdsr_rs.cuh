@@ -28,7 +28,7 @@
 // = 4.6 clk/px; the tile form needs 7.4 clk/px (3.8 k clk per 512 px).
 //
 // Roles (1024 threads, eight warpgroups):
-//   WG0 warps 0/1  issuers of the even / odd steps: G2(s), G1(s+2), G3(s-2) in ONE batch per step        warps 2/3  idle
+//   WG0 warps 0/1  issuer A of the even / odd steps: G2(s), G1(s+2)      warp 2  issuer B: G3(s)      warp 3  idle
 //   WG1..WG3    also load the trunk rows into the X ring (NX slots): one 16-byte cp.async per thread and row, 8 rows ahead
 //   WG1..WG4    E1         relu(D1) -> packed bf16 A operand of G2, in place; each warpgroup owns whole K = 16 steps of G2
 //                          (expand channels 0..31 / 32..63 / 64..95 / 96..143).  A TMEM round trip (ld -> cvt -> st -> wait) is
@@ -166,34 +166,23 @@ wdsr_block_rs_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, const 
     const int wg = warp >> 2;
     if (wg == 0) {
         tc5::setmaxnreg_dec<56>();   // budgets (x 128 threads): WG0 56 + E1 4 x 64 + E2 2 x 64 + E3 72 = 8 x 64
-        // Two issuer warps, even / odd steps.  Per step ONE thread issues, back to back,  G2(s), G1(s+2), G3(s-2):
-        //   * everything that touches D1[e] / D2[e] comes from one thread, so "G1(s+2) overwrites D1[e] after G2(s) has read it" is
-        //     plain issue order;
-        //   * the latency-critical pair (G2 -> G1, whose result E1 is waiting for) is queued AHEAD of the 3x3, which nobody is
-        //     waiting for: with separate G3 issuer warps the pair sat behind up to a whole 3x3 batch in the in-order tensor queue;
-        //   * a thread that has issued tcgen05.mma stalls on its next mbarrier / shared-memory access until its queued MMAs have
-        //     drained, so both waits come first, when the thread has had nothing in flight for a whole step (the other warp's turn);
-        //     G3 runs two steps behind G2 so that its operands (t2 row s-2, re-zeroed slot) are complete by then;
-        //   * G3(s-1), G3(s), G3(s+1) accumulate into row s's slot from two threads; E3 has waited for all three commits.
+        // Three issuer warps.
+        //   warps 0 / 1  issuer A of the even / odd steps: G2(s), then G1(s+2).  Everything that touches D1[e] / D2[e] comes from ONE
+        //                thread, so "G1(s+2) overwrites D1[e] after G2(s) has read it" is plain issue order.  Two of them because a
+        //                thread that has issued tcgen05.mma stalls on its next mbarrier probe until its queued MMAs have drained:
+        //                while one drains, the other -- idle since the step before last -- takes the next step.
+        //   warp 2       issuer B: G3(s) of every step, in order.  ONE thread on purpose: rows s-1, s, s+1 accumulate into the same
+        //                TMEM slot, and only a single issue stream fixes the order of those fp32 additions (two alternating 3x3
+        //                issuers were measured no faster and made the low bits depend on which thread's batch reached the queue first).
         // (tools/rs_umma_bench.cu: the three streams need ~630 clk of tensor-queue time per step however they are issued.)
         const int e = warp & 1;
         if (warp < 2) {
+            // ============================== issuer A: G1 (expand) and G2 (reduce) ==============================
             const bool leader = tc5::elect_one();
             const uint32_t idesc1 = tc5::idesc_bf16_f32(128, M1P), idesc32 = tc5::idesc_bf16_f32(128, 32);
-            const uint32_t idesc96 = tc5::idesc_bf16_f32(128, 96), idesc64 = tc5::idesc_bf16_f32(128, 64);
             const uint64_t bw1a = tc5::smem_desc(w_u + L.w1, 128, 512), bw1b = tc5::smem_desc(w_u + L.w1 + 256, 128, 512);
             const uint64_t bw2 = tc5::smem_desc(w_u + L.w2, 128, L.sbo2);
             const int nk2 = M1P / 16;
-            const int *tab = reinterpret_cast<const int *>(wsm + L.tab);
-            const int ng3 = tab[0];
-            // 3x3 A descriptors: only the low words differ (start address | LBO << 16); the high word (SBO = 128 B, version 1) is shared
-            uint32_t alo[BlockRsLayout::MAXG3];
-#pragma unroll
-            for (int i = 0; i < BlockRsLayout::MAXG3; ++i)
-                alo[i] = (uint32_t)tc5::smem_desc(t2_u + (uint32_t)tab[1 + i], (uint32_t)tab[1 + BlockRsLayout::MAXG3 + i], 128);
-            const uint32_t ahi = (uint32_t)(tc5::smem_desc(0, 0, 128) >> 32);
-            const uint64_t bw3 = tc5::smem_desc(w_u + L.w3, 128, L.sbo3);
-            const uint32_t grp = (uint32_t)((4 * L.sbo3) >> 4);   // 32 B rows (one dy group) further into the B image
             auto issue_g1 = [&](int s) {  // leader only
                 const int slot = s % NX;
                 const uint32_t base = xs_u + slot * XSLOT;
@@ -201,69 +190,83 @@ wdsr_block_rs_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, const 
                 tc5::mma_ss(tmem + d1_col(e), tc5::smem_desc(base + 2 * XPLANE, X_ONE - slot * XSLOT - 2 * XPLANE, 128), bw1b, idesc1, true);  // plane 2, ONE
                 tc5::commit(bar(D1_FULL + e));
             };
-            auto issue_g3 = [&](int s) {  // leader only
-                const int b = s % NT;
-                const uint32_t aoff = (uint32_t)((b * T2SLOT) >> 4);
-                const int a = (s + NT - 1) % NT;   // OUT slot of row s-1; rows s and s+1 follow (mod NT)
-                if (a <= NT - 3) {
-#pragma unroll
-                    for (int i = 0; i < BlockRsLayout::MAXG3; ++i)
-                        if (i < ng3) tc5::mma_ss(tmem + out_col(a), ((uint64_t)ahi << 32) | (uint64_t)(alo[i] + aoff), bw3 + (uint64_t)(16 * i), idesc96, true);
-                } else if (a == NT - 2) {   // rows s-1, s in the last two slots; row s+1 in slot 0
-#pragma unroll
-                    for (int i = 0; i < BlockRsLayout::MAXG3; ++i)
-                        if (i < ng3) tc5::mma_ss(tmem + out_col(NT - 2), ((uint64_t)ahi << 32) | (uint64_t)(alo[i] + aoff), bw3 + (uint64_t)(16 * i), idesc64, true);
-#pragma unroll
-                    for (int i = 0; i < BlockRsLayout::MAXG3; ++i)
-                        if (i < ng3) tc5::mma_ss(tmem + out_col(0), ((uint64_t)ahi << 32) | (uint64_t)(alo[i] + aoff), bw3 + 2 * grp + (uint64_t)(16 * i), idesc32, true);
-                } else {                    // row s-1 in the last slot (nothing there on the CTA's first step); rows s, s+1 in slots 0, 1
-                    if (s > 0) {
-#pragma unroll
-                        for (int i = 0; i < BlockRsLayout::MAXG3; ++i)
-                            if (i < ng3) tc5::mma_ss(tmem + out_col(NT - 1), ((uint64_t)ahi << 32) | (uint64_t)(alo[i] + aoff), bw3 + (uint64_t)(16 * i), idesc32, true);
-                    }
-#pragma unroll
-                    for (int i = 0; i < BlockRsLayout::MAXG3; ++i)
-                        if (i < ng3) tc5::mma_ss(tmem + out_col(0), ((uint64_t)ahi << 32) | (uint64_t)(alo[i] + aoff), bw3 + grp + (uint64_t)(16 * i), idesc64, true);
-                }
-                tc5::commit(bar(STEP_DONE + b));
-            };
             if (e < T) {
                 tc5::mbar_wait(bar(X_START), 0);
                 tc5::fence_after_sync();
                 if (leader) issue_g1(e);
                 __syncwarp();
             }
-            int last3 = -1;
             RS_MARK(7);
-            for (int s = e; s < T + 2; s += 2) {   // G2(s), G1(s+2) while s < T;  G3(s-2) two steps behind
-                if (s < T) tc5::mbar_wait(bar(G2_READY + e), (s >> 1) & 1);
+            for (int s = e; s < T; s += 2) {
+                tc5::mbar_wait(bar(G2_READY + e), (s >> 1) & 1);
                 RS_MARK(0);
-                if (s >= 2) tc5::mbar_wait(bar(G3_READY + (s - 2) % NT), ((s - 2) / NT) & 1);
-                RS_MARK(1);
                 RS_EVT(100);
                 tc5::fence_after_sync();
                 if (leader) {
-                    if (s < T) {
-                        const uint32_t d2 = tmem + d2_col(e), a2 = tmem + d1_col(e);
-                        // A2 columns of K step j: each E1 warpgroup packs into the start of its own column range (see E1)
-                        tc5::mma_ts(d2, a2, bw2, idesc32, false);
+                    const uint32_t d2 = tmem + d2_col(e), a2 = tmem + d1_col(e);
+                    // A2 columns of K step j: each E1 warpgroup packs into the start of its own column range (see E1)
+                    tc5::mma_ts(d2, a2, bw2, idesc32, false);
 #pragma unroll
-                        for (int j = 1; j < 9; ++j)
-                            if (j < nk2) tc5::mma_ts(d2, a2 + a2_col(j), bw2 + (uint64_t)(16 * j), idesc32, true);
-                        tc5::commit(bar(D2_FULL + e));
-                        if (s + 2 < T) issue_g1(s + 2);   // D1[e] is free once G2(s) has read it: same thread, in order
-                    }
-                    if (s >= 2) issue_g3(s - 2);
+                    for (int j = 1; j < 9; ++j)
+                        if (j < nk2) tc5::mma_ts(d2, a2 + a2_col(j), bw2 + (uint64_t)(16 * j), idesc32, true);
+                    tc5::commit(bar(D2_FULL + e));
+                    if (s + 2 < T) issue_g1(s + 2);   // D1[e] is free once G2(s) has read it: same thread, in order
                 }
                 __syncwarp();
-                if (s >= 2) last3 = s - 2;
                 RS_MARK(2);
                 RS_EVT(102);
             }
-            // everything this thread issued has retired (its last commit tracks all of its earlier MMAs)
-            if (last3 >= 0) tc5::mbar_wait(bar(STEP_DONE + last3 % NT), (last3 / NT) & 1);
-            else if (e < T) tc5::mbar_wait(bar(D2_FULL + e), 0);
+            const int last = ((T - 1 - e) & ~1) + e;   // this issuer's last step
+            if (e < T) tc5::mbar_wait(bar(D2_FULL + e), (last >> 1) & 1);   // every G1 / G2 of this thread retired
+        } else if (warp == 2) {
+            // ============================== issuer B: G3 (3x3, dy stacked in N) ==============================
+            const bool leader = tc5::elect_one();
+            const uint32_t idesc96 = tc5::idesc_bf16_f32(128, 96), idesc64 = tc5::idesc_bf16_f32(128, 64), idesc32 = tc5::idesc_bf16_f32(128, 32);
+            const int *tab = reinterpret_cast<const int *>(wsm + L.tab);
+            const int ng3 = tab[0];
+            // A descriptors: only the low words differ (start address | LBO << 16); the high word (SBO = 128 B, version 1) is shared
+            uint32_t alo[BlockRsLayout::MAXG3];
+#pragma unroll
+            for (int i = 0; i < BlockRsLayout::MAXG3; ++i)
+                alo[i] = (uint32_t)tc5::smem_desc(t2_u + (uint32_t)tab[1 + i], (uint32_t)tab[1 + BlockRsLayout::MAXG3 + i], 128);
+            const uint32_t ahi = (uint32_t)(tc5::smem_desc(0, 0, 128) >> 32);
+            const uint64_t bw3 = tc5::smem_desc(w_u + L.w3, 128, L.sbo3);
+            const uint32_t grp = (uint32_t)((4 * L.sbo3) >> 4);   // 32 B rows (one dy group) further into the B image
+            for (int s = 0; s < T; ++s) {
+                const int b = s % NT;
+                tc5::mbar_wait(bar(G3_READY + b), (s / NT) & 1);
+                tc5::fence_after_sync();
+                RS_EVT(200);
+                if (leader) {
+                    const uint32_t aoff = (uint32_t)((b * T2SLOT) >> 4);
+                    const int a = (s + NT - 1) % NT;   // OUT slot of row s-1; rows s and s+1 follow (mod NT)
+                    if (a <= NT - 3) {
+#pragma unroll
+                        for (int i = 0; i < BlockRsLayout::MAXG3; ++i)
+                            if (i < ng3) tc5::mma_ss(tmem + out_col(a), ((uint64_t)ahi << 32) | (uint64_t)(alo[i] + aoff), bw3 + (uint64_t)(16 * i), idesc96, true);
+                    } else if (a == NT - 2) {   // rows s-1, s in the last two slots; row s+1 in slot 0
+#pragma unroll
+                        for (int i = 0; i < BlockRsLayout::MAXG3; ++i)
+                            if (i < ng3) tc5::mma_ss(tmem + out_col(NT - 2), ((uint64_t)ahi << 32) | (uint64_t)(alo[i] + aoff), bw3 + (uint64_t)(16 * i), idesc64, true);
+#pragma unroll
+                        for (int i = 0; i < BlockRsLayout::MAXG3; ++i)
+                            if (i < ng3) tc5::mma_ss(tmem + out_col(0), ((uint64_t)ahi << 32) | (uint64_t)(alo[i] + aoff), bw3 + 2 * grp + (uint64_t)(16 * i), idesc32, true);
+                    } else {                    // row s-1 in the last slot (nothing there on the CTA's first step); rows s, s+1 in slots 0, 1
+                        if (s > 0) {
+#pragma unroll
+                            for (int i = 0; i < BlockRsLayout::MAXG3; ++i)
+                                if (i < ng3) tc5::mma_ss(tmem + out_col(NT - 1), ((uint64_t)ahi << 32) | (uint64_t)(alo[i] + aoff), bw3 + (uint64_t)(16 * i), idesc32, true);
+                        }
+#pragma unroll
+                        for (int i = 0; i < BlockRsLayout::MAXG3; ++i)
+                            if (i < ng3) tc5::mma_ss(tmem + out_col(0), ((uint64_t)ahi << 32) | (uint64_t)(alo[i] + aoff), bw3 + grp + (uint64_t)(16 * i), idesc64, true);
+                    }
+                    tc5::commit(bar(STEP_DONE + b));
+                }
+                __syncwarp();
+                RS_EVT(201);
+            }
+            if (T > 0) tc5::mbar_wait(bar(STEP_DONE + (T - 1) % NT), ((T - 1) / NT) & 1);   // every G3 retired
         }
     } else {
         // ============================== epilogue warpgroups ==============================
@@ -335,6 +338,9 @@ wdsr_block_rs_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, const 
                 RS_MARK(0);
                 RS_EVT(300);
                 const uint32_t d1 = tmem + lane_base + d1_col(eb) + (q < 3 ? 32 * q : 96);
+#ifdef B200SR_EXP_E1SHORT
+                if (true) { uint32_t v8[8]; tc5::tmem_ld8(d1, v8); tc5::tmem_wait_ld(); if (v8[0] == 0x7fc12345u) tc5::tmem_st8(d1, v8); } else   // (timing experiment)
+#endif
                 if (ncol == 32) cvt(d1, std::integral_constant<int, 32>{});
                 else if (ncol == 48) cvt(d1, std::integral_constant<int, 48>{});
                 else if (ncol == 16) cvt(d1, std::integral_constant<int, 16>{});
@@ -343,6 +349,7 @@ wdsr_block_rs_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, const 
                 else tc5::mbar_arrive_relaxed(bar(G2_READY + eb));
                 RS_MARK(2);
                 RS_EVT(301);
+#ifndef B200SR_EXP_NOLOAD   // (timing experiment: no trunk loads at all)
                 if (q < 3) {
                     cp_async_wait<LA - 4>();     // row s+3 has landed: the next arrive hands it over
                     RS_MARK(4);
@@ -350,6 +357,7 @@ wdsr_block_rs_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, const 
                     RS_MARK(5);
                     load_row(s + LA);
                 }
+#endif
                 RS_MARK(3);
                 RS_EVT(303);
             }
@@ -389,6 +397,9 @@ wdsr_block_rs_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, const 
                 RS_MARK(3);
                 RS_EVT(402);
                 uint8_t *dst = t2 + b * T2SLOT + (row + 1) * 16;
+#ifdef B200SR_EXP_NOE2
+                if (cw[0] == 0x7fc12345u)   // (timing experiment)
+#endif
 #pragma unroll
                 for (int q = 0; q < (PACK ? 2 : NC2); ++q) *reinterpret_cast<uint4 *>(dst + q * T2PLANE) = c[q];
                 if (PACK) {   // channels 16..19 twice: low half of the lane's own entry, high half of the entry on its left
@@ -424,7 +435,6 @@ wdsr_block_rs_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, const 
                 if (r > 0) fresh = it.advance();
                 if (fresh) px = lane_pixel(it.strip, row, N, H, W);
                 RS_MARK(7);
-                if (r == 0) tc5::mbar_wait(bar(STEP_DONE + 0), 0);   // G3(0) and G3(1) come from different issuer threads
                 tc5::mbar_wait(bar(STEP_DONE + (r + 1) % NT), ((r + 1) / NT) & 1);
                 tc5::fence_after_sync();
                 RS_MARK(0);
@@ -450,7 +460,11 @@ wdsr_block_rs_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, const 
                 tc5::mbar_arrive_relaxed(bar(X_EMPTY + xslot));                 // residual values are in registers
                 RS_MARK(1);
                 RS_EVT(501);
+#ifdef B200SR_EXP_NOSTORE
+                if (it.stored() && px >= 0 && row >= 1 && row <= SPAN && v[0] == 0x7fc12345u) {   // (timing experiment)
+#else
                 if (it.stored() && px >= 0 && row >= 1 && row <= SPAN) {
+#endif
                     bf16 *o = out + (px + (long long)it.y * W) * 8;   // planar-8 trunk: plane q is H*W*8 elements further
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {

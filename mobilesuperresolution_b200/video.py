@@ -371,8 +371,11 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
                     fl = flows[:, flow_index(i)].contiguous()
                     if feat_first:
                         flow_warp_nhwc(feat, fl, out=buf)          # straight into channels [0, nf) of the trunk input
-                    else:
+                    elif nf % (4 if adt == torch.float32 else 8) == 0:
                         buf[..., 3:3 + nf] = flow_warp_nhwc(feat, fl)
+                    else:   # odd feature counts (the fork's BasicVSR only runs for num_feat = 3): the reference-layout NCHW kernel, fp32
+                        wv = flow_warp(feat.float().permute(0, 3, 1, 2).contiguous(), fl.permute(0, 2, 3, 1))
+                        buf[..., 3:3 + nf] = wv.permute(0, 2, 3, 1).to(adt)
                 feat = self._trunk(convs, trunk, buf, nb)
                 feats[i] = feat
             return feats
@@ -396,6 +399,30 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
         for f in fwd:
             f.record_stream(main)
         return back, fwd
+
+    # ---- tail of the fork's BasicVSR and of MotionVectorVSR: lrelu(fusion) -> conv_last = ConvTranspose2d(2nf, 3, 5, stride 4) -> bilinear
+    #      resize to (height, weight) + bilinear base (models/basicvsr_arch.py:93-102, models/mvvsr_arch.py:95-104)
+    def _deconv_handle(self, device) -> _ConvHandle:
+        sig = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.conv_last.parameters())
+        if getattr(self, "_tail_sig", None) != sig:
+            self._tail_handle, self._tail_sig = _ConvHandle(_transposed_s4k5_as_conv3x3(self.conv_last), device), sig
+        return self._tail_handle
+
+    def _deconv_tail(self, x: torch.Tensor, back, fwd, height: int, weight: int) -> torch.Tensor:
+        b, n, _, h, w = x.shape
+        dev, p = x.device, self.precision
+        convs, tail = self._convs(dev), self._deconv_handle(dev)
+        L, st = _lib.lib(), _lib.current_stream_ptr(dev)
+        out = torch.empty((b, n, 3, height, weight), dtype=torch.float32, device=dev)
+        for i in range(n):
+            o = convs["fusion"](torch.cat([back[i], fwd[i]], dim=-1), p, ACT_LRELU)
+            o = torch.nn.functional.pad(o, (0, 0, 0, 1, 0, 1))              # one zero row / column: the fifth tap's outputs
+            t = tail(o, p, ACT_NONE, out_dtype=torch.float32)               # (b, h+1, w+1, 3*16)
+            xi = x[:, i]
+            with torch.cuda.device(dev):                                     # shuffle(4) + crop + resize + base + add: one kernel
+                _lib.check(L.b200sr_vsr_deconv_tail(_ptr(t), _lib.F32, t.shape[-1], _ptr(xi), _lib.dtype_code(x.dtype), x.stride(0), _ptr(out[:, i]),
+                                                    out.stride(0), b, h, w, height, weight, st))
+        return out
 
     def _side_stream(self, dev) -> "torch.cuda.Stream":
         key = str(dev)
@@ -466,9 +493,9 @@ class BasicVSR_origin(_VsrBase):
 
 class BasicVSR(_VsrBase):
     """The fork's light BasicVSR (models/basicvsr_arch.py:10-105): same constructor and state_dict; ``get_flow`` and the
-    propagation loops run on the B200 path.  Its ``forward`` is broken as committed for ``num_feat != 3`` -- ``conv_last``
-    yields ``num_feat`` channels that are added to a 3-channel bilinear base (:96-100) -- and that ``RuntimeError`` is
-    reproduced rather than "fixed" (SURVEY.md 0-3).  The ConvTranspose2d tail is a SURVEY.md 8f "next" item."""
+    propagation loops and the ConvTranspose2d tail run on the B200 path.  Its ``forward`` is broken as committed for
+    ``num_feat != 3`` -- ``conv_last`` yields ``num_feat`` channels that are added to a 3-channel bilinear base (:96-100) -- and that
+    ``RuntimeError`` is reproduced rather than "fixed" (SURVEY.md 0-3); with ``num_feat == 3`` it runs, here as there."""
 
     def __init__(self, num_feat=64, num_block=15, spynet_path=None):
         super().__init__()
@@ -486,9 +513,14 @@ class BasicVSR(_VsrBase):
         self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
 
     def forward(self, x: torch.Tensor, height: int = 1080, weight: int = 1920) -> torch.Tensor:
+        """models/basicvsr_arch.py:56-105.  As committed the reference only runs for ``num_feat == 3`` (``conv_last`` yields ``num_feat``
+        channels that are added to the 3-channel bilinear base, :96-101); for any other width its ``out += base`` raises, and so does this."""
         if self.num_feat != 3:
             raise RuntimeError(f"The size of tensor a ({self.num_feat}) must match the size of tensor b (3) at non-singleton dimension 1")
-        raise NotImplementedError("fork BasicVSR tail (ConvTranspose2d stride 4) is not on the accelerated path; use BasicVSR_origin")
+        _lib.require_cuda_tensor(x, "x")
+        flows_forward, flows_backward = self.get_flow(x)
+        back, fwd = self.propagate(x.contiguous(), flows_forward, flows_backward)
+        return self._deconv_tail(x.contiguous(), back, fwd, height, weight)
 
 
 def _transposed_s4k5_as_conv3x3(deconv: nn.ConvTranspose2d) -> nn.Conv2d:
@@ -533,34 +565,10 @@ class MotionVectorVSR(_VsrBase):
         self.pixel_shuffle = nn.PixelShuffle(2)
         self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
 
-    def _tail(self, device) -> _ConvHandle:
-        sig = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.conv_last.parameters())
-        if getattr(self, "_tail_sig", None) != sig:
-            self._tail_handle, self._tail_sig = _ConvHandle(_transposed_s4k5_as_conv3x3(self.conv_last), device), sig
-        return self._tail_handle
-
     def forward(self, x_: torch.Tensor, height: int = 1080, weight: int = 1920) -> torch.Tensor:
         _lib.require_cuda_tensor(x_, "x_")
         x = x_[:, :, :3].contiguous()
         flows_forward = x_[:, 1:, 3:].float().contiguous()                    # mv[:, 1:]            (:65-66)
         flows_backward = flows_forward * (-1)
         back, fwd = self.propagate(x, flows_forward, flows_backward)
-        b, n, _, h, w = x.shape
-        dev, p = x.device, self.precision
-        convs, tail = self._convs(dev), self._tail(dev)
-        L, st = _lib.lib(), _lib.current_stream_ptr(dev)
-        out = torch.empty((b, n, 3, height, weight), dtype=torch.float32, device=dev)
-        for i in range(n):
-            o = convs["fusion"](torch.cat([back[i], fwd[i]], dim=-1), p, ACT_LRELU)
-            o = torch.nn.functional.pad(o, (0, 0, 0, 1, 0, 1))              # one zero row / column: the fifth tap's outputs
-            t = tail(o, p, ACT_NONE, out_dtype=torch.float32)               # (b, h+1, w+1, 3*16)
-            hr = t.view(b, h + 1, w + 1, 3, 4, 4).permute(0, 3, 1, 4, 2, 5).reshape(b, 3, 4 * h + 4, 4 * w + 4)
-            hr = hr[:, :, :4 * h + 1, :4 * w + 1].contiguous()              # ConvTranspose2d output size (h-1)*4 + 5
-            xi = x[:, i].float().contiguous()
-            res = torch.empty((b, 3, height, weight), dtype=torch.float32, device=dev)
-            base = torch.empty((b, 3, height, weight), dtype=torch.float32, device=dev)
-            with torch.cuda.device(dev):
-                _lib.check(L.b200sr_resize_bilinear_nchw(_ptr(hr), _lib.F32, _ptr(res), b, 3, 4 * h + 1, 4 * w + 1, height, weight, 0, None, None, st))
-                _lib.check(L.b200sr_resize_bilinear_nchw(_ptr(xi), _lib.F32, _ptr(base), b, 3, h, w, height, weight, 0, None, None, st))
-            out[:, i] = res + base
-        return out
+        return self._deconv_tail(x, back, fwd, height, weight)

@@ -6,7 +6,8 @@ Same constructors, ``forward`` signatures and ``state_dict`` layout as the refer
 * ``BASIC_MODEL(params)``            models/basic_wdsr_b.py:16-93
 * ``Block(...)``                     models/basic_wdsr_b.py:96-144 / models/wdsr_b.py:253-319 (optional masks)
 * ``AggregationLayer(...)``          models/wdsr_b.py:322-373 (depth gate, eval branch :358-365)
-* ``NAS_MODEL(params)``              models/wdsr_b.py:30-137 with the classic AggregationLayer body
+* ``NAS_MODEL_classic(params)``      the UPSTREAM supernet design: models/wdsr_b.py:30-137 with the classic AggregationLayer body
+                                      (the fork's own ``NAS_MODEL`` -- Split_Block body + speed estimator -- lives in ``nas.py``)
 * ``Model(scale, filename)``         export_onnx.py:6-88 (pruned net from a search ``block_index.txt``)
 
 Weight-norm (recomputed by a hook on every reference forward) is folded once in fp32 when the
@@ -30,7 +31,7 @@ import torch.nn.init as init
 from . import _lib
 from .masks import BinaryConv2d, rounding
 
-__all__ = ["BASIC_MODEL", "NAS_MODEL", "Model", "Block", "AggregationLayer", "WdsrPlan"]
+__all__ = ["BASIC_MODEL", "NAS_MODEL_classic", "Model", "Block", "AggregationLayer", "WdsrPlan"]
 
 
 def _weight_norm(conv: nn.Conv2d) -> nn.Conv2d:
@@ -449,9 +450,10 @@ class BASIC_MODEL(_WdsrNet):
                         True, self.image_mean, device)
 
 
-class NAS_MODEL(_WdsrNet):
+class NAS_MODEL_classic(_WdsrNet):
     """Supernet of models/wdsr_b.py:30-137 with the classic ``AggregationLayer`` body (the upstream design the
-    north star describes; the fork's ``Split_Block`` body is a SURVEY.md 8f "next" row).
+    north star describes: 1x1 expand / reduce / 3x3 blocks with width masks).  The fork's ``NAS_MODEL`` as committed
+    (``MyAggregationLayer`` / ``Split_Block`` body, ``speed_estimator``) is ``nas.NAS_MODEL``.
 
     ``forward`` returns ``(sr, speed_accu)`` like the reference (:137).  Width masks (``mask``, per-block
     ``body.2``/``body.4``) and depth gates are resolved at prepare time into a pruned plan; nothing is

@@ -325,6 +325,52 @@ def basicvsr_origin_forward(sd: SD, x: torch.Tensor, height: int, weight: int) -
     return torch.stack(outs, dim=1)
 
 
+def basicvsr_fork_forward(sd: SD, x: torch.Tensor, height: int, weight: int) -> torch.Tensor:
+    """The fork's BasicVSR.forward, models/basicvsr_arch.py:56-105 (runs as committed only for num_feat == 3): SPyNet flows, the two
+    propagation loops, then per frame lrelu(fusion 1x1 (2nf -> 2nf)) -> ConvTranspose2d(2nf, nf, 5, stride 4) -> bilinear resize to
+    (height, weight); ``out += base`` with the bilinear base of the 3-channel frame."""
+    num_feat = sd["backward_trunk.main.0.weight"].shape[0]
+    ff, fb = vsr_get_flow(sd, x)
+    back, fwd = vsr_propagate(sd, x, ff, fb, num_feat)
+    outs = []
+    for i in range(x.size(1)):
+        o = F.leaky_relu(F.conv2d(torch.cat([back[i], fwd[i]], 1), sd["fusion.weight"], sd["fusion.bias"]), 0.1)
+        o = F.conv_transpose2d(o, sd["conv_last.weight"], sd["conv_last.bias"], stride=4)
+        o = F.interpolate(o, size=(height, weight), mode="bilinear")
+        o = o + F.interpolate(x[:, i], size=(height, weight), mode="bilinear", align_corners=False)
+        outs.append(o)
+    return torch.stack(outs, dim=1)
+
+
+def nas_fork_speed_curr(sd: SD, prefix: str) -> torch.Tensor:
+    """BlockBSpeedEstimator.estimateByMyMask, speed_models/speed_estimator.py:57-84 (the MLP call is commented out upstream; the
+    analytic proxy uses ``rounding`` with its DEFAULT least_channel = 8 for both masks)."""
+    channels = torch.cat([rounding(sd["mask.weight"]).sum().unsqueeze(0), rounding(sd[prefix + "split.weight"]).sum().unsqueeze(0)])
+    output = 0
+    kernels = torch.Tensor([3, 5, 7])
+    for i in range(3):
+        output = output + ((channels[1] + 0.2 * channels[0]) * ((kernels[i] * kernels[i]).unsqueeze(0)) * sd[prefix + "alpha"][i]) / 40
+    return output
+
+
+def nas_fork_forward(sd: SD, x: torch.Tensor, scale: int, image_mean: float = 0.5) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The fork's NAS_MODEL.forward as committed (width_search=True), models/wdsr_b.py:105-137, eval:
+    y = head(x - mean); per block: y = mask(y); y = MyAggregationLayer(y) (identity when alpha1 >= alpha2, :539-546) and
+    speed_accu += beta2 * speed_curr; y = mask(y); out = shuffle(tail(y) + skip(x - mean)) + mean.  Returns (out, speed_accu)."""
+    x0 = x - image_mean
+    y = _wn_conv(sd, "head.", x0, 1)
+    speed = x0.new_zeros(1)
+    for i in range(count_blocks(sd)):
+        p = f"body.{i}."
+        cur = nas_fork_speed_curr(sd, p)
+        y = binary_mask_apply(y, sd["mask.weight"])
+        y = my_aggregation_layer(sd, p, y)
+        speed = speed + sd[p + "beta2"] * cur
+    y = binary_mask_apply(y, sd["mask.weight"])
+    y = _wn_conv(sd, "tail.", y, 1) + _wn_conv(sd, "skip.", x0, 2)
+    return F.pixel_shuffle(y, scale) + image_mean, speed
+
+
 # ----------------------------------------------------------------------------
 # parity metrics (SURVEY.md 8d)
 # ----------------------------------------------------------------------------

@@ -162,7 +162,7 @@ def test_empty_batch(G):
 def test_masked_supernet_equals_sliced(G):
     """P3: NAS supernet with width masks and a depth gate -> pruned plan == the reference's masked forward."""
     from oracle import port
-    m = G.sr.NAS_MODEL(G.params(2, 4, width_search=True)).eval()
+    m = G.sr.NAS_MODEL_classic(G.params(2, 4, width_search=True)).eval()
     sd = G.synth_load(m, 71)
     sd["body.1.alpha1"], sd["body.1.alpha2"] = torch.tensor([0.9]), torch.tensor([0.1])      # block 1 skipped
     sd["body.2.alpha1"], sd["body.2.alpha2"] = torch.tensor([0.1]), torch.tensor([0.9])

@@ -131,7 +131,7 @@ def test_state_dict_layouts_match_appendix_b(sr, kat):
     assert "body.3.weight_v" in blk and "body.5.weight_v" in blk
     agg = sr.AggregationLayer(num_residual_units=24, kernel_size=3, width_search=False).state_dict()
     assert all(k in agg for k in ("alpha1", "alpha2", "beta1", "beta2"))
-    nas = sr.NAS_MODEL(P(4, 4, ws=True)).state_dict()
+    nas = sr.NAS_MODEL_classic(P(4, 4, ws=True)).state_dict()
     assert "mask.weight" in nas and "skip.weight_v" in nas and "skip.0.weight_v" not in nas
 
 
@@ -172,7 +172,7 @@ def test_mask_folding_equals_masked_block(sr):
 
 
 def test_depth_gate_and_width_readout(sr):
-    m = sr.NAS_MODEL(P(4, 3, ws=True)).eval()
+    m = sr.NAS_MODEL_classic(P(4, 3, ws=True)).eval()
     m.body[1].alpha1.fill_(0.9)
     m.body[1].alpha2.fill_(0.1)
     assert m.get_block_status() == [0, 2] and m.get_current_blocks() == 2
@@ -228,3 +228,24 @@ def test_two_rank_gloo_sharding(tmp_path):
     assert all(p.returncode == 0 for p in procs), outs
     res = json.loads(outs[0][0].strip().splitlines()[-1])
     assert res == {"world": 2, "covered": 13.0, "slowest": 11.0}
+
+
+def test_fork_nas_model_state_dict_and_seeded_construction(sr):
+    """The fork's NAS_MODEL as committed (models/wdsr_b.py:30-137): App. B layout (421 + mask tensors for 16 blocks) and a constructor
+    that consumes the RNG exactly like the reference's (head, speed-estimator MLP incl. its re-initialisation, blocks, mask, tail,
+    skip): the weight sum of every key but the estimator's pickled values equals the reference's under torch.manual_seed(0)."""
+    from conftest import load_golden
+    sd = sr.NAS_MODEL(P(4, 16, ws=True)).state_dict()
+    assert len(sd) == 422 and "mask.weight" in sd and "skip.weight_v" in sd and "skip.0.weight_v" not in sd
+    assert tuple(sd["speed_estimator.estimator.fc3.weight"].shape) == (128, 64)
+    assert tuple(sd["body.7.body.5.0.body.0.weight_v"].shape) == (24, 1, 5, 5) and tuple(sd["body.7.body.7.0.body.2.weight_v"].shape) == (24, 24, 1, 1)
+    assert tuple(sd["body.0.split.weight"].shape) == (24, 1, 1, 1) and tuple(sd["body.0.alpha"].shape) == (3,)
+    meta, _ = load_golden("nas_fork")
+    torch.manual_seed(0)
+    m = sr.NAS_MODEL(P(meta["scale"], meta["nb"], ws=True))
+    wsum = float(sum(v.double().sum() for k, v in m.state_dict().items() if not k.startswith("speed_estimator.")))
+    assert abs(wsum - meta["seed0_weights_sum_without_estimator"]) < 1e-9
+    # read-outs: (IN, split, kernel) triples, host arithmetic only
+    assert m.get_block_status() == [0, 1, 2] and all(len(t) == 3 and t[2] in (3, 5, 7) for t in m.get_width_from_block_idx([0, 1, 2]))
+    with pytest.raises(RuntimeError):
+        m.eval()(torch.rand(1, 3, 8, 8))            # CPU tensor: no fallback
