@@ -231,6 +231,13 @@ B200SR_API int b200sr_vsr_conv_last_base(const b200sr_conv_t *conv, const void *
                                          const float *base_dev, int64_t base_nstride, float *y_dev, int64_t y_nstride, int n, int H, int W,
                                          void *stream);
 
+/* 8-bit frame glue around the forward.
+ *   b200sr_u8_to_unit: y = x / 255, torchvision's to_tensor on an 8-bit frame (datasets/_isr.py:74-75), any shape, `count` elements.
+ *   b200sr_ssd_u8:     out[i] = sum over (c, shaved h, shaved w) of (a - b)^2 of image i, uint64 -- the integer core of
+ *                      common/metrics.py:10-19 for two quantised frames: psnr_i = -10 log10( out[i] / (255^2 * c*(h-2s)*(w-2s)) ). */
+B200SR_API int b200sr_u8_to_unit(const uint8_t *x_dev, void *y_dev, int y_dtype, int64_t count, void *stream);
+B200SR_API int b200sr_ssd_u8(const uint8_t *a_dev, const uint8_t *b_dev, uint64_t *out_dev, int n, int c, int h, int w, int shave, void *stream);
+
 /* Tail of the fork's BasicVSR / MotionVectorVSR (models/basicvsr_arch.py:96-102, models/mvvsr_arch.py:98-104) behind conv_last =
  * ConvTranspose2d(2nf, 3, 5, stride 4) evaluated as a 3x3 convolution with 3 x 16 output channels on the (h+1) x (w+1) zero-extended
  * features: t_dev NHWC (n, h+1, w+1, t_cstride >= 48).  PixelShuffle(4) + crop to (4h+1) x (4w+1) + bilinear resize to (oh, ow) +

@@ -855,6 +855,18 @@ int b200sr_vsr_deconv_tail(const void *t, int t_dtype, int t_cstride, const void
     CU(launch_deconv_tail_resize_add(t, t_dtype, t_cstride, img, img_dtype, img_nstride, y, y_nstride, n, h, w, oh, ow, (cudaStream_t)stream));
     return 0;
 }
+int b200sr_u8_to_unit(const uint8_t *x, void *y, int y_dtype, int64_t count, void *stream) {
+    if (!x || !y || count < 0) return fail(B200SR_E_INVAL, "u8_to_unit: bad argument");
+    if (y_dtype != B200SR_F32 && y_dtype != B200SR_BF16) return fail(B200SR_E_INVAL, "u8_to_unit: y_dtype %d", y_dtype);
+    CU(launch_u8_to_unit(x, y, y_dtype, count, (cudaStream_t)stream));
+    return 0;
+}
+int b200sr_ssd_u8(const uint8_t *a, const uint8_t *b, uint64_t *out, int n, int c, int h, int w, int shave, void *stream) {
+    if (!a || !b || !out) return fail(B200SR_E_INVAL, "ssd_u8: null tensor");
+    if (n < 0 || c <= 0 || shave < 0 || h - 2 * shave <= 0 || w - 2 * shave <= 0) return fail(B200SR_E_INVAL, "ssd_u8: bad shape / shave");
+    CU(launch_ssd_u8(a, b, (unsigned long long *)out, n, c, h, w, shave, (cudaStream_t)stream));
+    return 0;
+}
 int b200sr_avg_pool2_nchw(const float *x, float *y, int n, int c, int h, int w, void *stream) {
     if (!x || !y) return fail(B200SR_E_INVAL, "avg_pool2: null tensor");
     CU(launch_avg_pool2(x, y, n, c, h, w, (cudaStream_t)stream));

@@ -74,6 +74,9 @@ cudaError_t launch_split_block(int C, int dtype, const void *x, void *y, const f
 cudaError_t launch_trunk_convert(const void *src, int src_layout, void *dst, int dst_layout, int dtype, int n, int c, int cp, int h, int w, cudaStream_t st);
 cudaError_t launch_deconv_tail_resize_add(const void *t, int t_dtype, int cs, const void *img, int img_dtype, long long img_nstride, float *y,
                                           long long y_nstride, int n, int h, int w, int oh, int ow, cudaStream_t st);
+// 8-bit frame glue (video_glue.cu)
+cudaError_t launch_u8_to_unit(const uint8_t *x, void *y, int y_dtype, long long total, cudaStream_t st);
+cudaError_t launch_ssd_u8(const uint8_t *a, const uint8_t *b, unsigned long long *out, int n, int c, int h, int w, int shave, cudaStream_t st);
 // video glue (video_glue.cu)
 cudaError_t launch_resize_bilinear_nchw(const void *x, int x_dtype, float *y, int n, int c, int h, int w, int oh, int ow, int align,
                                         const float *sub4, const float *mul4, cudaStream_t st);

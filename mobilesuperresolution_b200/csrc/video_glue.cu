@@ -272,6 +272,65 @@ cudaError_t launch_deconv_tail_resize_add(const void *t, int t_dtype, int cs, co
     return cudaErrorInvalidValue;
 }
 
+// ---- 8-bit frame glue (utils/estimate.py:23-133, common/metrics.py:10-19, datasets/_isr.py:74-75) ---------------------------
+// y = x / 255: torchvision's to_tensor on an 8-bit frame, on the device (the H2D copy carries a quarter of the float32 bytes)
+template <typename T>
+__global__ void __launch_bounds__(256) u8_to_unit_kernel(const uint8_t *__restrict__ x, T *__restrict__ y, long long total) {
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < total; i += (long long)gridDim.x * blockDim.x * 4) {
+        if (i + 3 < total && (reinterpret_cast<uintptr_t>(x + i) & 3) == 0) {
+            const uchar4 v = *reinterpret_cast<const uchar4 *>(x + i);
+            y[i] = from_f32<T>((float)v.x / 255.f), y[i + 1] = from_f32<T>((float)v.y / 255.f);
+            y[i + 2] = from_f32<T>((float)v.z / 255.f), y[i + 3] = from_f32<T>((float)v.w / 255.f);
+        } else {
+            for (long long j = i; j < total && j < i + 4; ++j) y[j] = from_f32<T>((float)x[j] / 255.f);
+        }
+    }
+}
+cudaError_t launch_u8_to_unit(const uint8_t *x, void *y, int y_dtype, long long total, cudaStream_t st) {
+    if (total == 0) return cudaSuccess;
+    long long blocks = (total / 4 + 255) / 256 + 1;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    if (y_dtype == kF32) u8_to_unit_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(x, (float *)y, total);
+    else if (y_dtype == kBF16) u8_to_unit_kernel<bf16><<<(unsigned)blocks, 256, 0, st>>>(x, (bf16 *)y, total);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+// Sum of squared differences of two 8-bit frames per image over the shaved window: the integer core of common/metrics.py:10-19
+// (psnr = -10 log10( sum / (255^2 * count) ) per image; both sides are already the quantised frames).  Exact: uint64 accumulation.
+__global__ void __launch_bounds__(256) ssd_u8_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, unsigned long long *__restrict__ out,
+                                                     int C, int H, int W, int shave, int blocks_per_image) {
+    const int n = blockIdx.x / blocks_per_image, blk = blockIdx.x % blocks_per_image;
+    const int hh = H - 2 * shave, ww = W - 2 * shave;
+    const long long count = (long long)C * hh * ww;
+    unsigned long long acc = 0;
+    for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < count; i += (long long)blocks_per_image * blockDim.x) {
+        const int x = (int)(i % ww) + shave, y = (int)((i / ww) % hh) + shave, c = (int)(i / ((long long)ww * hh));
+        const long long o = (((long long)n * C + c) * H + y) * W + x;
+        const int d = (int)a[o] - (int)b[o];
+        acc += (unsigned long long)(d * d);
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    __shared__ unsigned long long part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < 8; ++i) t += part[i];
+        atomicAdd(out + n, t);
+    }
+}
+cudaError_t launch_ssd_u8(const uint8_t *a, const uint8_t *b, unsigned long long *out, int n, int c, int h, int w, int shave, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(unsigned long long) * n, st);
+    if (e != cudaSuccess) return e;
+    const long long count = (long long)c * (h - 2 * shave) * (w - 2 * shave);
+    int bpi = (int)((count + 256 * 16 - 1) / (256 * 16));
+    bpi = bpi < 1 ? 1 : bpi > 1024 ? 1024 : bpi;
+    ssd_u8_kernel<<<n * bpi, 256, 0, st>>>(a, b, out, c, h, w, shave, bpi);
+    return cudaGetLastError();
+}
+
 // Trunk layout conversion between the WDSR head / tail kernels' trunk (NHWC or planar-8, cp channels) and the NCHW tensors of the
 // fork's Split_Block kernel (c channels): one thread moves the 8 channels of one pixel and chunk.  layout: 0 = NHWC [n][h][w][cp],
 // 1 = planar-8 [n][cp/8][h][w][8], 2 = NCHW [n][c][h][w] (channels >= c of the padded side read as / are written as zero).
