@@ -231,6 +231,16 @@ B200SR_API int b200sr_vsr_conv_last_base(const b200sr_conv_t *conv, const void *
                                          const float *base_dev, int64_t base_nstride, float *y_dev, int64_t y_nstride, int n, int H, int W,
                                          void *stream);
 
+/* SpyNet.forward (models/spynet_arch.py:49-96) in one call: bilinear resize to multiples of 32 + ImageNet normalisation, the 5 average
+ * pools, six pyramid levels (x2 upsample of the flow -> warp(border) -> 7x7 convs 8-32-64-32-16-2 -> + flow), final resize + rescale.
+ * convs: 30 handles, level-major (basic_module.L.basic_module.{0,2,4,6,8}, L = 0..5).  ref / supp: NCHW (n,3,h,w) of img_dtype;
+ * flow_out: float32 NCHW (n,2,h,w).  mean4 / inv_std4: host arrays {r,g,b,0} / {1/r,1/g,1/b,1} (the module's `mean` / `std` buffers).
+ * precision B200SR_BF16 runs the convolutions on bf16 tensor-core operands; flows, warps and the pyramid stay float32. */
+B200SR_API size_t b200sr_spynet_workspace_bytes(int n, int h, int w, int precision);
+B200SR_API int b200sr_spynet_forward(const b200sr_conv_t *const *convs, const void *ref_dev, const void *supp_dev, int img_dtype,
+                                     float *flow_out_dev, int n, int h, int w, int precision, const float *mean4_host,
+                                     const float *inv_std4_host, void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* 8-bit frame glue around the forward.
  *   b200sr_u8_to_unit: y = x / 255, torchvision's to_tensor on an 8-bit frame (datasets/_isr.py:74-75), any shape, `count` elements.
  *   b200sr_ssd_u8:     out[i] = sum over (c, shaved h, shaved w) of (a - b)^2 of image i, uint64 -- the integer core of

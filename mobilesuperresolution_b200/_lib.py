@@ -72,6 +72,9 @@ SYMBOLS = {
     "b200sr_resize_bilinear_nchw": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                             c_void_p]),
     "b200sr_vsr_deconv_tail": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sr_spynet_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "b200sr_spynet_forward": (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_size_t, c_void_p]),
     "b200sr_u8_to_unit": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "b200sr_ssd_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_avg_pool2_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

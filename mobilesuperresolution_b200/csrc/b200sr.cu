@@ -872,6 +872,95 @@ int b200sr_avg_pool2_nchw(const float *x, float *y, int n, int c, int h, int w, 
     CU(launch_avg_pool2(x, y, n, c, h, w, (cudaStream_t)stream));
     return 0;
 }
+// ---------------------------------------------------------------------------------------------------------
+// SpyNet.forward (models/spynet_arch.py:49-96) as ONE call: resize + normalise, 5 x avg-pool, six pyramid levels of
+// (upsample x2 -> warp(border) -> concat8 -> 7x7 convs 8-32-64-32-16-2 -> + up), final resize + rescale.  ~100 launches sequenced in C on
+// a caller-provided workspace; nothing is allocated, nothing synchronises.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct SpyGeom {
+    int h_up, w_up, hl[6], wl[6];
+    size_t pyr_off[2][6], inp_off, up_off, flow_off[2], act_off[2], head_off, total;
+};
+inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+SpyGeom spynet_geom(int n, int h, int w, int precision) {
+    SpyGeom g;
+    g.h_up = (h + 31) / 32 * 32, g.w_up = (w + 31) / 32 * 32;
+    g.hl[5] = g.h_up, g.wl[5] = g.w_up;
+    for (int l = 4; l >= 0; --l) g.hl[l] = g.hl[l + 1] / 2, g.wl[l] = g.wl[l + 1] / 2;
+    const size_t es = precision == B200SR_F32 ? 4 : 2;
+    const int cs = precision == B200SR_F32 ? 8 : 16;
+    size_t off = 0;
+    for (int k = 0; k < 2; ++k)
+        for (int l = 0; l < 6; ++l) g.pyr_off[k][l] = off, off += al256((size_t)n * 3 * g.hl[l] * g.wl[l] * 4);
+    const size_t px = (size_t)n * g.h_up * g.w_up;
+    g.inp_off = off, off += al256(px * cs * es);
+    g.up_off = off, off += al256(px * 2 * 4);
+    for (int k = 0; k < 2; ++k) g.flow_off[k] = off, off += al256(px * 2 * 4);
+    for (int k = 0; k < 2; ++k) g.act_off[k] = off, off += al256(px * 64 * es);
+    g.head_off = off, off += al256(px * 2 * 4);
+    g.total = off;
+    return g;
+}
+}  // namespace
+
+size_t b200sr_spynet_workspace_bytes(int n, int h, int w, int precision) {
+    if (n <= 0 || h <= 0 || w <= 0) return 0;
+    return spynet_geom(n, h, w, precision).total;
+}
+
+int b200sr_spynet_forward(const b200sr_conv_t *const *convs, const void *ref, const void *supp, int img_dtype, float *flow_out, int n, int h,
+                          int w, int precision, const float *mean4, const float *inv_std4, void *ws, size_t ws_bytes, void *stream) {
+    if (!convs || !ref || !supp || !flow_out || !ws || !mean4 || !inv_std4) return fail(B200SR_E_INVAL, "spynet_forward: null argument");
+    if (n <= 0 || h <= 0 || w <= 0) return fail(B200SR_E_INVAL, "spynet_forward: bad shape");
+    if (precision != B200SR_F32 && precision != B200SR_BF16) return fail(B200SR_E_INVAL, "spynet_forward: bad precision %d", precision);
+    for (int i = 0; i < 30; ++i)
+        if (!convs[i]) return fail(B200SR_E_INVAL, "spynet_forward: conv %d is null (30 handles: level-major, layers 8-32-64-32-16-2)", i);
+    const SpyGeom g = spynet_geom(n, h, w, precision);
+    if (g.h_up < 64 || g.w_up < 64) return fail(B200SR_E_INVAL, "spynet_forward: SPyNet needs at least 33 pixels per side");
+    if (ws_bytes < g.total) return fail(B200SR_E_WORKSPACE, "spynet_forward: workspace %zu < %zu bytes", ws_bytes, g.total);
+    uint8_t *base = (uint8_t *)ws;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int adt = precision, cs = precision == B200SR_F32 ? 8 : 16;
+    const int N_ = B200SR_TRUNK_NHWC, P = B200SR_TRUNK_PLANAR8;
+    const void *img[2] = {ref, supp};
+    for (int k = 0; k < 2; ++k) {   // resize (align_corners=False) + ImageNet normalisation, then the 5 average pools  (:88-89, 45-47, 52-57)
+        CU(launch_resize_bilinear_nchw(img[k], img_dtype, (float *)(base + g.pyr_off[k][5]), n, 3, h, w, g.h_up, g.w_up, 0, mean4, inv_std4, st));
+        for (int l = 4; l >= 0; --l)
+            CU(launch_avg_pool2((const float *)(base + g.pyr_off[k][l + 1]), (float *)(base + g.pyr_off[k][l]), n, 3, g.hl[l + 1], g.wl[l + 1], st));
+    }
+    const float *flow = nullptr;
+    int ph = g.hl[0] / 2, pw = g.wl[0] / 2, rc;
+    for (int l = 0; l < 6; ++l) {
+        const int hl = g.hl[l], wl = g.wl[l];
+        float *up = (float *)(base + g.up_off);
+        CU(launch_spynet_level_input((const float *)(base + g.pyr_off[0][l]), (const float *)(base + g.pyr_off[1][l]), flow, base + g.inp_off, adt,
+                                     up, n, hl, wl, ph, pw, cs, st));
+        const b200sr_conv_t *const *L = convs + 5 * l;
+        // bf16: layers 0-3 run on the tcgen05 7x7 kernel and keep their private tensors planar-8; the 16 -> 2 flow head reads NHWC
+        bool planar = precision != B200SR_F32;
+        for (int j = 0; j < 4 && planar; ++j) planar = b200sr_conv_tcgen05_ok(L[j]) != 0;
+        const void *t = base + g.inp_off;
+        int tcs = cs;
+        for (int j = 0; j < 5; ++j) {
+            const bool last = j == 4;
+            void *y = last ? (void *)(base + g.head_off) : (void *)(base + g.act_off[j & 1]);
+            const int xl = planar && j >= 1 && j <= 3 ? P : N_, yl = planar && j <= 2 ? P : N_;
+            const int ycs = L[j]->cout;
+            if ((rc = b200sr_conv_forward_layout(L[j], t, xl, xl == P ? L[j]->cin : tcs, 0, y, yl, ycs, 0, nullptr, 0, 0, n, hl, wl,
+                                                 last ? B200SR_ACT_NONE : B200SR_ACT_RELU, 1, adt, last ? B200SR_F32 : adt, precision, stream)))
+                return rc;
+            t = y, tcs = ycs;
+        }
+        float *fnew = (float *)(base + g.flow_off[l & 1]);
+        CU(launch_nhwc_plus_nchw((const float *)(base + g.head_off), up, fnew, n, 2, hl, wl, 2, st));
+        flow = fnew, ph = hl, pw = wl;
+    }
+    const float zero[4] = {0, 0, 0, 0}, scale[4] = {(float)w / (float)g.w_up, (float)h / (float)g.h_up, 1.f, 1.f};   // (:91-94)
+    CU(launch_resize_bilinear_nchw(flow, B200SR_F32, flow_out, n, 2, g.h_up, g.w_up, h, w, 0, zero, scale, st));
+    return 0;
+}
+
 int b200sr_spynet_level_input(const float *ref, const float *supp, const float *flow_prev, void *out, int out_dtype, float *up, int n,
                               int h, int w, int ph, int pw, int cs, void *stream) {
     if (!ref || !supp || !out || !up) return fail(B200SR_E_INVAL, "spynet_level_input: null tensor");

@@ -162,13 +162,28 @@ __device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+// Developer switch: -DB200SR_MBAR_SUSPEND_HINT_NS=<ns> passes a suspend-time hint.  Without it try_wait comes back after a short
+// system-defined time and a waiting warp's retry loop keeps re-issuing -- a third of ALL executed instructions in the row-streaming block
+// kernel (ncu source page, profiles/r02_block_rs_ncu.md).  Measured: neither the hint (10 ms) nor letting only one warp per warpgroup
+// poll (mbar_wait_wg) changed the kernel times -- the retries only take issue slots nobody else wanted.
+#ifndef B200SR_MBAR_SUSPEND_HINT_NS
+#define B200SR_MBAR_SUSPEND_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if B200SR_MBAR_SUSPEND_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"((uint32_t)B200SR_MBAR_SUSPEND_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking probe
@@ -197,6 +212,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #endif
             __trap();
         }
+}
+
+// A whole warpgroup (4 consecutive warps) waits for one mbarrier phase: only its first warp polls, the other three block in a named
+// hardware barrier (bar.sync costs no issue slots while blocked; a polling warp re-issues its retry loop and competes with the warps that
+// have work -- a third of all executed instructions in the row-streaming block kernel before this).  id: 1..15, one per warpgroup.
+__device__ __forceinline__ void mbar_wait_wg(uint32_t bar, uint32_t parity, int id) {
+    if (((threadIdx.x >> 5) & 3) == 0) mbar_wait(bar, parity);
+    asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
+}
+// spin on the non-blocking probe: lower wake-up latency than the suspending try_wait, at the price of issue slots and shared-memory
+// probes while waiting.  For the one or two barriers that sit on a kernel's critical loop only.
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+    for (uint32_t it = 0; !mbar_test(bar, parity); ++it)
+        if (it > (1u << 28)) __trap();
 }
 
 }  // namespace tc5

@@ -49,7 +49,11 @@
 __device__ unsigned long long g_rs_evt[32][4096];
 __device__ int g_rs_evtn[32];
 #define RS_DECL() int evn__ = 0
-#define RS_EVT(id) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && evn__ < 4096) { g_rs_evt[threadIdx.x >> 5][evn__++] = ((unsigned long long)(id) << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull); } } while (0)
+#ifndef B200SR_RS_EVT_LO
+#define B200SR_RS_EVT_LO 0
+#define B200SR_RS_EVT_HI 1000
+#endif
+#define RS_EVT(id) do { if ((id) >= B200SR_RS_EVT_LO && (id) < B200SR_RS_EVT_HI && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && evn__ < 4096) { g_rs_evt[threadIdx.x >> 5][evn__++] = ((unsigned long long)(id) << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull); } } while (0)
 #define RS_FLUSH() do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_rs_evtn[threadIdx.x >> 5] = evn__; } while (0)
 #else
 #define RS_DECL() do {} while (0)
@@ -67,6 +71,13 @@ __device__ unsigned long long g_rs_tm[32][8];
 #define RS_TM_DECL() do {} while (0)
 #define RS_MARK(i) do {} while (0)
 #define RS_TM_FLUSH() do {} while (0)
+#endif
+
+// the two waits on the G1 -> E1 -> G2 loop (developer switch: -DB200SR_RS_SPIN spins on the non-blocking probe instead of suspending)
+#ifdef B200SR_RS_SPIN
+#define RS_CRIT_WAIT(b, p) tc5::mbar_spin(b, p)
+#else
+#define RS_CRIT_WAIT(b, p) tc5::mbar_wait(b, p)
 #endif
 
 namespace b200sr {
@@ -198,7 +209,7 @@ wdsr_block_rs_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, const 
             }
             RS_MARK(7);
             for (int s = e; s < T; s += 2) {
-                tc5::mbar_wait(bar(G2_READY + e), (s >> 1) & 1);
+                RS_CRIT_WAIT(bar(G2_READY + e), (s >> 1) & 1);
                 RS_MARK(0);
                 RS_EVT(100);
                 tc5::fence_after_sync();
@@ -333,7 +344,7 @@ wdsr_block_rs_kernel(const bf16 *__restrict__ in, bf16 *__restrict__ out, const 
             RS_MARK(7);
             for (int s = 0; s < T; ++s) {
                 const int eb = s & 1;
-                tc5::mbar_wait(bar(D1_FULL + eb), (s >> 1) & 1);
+                RS_CRIT_WAIT(bar(D1_FULL + eb), (s >> 1) & 1);
                 tc5::fence_after_sync();
                 RS_MARK(0);
                 RS_EVT(300);

@@ -230,47 +230,24 @@ class SpyNet(nn.Module, _VideoPlanMixin):
             self._norm_args = ((ctypes.c_float * 4)(*mean), (ctypes.c_float * 4)(*inv_std))
             self._norm_sig = nsig
         sub, mul = self._norm_args
-        f32 = dict(dtype=torch.float32, device=dev)
+        # ONE C-ABI call (b200sr_spynet_forward): the ~100 launches of the pyramid are sequenced in C on a cached workspace -- no
+        # per-launch ctypes call, no torch.empty per intermediate
+        hkey = "__spynet_handles__"
+        if hkey not in convs:
+            hs = [convs[f"basic_module.{level}.basic_module.{idx}"]._h for level in range(6) for idx in (0, 2, 4, 6, 8)]
+            convs[hkey] = (ctypes.c_void_p * len(hs))(*[h.value for h in hs])
+        prec = _lib.precision_code(self.precision)
+        need = L.b200sr_spynet_workspace_bytes(n, h, w, prec)
+        ws = self.__dict__.get("_ws")
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = self.__dict__["_ws"] = torch.empty(need, dtype=torch.uint8, device=dev)
+        ref, supp = ref.contiguous(), supp.contiguous()
+        if supp.dtype != ref.dtype:
+            supp = supp.to(ref.dtype)
+        out = torch.empty((n, 2, h, w), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            def prep(img):
-                img = img.contiguous()
-                out = torch.empty((n, 3, h_up, w_up), **f32)
-                _lib.check(L.b200sr_resize_bilinear_nchw(_ptr(img), _lib.dtype_code(img.dtype), _ptr(out), n, 3, h, w, h_up, w_up, 0, sub, mul, st))
-                pyr = [out]
-                for _ in range(5):
-                    ph, pw = pyr[0].shape[2] // 2, pyr[0].shape[3] // 2
-                    nxt = torch.empty((n, 3, ph, pw), **f32)
-                    _lib.check(L.b200sr_avg_pool2_nchw(_ptr(pyr[0]), _ptr(nxt), n, 3, pyr[0].shape[2], pyr[0].shape[3], st))
-                    pyr.insert(0, nxt)
-                return pyr
-
-            refs, supps = prep(ref), prep(supp)
-            adt = self._act_dtype()
-            cs = 8 if self.precision == "fp32" else 16
-            flow = None
-            ph, pw = refs[0].shape[2] // 2, refs[0].shape[3] // 2
-            for level in range(6):
-                hl, wl = refs[level].shape[2], refs[level].shape[3]
-                inp = torch.empty((n, hl, wl, cs), dtype=adt, device=dev)
-                up = torch.empty((n, 2, hl, wl), **f32)
-                _lib.check(L.b200sr_spynet_level_input(_ptr(refs[level]), _ptr(supps[level]), _ptr(flow) if flow is not None else None,
-                                                       _ptr(inp), _lib.dtype_code(adt), _ptr(up), n, hl, wl, ph, pw, cs, st))
-                t = inp
-                layers = [convs[f"basic_module.{level}.basic_module.{idx}"] for idx in (0, 2, 4, 6, 8)]
-                # bf16: layers 0-3 run on the tcgen05 7x7 kernel and keep their private tensors planar-8 (TMA box rows of 512
-                # contiguous bytes); the 16 -> 2 flow head reads NHWC
-                planar = self.precision != "fp32" and all(c.tcgen05_ok() for c in layers[:4])
-                for j, conv in enumerate(layers):
-                    last = j == 4
-                    t = conv(t, self.precision, ACT_NONE if last else ACT_RELU, out_dtype=torch.float32 if last else adt,
-                             x_planar=planar and 1 <= j <= 3, y_planar=planar and j <= 2)
-                flow = torch.empty((n, 2, hl, wl), **f32)
-                _lib.check(L.b200sr_nhwc_plus_nchw(_ptr(t), _ptr(up), _ptr(flow), n, 2, hl, wl, 2, st))
-                ph, pw = hl, wl
-            out = torch.empty((n, 2, h, w), **f32)
-            zero = (ctypes.c_float * 4)(0, 0, 0, 0)
-            scale = (ctypes.c_float * 4)(float(w) / float(w_up), float(h) / float(h_up), 1.0, 1.0)
-            _lib.check(L.b200sr_resize_bilinear_nchw(_ptr(flow), _lib.F32, _ptr(out), n, 2, h_up, w_up, h, w, 0, zero, scale, st))
+            _lib.check(L.b200sr_spynet_forward(convs[hkey], _ptr(ref), _ptr(supp), _lib.dtype_code(ref.dtype), _ptr(out), n, h, w, prec, sub, mul,
+                                               _ptr(ws), ws.numel(), st))
         return out
 
 

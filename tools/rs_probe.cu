@@ -60,6 +60,18 @@ int main(int argc, char **argv) {
     const int ws[] = {0, 1, 2, 3, 4, 8, 12, 16, 20, 24, 28};
     for (int w : ws) { int cnt[1024] = {0}; for (int i = 0; i < evn[w]; ++i) { int id = (int)(ev[w][i] >> 48); all.push_back({ev[w][i] & 0xFFFFFFFFFFFFull, w, id, cnt[id]++}); } }
     std::sort(all.begin(), all.end(), [](const E &a, const E &b) { return a.t < b.t; });
+    {   // issue durations: A even (warp 0), A odd (warp 1): 100 -> 102;  B (warp 2): 200 -> 201
+        for (int w : {0, 1, 2}) {
+            const int a = w < 2 ? 100 : 200, b = w < 2 ? 102 : 201;
+            std::vector<unsigned long long> ta_, tb_;
+            for (auto &e : all) if (e.w == w) { if (e.id == a) ta_.push_back(e.t); if (e.id == b) tb_.push_back(e.t); }
+            const size_t n = std::min(ta_.size(), tb_.size());
+            if (n < 8) continue;
+            double dur = 0, per = 0; size_t cnt = 0;
+            for (size_t i = 4; i + 2 < n; ++i) { dur += (double)(tb_[i] - ta_[i]); per += (double)(ta_[i + 1] - ta_[i]); ++cnt; }
+            printf("warp %d: %zu iterations, mean issue %.0f clk, mean period %.0f clk (wait = %.0f)\n", w, n, dur / cnt, per / cnt, (per - dur) / cnt);
+        }
+    }
     // per-step period as seen by issuer A
     std::vector<unsigned long long> ta;
     for (auto &e : all) if (e.w == 1 && e.id == 100) ta.push_back(e.t);
