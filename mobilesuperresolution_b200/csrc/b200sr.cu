@@ -367,7 +367,7 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
         }
         if ((rc = upload(img.data(), img.size(), (void **)&p->d_head_tc5))) return rc;
     }
-    if (CP == 24) {   // tcgen05 tail image (wdsr_tc5_tail.cuh): 3x3 chunks ordered (dx, c, dy); skip = 25 window pixels x 4 channels
+    if (CP == 24) {   // tcgen05 tail image (wdsr_tc5_tail.cuh): 3x3 chunks ordered (dx, c, dy); skip = 15 (window row, tap pair) chunks x [2 taps x 4 channels]
         const int NOP = round_up(NO, 16);
         TailTc5Layout L(NOP);
         std::vector<uint8_t> img((size_t)L.total, 0);
@@ -382,8 +382,12 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
             for (int c = 0; c < 3; ++c)
                 for (int ky = 0; ky < 5; ++ky)
                     for (int kx = 0; kx < 5; ++kx) {
-                        const int k = (ky * 5 + kx) * 4 + c;   // window pixel * 4 + channel
-                        at(L.ws + (o / 8) * L.sbo_s + (k / 8) * 128 + (o % 8) * 16)[k % 8] = f2bf(p->skip_w[(size_t)o * 75 + c * 25 + ky * 5 + kx]);
+                        // chunk (ky, j = kx / 2) holds taps 2j | 2j+1 x 4 channels; instruction order (wdsr_tc5_tail.cuh): i = ky: (ky,0) | (ky,1);
+                        // then the j = 2 chunks in pairs: (0,2) | (1,2), (2,2) | (3,2), (4,2) | zero
+                        const int j = kx / 2;
+                        const int chunk = j < 2 ? 2 * ky + j : 10 + ky;
+                        const int k = (kx & 1) * 4 + c;
+                        at(L.ws + (o / 8) * L.sbo_s + chunk * 128 + (o % 8) * 16)[k] = f2bf(p->skip_w[(size_t)o * 75 + c * 25 + ky * 5 + kx]);
                     }
             ((float *)(img.data() + L.bias))[o] = p->tail_b[o] + p->skip_b[o];
         }

@@ -6,9 +6,14 @@
 //   warp 0      TMA      nine cp.async.bulk.tensor.5d per tile: three x-shifted copies (one per horizontal tap) of the three
 //                        8-channel planes of the trunk tile + 1-row halo, so every 3x3 tap is a constant address offset;
 //                        out-of-image pixels are zero-filled by the TMA unit (= the conv's zero padding); double buffered
-//   warps 2-5   builder  stages (x - mean) as an NHWC4 bf16 tile, then im2col of the 5x5 skip for one M-tile: pixel p's 25
-//                        window pixels x 4 channels are 25 8-byte loads and 13 16-byte stores, no repacking (K = 104)
-//   warp 1      MMA      14 (3x3: 27 (tap, chunk) slices paired through the LBO stride) + 7 (skip) tcgen05.mma, N = 3 s^2 padded to 16
+//   warps 2-5   builder  stages (x - mean) as an NHWC4 bf16 tile (the next tile's pixels are prefetched into registers), then writes the
+//                        skip operand ONCE PER TILE: three x-shifted copies (shift 0, 2, 4) of the tile + 2-row halo whose 16-byte
+//                        entries hold TWO horizontally adjacent pixels [x | x+1] x 4 channels, so a K = 8 chunk covers two taps of a
+//                        window row and every (ky, tap pair) is a constant address offset -- no im2col.  (The first form built a K = 104
+//                        im2col per M-tile, 25 loads + 13 stores per pixel: ncu showed the builder warps 94 % busy and everybody else
+//                        waiting for them, profiles/r02_tail_head_ncu.md.)
+//   warp 1      MMA      14 (3x3: 27 (tap, chunk) slices paired through the LBO stride) + 8 (skip: 5 window rows x 3 tap pairs = 15
+//                        chunks) tcgen05.mma, N = 3 s^2 padded to 16
 //   warps 6-9   epilogue tcgen05.ld -> + bias + mean -> PixelShuffle store: lane = LR pixel, 32 lanes x s outputs are one
 //                        contiguous segment of an HR row
 #pragma once
@@ -23,7 +28,7 @@ struct TailTc5Layout {  // weight image (bytes); rows = output channel (NOP = 3 
     int wt, ws, bias, total, sbo_t, sbo_s;
     __host__ __device__ TailTc5Layout(int NOP) {
         sbo_t = 28 * 128;  // 27 (dx, c, dy) chunks + zero chunk
-        sbo_s = 14 * 128;  // 13 window chunks + zero chunk
+        sbo_s = 16 * 128;  // 15 (window row, tap pair) chunks + zero chunk: 8 instructions x 2 halves
         wt = 0;
         ws = wt + (NOP / 8) * sbo_t;
         bias = ws + (NOP / 8) * sbo_s;
@@ -35,10 +40,11 @@ namespace tc5tail {
 constexpr int TW = 32, TH = 8, NTHREADS = 320;
 constexpr int PLANE = (TH + 2) * TW * 16;  // 5,120 B: 10 rows x 32 px x 16 B
 constexpr int TC_BUF = 9 * PLANE;          // 46,080 B per tile (3 copies x 3 planes)
-constexpr int SK_BUF = 13 * 128 * 16;      // 26,624 B per M-tile (+ 2 KB slack read by the dummy half of the 7th instruction)
-constexpr int SK_STRIDE = SK_BUF + 2048;
-constexpr int XW = TW + 4, XH = TH + 4;    // x tile with 2-pixel halo, 8 bytes per pixel
-constexpr int X4_BUF = XH * XW * 8;        // 3,456 B
+constexpr int XW = TW + 5, XH = TH + 4;    // x tile with 2-pixel halo (+ 1 column: the zero-weight partner of the fifth tap), 8 bytes per pixel
+constexpr int X4_BUF = (XH * XW * 8 + 15) / 16 * 16;
+constexpr int SK_COPY = XH * TW * 16;      // 6,144 B: one x-shifted copy, 12 rows x 32 entries x 16 B ([pixel | right neighbour] x 4 channels)
+constexpr int SK_BUF = 3 * SK_COPY;        // 18,432 B per tile
+constexpr int SK_STRIDE = SK_BUF;
 constexpr int CTRL = 256;
 enum Bar { TC_FULL = 0, TC_EMPTY = 2, SK_FULL = 4, SK_EMPTY = 6, D_FULL = 8, D_EMPTY = 10, NBARS = 12 };
 __host__ __device__ inline size_t smem_bytes(int NOP) {
@@ -80,7 +86,7 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
     if (warp == 0) tc5::tmem_alloc(smem_u32(ctrl + 240), 128);
     for (int i = tid; i < L.total / 16; i += NTHREADS) cp_async16(wsm + i * 16, wimg + i * 16, 16);
     cp_async_commit();
-    for (int i = tid; i < 2 * SK_STRIDE / 16; i += NTHREADS) *reinterpret_cast<uint4 *>(sk + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (2 * SK_STRIDE + X4_BUF) / 16; i += NTHREADS) *reinterpret_cast<uint4 *>(sk + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     // the zero-weight dummy half of the 14th 3x3 instruction reads one row past the last plane of a buffer: keep it finite
     // before buffer 1 has ever been loaded (buffer 1 overflows into the zeroed skip area)
     for (int i = tid; i < 512 / 16; i += NTHREADS) *reinterpret_cast<uint4 *>(tc + TC_BUF + i * 16) = make_uint4(0u, 0u, 0u, 0u);
@@ -120,11 +126,13 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
         const bool leader = tc5::elect_one();
         const uint32_t idesc = tc5::idesc_bf16_f32(128, NOP);
         const uint64_t bwt = tc5::smem_desc(w_u + L.wt, 128, L.sbo_t), bws = tc5::smem_desc(w_u + L.ws, 128, L.sbo_s);
-        const uint64_t at0 = tc5::smem_desc(tc_u, 0, 128), as0 = tc5::smem_desc(sk_u, 2048, 128);
+        const uint64_t at0 = tc5::smem_desc(tc_u, 0, 128), as0 = tc5::smem_desc(sk_u, 0, 128);
         for (int g = 0; g < 2 * nmine; ++g) {
             const int it = g >> 1, h = g & 1, b = it & 1, e = g & 1;
-            if (h == 0) tc5::mbar_wait(bar(TC_FULL + b), (it >> 1) & 1);
-            tc5::mbar_wait(bar(SK_FULL + e), (g >> 1) & 1);
+            if (h == 0) {
+                tc5::mbar_wait(bar(TC_FULL + b), (it >> 1) & 1);
+                tc5::mbar_wait(bar(SK_FULL + b), (it >> 1) & 1);
+            }
             tc5::mbar_wait(bar(D_EMPTY + e), ((g >> 1) & 1) ^ 1);
             tc5::fence_after_sync();
             if (leader) {
@@ -137,57 +145,63 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
                     const int a1 = q1 < 27 ? (q1 / 3) * PLANE + (q1 % 3) * 512 : a0 + 512;
                     tc5::mma_ss(d, abase + (uint64_t)(a0 >> 4) + ((uint64_t)((a1 - a0) >> 4) << 16), bwt + (uint64_t)(16 * i), idesc, i > 0);
                 }
-                const uint64_t sbase = as0 + (uint64_t)((e * SK_STRIDE) >> 4);
+                // skip 5x5: chunk (ky, j) = copy j (shift 2j) at window row ky.  Instructions 0..4: (ky, 0) | (ky, 1) paired through the
+                // copy stride; 5..7: (0,2) | (1,2), (2,2) | (3,2), (4,2) | zero weights, paired through the row stride
+                const uint64_t sbase = as0 + (uint64_t)((b * SK_STRIDE + 4 * h * 512) >> 4);
 #pragma unroll
-                for (int i = 0; i < 7; ++i) tc5::mma_ss(d, sbase + (uint64_t)((2 * i * 2048) >> 4), bws + (uint64_t)(16 * i), idesc, true);
+                for (int i = 0; i < 5; ++i) tc5::mma_ss(d, sbase + (uint64_t)((i * 512) >> 4) + ((uint64_t)(SK_COPY >> 4) << 16), bws + (uint64_t)(16 * i), idesc, true);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                    tc5::mma_ss(d, sbase + (uint64_t)((2 * SK_COPY + 2 * i * 512) >> 4) + ((uint64_t)(512 >> 4) << 16), bws + (uint64_t)(16 * (5 + i)), idesc, true);
                 tc5::commit(bar(D_FULL + e));
-                tc5::commit(bar(SK_EMPTY + e));
-                if (h == 1) tc5::commit(bar(TC_EMPTY + b));
+                if (h == 1) {
+                    tc5::commit(bar(SK_EMPTY + b));
+                    tc5::commit(bar(TC_EMPTY + b));
+                }
             }
             __syncwarp();
         }
         if (nmine > 0) tc5::mbar_wait(bar(D_FULL + 1), ((2 * nmine - 1) >> 1) & 1);  // every MMA retired
     } else if (warp < 6) {
-        // ============================== builders: x - mean tile, skip im2col ==============================
+        // ============================== builders: x - mean tile, pair-packed shifted copies for the skip ==============================
         const int bt = tid - 64;  // 0..127
-        for (int g = 0; g < 2 * nmine; ++g) {
-            const int it = g >> 1, h = g & 1, e = g & 1;
+        constexpr int NIT = (XH * XW + 127) / 128;
+        float v[NIT][3];
+        auto fetch = [&](int it) {   // global loads of tile `it`'s (x - mean) pixels into registers (consumed one tile later)
             int x0, y0, n;
             tile_origin(it, x0, y0, n);
-            if (h == 0) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone finished reading the previous tile's x4
-                // all global loads of the staging pass are issued before the first use (one memory latency per tile, not four)
-                constexpr int NIT = (XH * XW + 127) / 128;
-                float v[NIT][3];
 #pragma unroll
-                for (int k = 0; k < NIT; ++k) {
-                    const int i = bt + 128 * k;
-                    const int gy = y0 - 2 + i / XW, gx = x0 - 2 + i % XW;
-                    const bool ok = i < XH * XW && gy >= 0 && gy < H && gx >= 0 && gx < W;
-                    const long long o = ok ? (((long long)n * 3) * H + gy) * W + gx : 0;
+            for (int k = 0; k < NIT; ++k) {
+                const int i = bt + 128 * k;
+                const int gy = y0 - 2 + i / XW, gx = x0 - 2 + i % XW;
+                const bool ok = i < XH * XW && gy >= 0 && gy < H && gx >= 0 && gx < W;
+                const long long o = ok ? (((long long)n * 3) * H + gy) * W + gx : 0;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) v[k][c] = ok ? to_f32<TIN>(x[o + (long long)c * H * W]) - mean : 0.f;
-                }
-#pragma unroll
-                for (int k = 0; k < NIT; ++k) {
-                    const int i = bt + 128 * k;
-                    if (i < XH * XW) *reinterpret_cast<uint2 *>(x4 + i * 8) = make_uint2(pack_bf16x2(v[k][0], v[k][1]), pack_bf16x2(v[k][2], 0.f));
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int c = 0; c < 3; ++c) v[k][c] = ok ? to_f32<TIN>(x[o + (long long)c * H * W]) - mean : 0.f;
             }
-            tc5::mbar_wait(bar(SK_EMPTY + e), ((g >> 1) & 1) ^ 1);
-            const int ly = 4 * h + (bt >> 5), lx = bt & 31;
-            uint2 wv[26];
+        };
+        if (nmine > 0) fetch(0);
+        for (int it = 0; it < nmine; ++it) {
+            const int b = it & 1;
 #pragma unroll
-            for (int ky = 0; ky < 5; ++ky)
+            for (int k = 0; k < NIT; ++k) {
+                const int i = bt + 128 * k;
+                if (i < XH * XW) *reinterpret_cast<uint2 *>(x4 + i * 8) = make_uint2(pack_bf16x2(v[k][0], v[k][1]), pack_bf16x2(v[k][2], 0.f));
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (it + 1 < nmine) fetch(it + 1);       // in flight while this tile's operand is written
+            tc5::mbar_wait(bar(SK_EMPTY + b), ((it >> 1) & 1) ^ 1);
+            uint8_t *dstb = sk + b * SK_STRIDE;
 #pragma unroll
-                for (int kx = 0; kx < 5; ++kx) wv[ky * 5 + kx] = *reinterpret_cast<const uint2 *>(x4 + ((ly + ky) * XW + lx + kx) * 8);
-            wv[25] = make_uint2(0u, 0u);
-            uint8_t *dst = sk + e * SK_STRIDE + bt * 16;
-#pragma unroll
-            for (int j = 0; j < 13; ++j) *reinterpret_cast<uint4 *>(dst + j * 2048) = make_uint4(wv[2 * j].x, wv[2 * j].y, wv[2 * j + 1].x, wv[2 * j + 1].y);
+            for (int k = 0; k < 3 * XH * TW / 128; ++k) {   // 9 entries per thread: copy j, row yy, column xx
+                const int e = bt + 128 * k, j = e / (XH * TW), r = e % (XH * TW), yy = r / TW, xx = r % TW;
+                const uint8_t *src = x4 + (yy * XW + xx + 2 * j) * 8;
+                const uint2 lo = *reinterpret_cast<const uint2 *>(src), hi = *reinterpret_cast<const uint2 *>(src + 8);
+                *reinterpret_cast<uint4 *>(dstb + j * SK_COPY + r * 16) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            }
             tc5::fence_proxy_async();
-            tc5::mbar_arrive(bar(SK_FULL + e));
+            tc5::mbar_arrive(bar(SK_FULL + b));
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone finished reading x4 before the next tile overwrites it
         }
     } else {
         // ============================== epilogue ==============================
@@ -195,10 +209,10 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const float *bias = reinterpret_cast<const float *>(wsm + L.bias);
         const int OH = S * H, OW = S * W;
+        int x0 = 0, y0 = 0, n = 0;
         for (int g = 0; g < 2 * nmine; ++g) {
             const int it = g >> 1, h = g & 1, e = g & 1;
-            int x0, y0, n;
-            tile_origin(it, x0, y0, n);
+            if (h == 0) tile_origin(it, x0, y0, n);   // (two integer divisions: once per tile, not per M-tile)
             tc5::mbar_wait(bar(D_FULL + e), (g >> 1) & 1);
             tc5::fence_after_sync();
             uint32_t v[NOP];
@@ -209,11 +223,13 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
             tc5::mbar_arrive_relaxed(bar(D_EMPTY + e));
             const int gy = y0 + 4 * h + (row >> 5), gx = x0 + (row & 31);
             if (gy < H && gx < W) {
+                TOUT *o0 = y + (((long long)n * 3) * OH + S * gy) * OW + S * gx;   // (c, i) add constant strides to one base
+                const long long cstride = (long long)OH * OW;
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
                     for (int i = 0; i < S; ++i) {
-                        TOUT *o = y + (((long long)n * 3 + c) * OH + (S * gy + i)) * OW + S * gx;
+                        TOUT *o = o0 + c * cstride + i * OW;
                         float r[S];
                         if constexpr (S == 4) {
                             const float4 bb = *reinterpret_cast<const float4 *>(bias + c * 16 + i * 4);  // broadcast read

@@ -24,7 +24,12 @@ def t(fn, reps=20, flush=False):
     return tot / reps * 1e3
 
 
-trunk = plan.head(x, "bf16")   # NHWC view; plan.tail converts to the internal layout (adds a copy to the tail timing)
+from mobilesuperresolution_b200 import _lib
+trunk = plan.head_internal(x, "bf16")   # the kernels' own trunk layout: no conversion inside the timed calls
+y = torch.empty(64, 3, 384, 384, device=dev, dtype=torch.bfloat16)
+L, st = _lib.lib(), _lib.current_stream_ptr(dev)
+def tail():
+    _lib.check(L.b200sr_wdsr_tail(plan.handle, trunk.data_ptr(), x.data_ptr(), _lib.BF16, y.data_ptr(), _lib.BF16, 64, 96, 96, _lib.BF16, st))
 for fl in (False, True):
-    print(f"L2 {'flushed' if fl else 'warm   '}: head {t(lambda: plan.head(x, 'bf16'), flush=fl):7.1f} us   tail {t(lambda: plan.tail(trunk, x, 'bf16'), flush=fl):7.1f} us   "
+    print(f"L2 {'flushed' if fl else 'warm   '}: head {t(lambda: plan.head_internal(x, 'bf16'), flush=fl):7.1f} us   tail {t(tail, flush=fl):7.1f} us   "
           f"forward {t(lambda: plan.forward(x, 'bf16'), flush=fl):7.1f} us")
