@@ -86,7 +86,7 @@ struct b200sr_wdsr {
     std::vector<uint8_t *> d_blk_bf16;
     std::vector<uint8_t *> d_blk_tc5;  // tcgen05 operand images (nullptr where the block is not eligible)
     std::vector<uint8_t *> d_blk_rs;   // row-streaming tcgen05 operand images (wdsr_rs.cuh), same eligibility
-    int block_impl = 0;                // 0 = mma.sync kernel, 1 = tcgen05 sequential form, 2 = tcgen05 tile form, 3 = tcgen05 row-streaming form
+    int block_impl = 0;                // 0 = mma.sync kernel, 1 = tcgen05 sequential form, 2 = tcgen05 tile form, 3 = tcgen05 row-streaming form, 4 = row-streaming with the reduce on mma.sync (wdsr_rh.cuh)
     float *d_tail_f32 = nullptr;
     uint8_t *d_tail_bf16 = nullptr;
     uint8_t *d_head_tc5 = nullptr;   // tcgen05 head image (trunk padded to 24 channels)
@@ -317,11 +317,12 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
     }
     {
         // default: the tcgen05 kernel wherever a block is eligible (trunk padded to 24, M2 <= 24), the mma.sync kernel
-        // elsewhere.  B200SR_BLOCK_IMPL = mma | tc5seq | tc5 | rs is a developer switch (A/B timing, reference form):
-        // tc5 = the tile form (wdsr_tc5p.cuh, the default), rs = the row-streaming form (wdsr_rs.cuh): parity-green and within
-        // +-7 % of the tile form (cfg2 28.4 vs 25.9 us, 1080p 74-82 vs 80 us per launch; DESIGN.md 4.1b says what bounds both).
+        // elsewhere.  B200SR_BLOCK_IMPL = mma | tc5seq | tc5 | rs | rh is a developer switch (A/B timing, reference form):
+        // tc5 = the tile form (wdsr_tc5p.cuh, the default); rs = the row-streaming form (wdsr_rs.cuh; cfg2 28.4 vs 26.9 us, 1080p 74-82 vs
+        // 80 us per launch); rh = row-streaming with the reduce 1x1 on mma.sync out of registers (wdsr_rh.cuh; 32.5 / 94 us: bound by the
+        // legacy HMMA rate, profiles/r02_block_rh.md).  All three are parity-green against the oracle and each other.
         const char *e = getenv("B200SR_BLOCK_IMPL");
-        p->block_impl = !e ? 2 : !strcmp(e, "mma") ? 0 : !strcmp(e, "tc5seq") ? 1 : !strcmp(e, "rs") ? 3 : 2;
+        p->block_impl = !e ? 2 : !strcmp(e, "mma") ? 0 : !strcmp(e, "tc5seq") ? 1 : !strcmp(e, "rs") ? 3 : !strcmp(e, "rh") ? 4 : 2;
     }
     const int NO = p->no;
     {   // tail fp32: Wt[9][CP][NOP4] | Ws[75][NOP4] | bias[NOP4]
@@ -460,6 +461,8 @@ int b200sr_wdsr_block(const b200sr_wdsr_t *p, int i, const void *tin, void *tout
                             (cudaStream_t)stream));
     else if (p->tc5_path() && p->block_impl == 3 && block_rs_eligible(n, h, w))
         CU(launch_block_rs(tin, tout, p->d_blk_rs[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
+    else if (p->tc5_path() && p->block_impl == 4 && block_rs_eligible(n, h, w))
+        CU(launch_block_rh(tin, tout, p->d_blk_rs[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
     else if (p->tc5_path())
         CU(launch_block_tc5(1, tin, tout, p->d_blk_tc5[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
     else if (p->block_impl == 1 && p->d_blk_tc5[i] && p->m2[i] > 16)   // sequential tcgen05 reference form (NHWC trunk, all 27 w3 slices; developer switch)

@@ -40,6 +40,8 @@ cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8
 // row-streaming tcgen05 form of the fused block (wdsr_rs.cuh; planar-8 trunk, CP == 24, M2 <= 24, M1P <= 144)
 bool block_rs_eligible(int N, int H, int W);
 cudaError_t launch_block_rs(const void *in, void *out, const uint8_t *wimg, int M1P, int M2, int N, int H, int W, cudaStream_t st);
+// the same with the reduce 1x1 on mma.sync out of registers (wdsr_rh.cuh; same operand image, same eligibility)
+cudaError_t launch_block_rh(const void *in, void *out, const uint8_t *wimg, int M1P, int M2, int N, int H, int W, cudaStream_t st);
 // tcgen05 form of the head (bf16 trunk padded to 24 channels)
 cudaError_t launch_head_tc5(int x_dtype, const void *x, void *trunk, const uint8_t *wimg, int N, int H, int W, float mean, cudaStream_t st);
 // tcgen05 form of the fused tail (trunk padded to 24 channels)

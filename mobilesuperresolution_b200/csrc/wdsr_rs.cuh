@@ -55,7 +55,12 @@ __device__ int g_rs_evtn[32];
 #endif
 #define RS_EVT(id) do { if ((id) >= B200SR_RS_EVT_LO && (id) < B200SR_RS_EVT_HI && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && evn__ < 4096) { g_rs_evt[threadIdx.x >> 5][evn__++] = ((unsigned long long)(id) << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull); } } while (0)
 #define RS_FLUSH() do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_rs_evtn[threadIdx.x >> 5] = evn__; } while (0)
+// the clock is read under a predicate computed from `dep` (a float the event must come after): ptxas cannot schedule the read ahead of it
+#define RS_EVT_DEP(id, dep) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && evn__ < 4096) { unsigned long long t__; \
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %1, 0f7F812345;\n\t@p mov.u64 %0, %%clock64;\n\t@!p mov.u64 %0, 0;\n\t}" : "=l"(t__) : "f"(dep)); \
+    g_rs_evt[threadIdx.x >> 5][evn__++] = ((unsigned long long)(id) << 48) | (t__ & 0xFFFFFFFFFFFFull); } } while (0)
 #else
+#define RS_EVT_DEP(id, dep) do {} while (0)
 #define RS_DECL() do {} while (0)
 #define RS_EVT(id) do {} while (0)
 #define RS_FLUSH() do {} while (0)

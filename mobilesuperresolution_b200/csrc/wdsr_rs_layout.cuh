@@ -7,7 +7,7 @@ namespace b200sr {
 
 struct BlockRsLayout {  // weight image, bytes (host builds it, the kernel copies it verbatim to shared memory)
     static constexpr int MAXG3 = 5;
-    int w1, w2, w3, b2, b3, tab, total, sbo2, sbo3;
+    int w1, w2, w3, b2, b3, tab, w2f, total, sbo2, sbo3;
     __host__ __device__ BlockRsLayout(int M1P) {
         w1 = 0;                           // [M1P/8][c0,c1,c2,BIAS][8 rows][8]      rows = expand channel (same as BlockTc5Layout)
         w2 = w1 + (M1P / 8) * 512;        // [4][M1P/8 chunks][8 rows][8]           rows = reduce channel (32, <= 24 used)
@@ -17,7 +17,8 @@ struct BlockRsLayout {  // weight image, bytes (host builds it, the kernel copie
         b2 = w3 + 12 * sbo3;              // f32[32]
         b3 = b2 + 128;                    // f32[32]
         tab = b3 + 128;                   // int32: ng3, a_off[MAXG3], a_lbo[MAXG3]   (A-operand slices of the 3x3, bytes)
-        total = tab + 64;
+        w2f = tab + 64;                   // [M1P/16 k-steps][3 n-tiles][32 lanes][2] u32: B fragments of mma.sync.m16n8k16 (wdsr_rh.cuh)
+        total = w2f + (M1P / 16) * 3 * 256;
     }
 };
 

@@ -97,6 +97,16 @@ inline void pack_block_rs(std::vector<uint8_t> &img, int C, int M1, int M2, int 
                     }
         }
     }
+    // reduce filter as mma.sync B fragments (wdsr_rh.cuh) in the K order of tcgen05.ld.16x128b (tc5.cuh): thread (g = lane / 4,
+    // j = lane % 4) of n-tile nt, k-step ks holds {w2[8nt + g][16ks + j], [16ks + 4 + j]} and {w2[8nt + g][16ks + 8 + j], [16ks + 12 + j]}
+    for (int ks = 0; ks < M1P / 16; ++ks)
+        for (int nt = 0; nt < 3; ++nt)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int n = 8 * nt + lane / 4, k0 = 16 * ks + lane % 4;
+                auto w = [&](int k) { return (n < M2 && k < M1) ? rs_f2bf(w2[(size_t)n * M1 + k]) : (uint16_t)0; };
+                uint16_t *f = at(L.w2f + ((ks * 3 + nt) * 32 + lane) * 8);
+                f[0] = w(k0), f[1] = w(k0 + 4), f[2] = w(k0 + 8), f[3] = w(k0 + 12);
+            }
     float *pb2 = (float *)(img.data() + L.b2), *pb3 = (float *)(img.data() + L.b3);
     for (int j = 0; j < M2; ++j) pb2[j] = b2[j];
     for (int o = 0; o < C; ++o) pb3[o] = b3[o];

@@ -173,8 +173,10 @@ def test_spynet_bf16_in_db_at_cfg4_size(sr):
 # ------------------------------------------------------------------------------------------------ row-streaming block
 @pytest.mark.parametrize("shape", [(1, 24, 16, 32), (2, 24, 37, 45), (3, 24, 96, 96), (1, 24, 5, 300), (2, 24, 1, 1), (1, 24, 131, 7)])
 @pytest.mark.parametrize("widths", [(24, 144, 20), (24, 144, 24), (20, 100, 13), (9, 91, 7)])
-def test_row_streaming_block_equals_oracle_and_tile_form(sr, shape, widths, monkeypatch):
-    """The row-streaming tcgen05 form of the fused block (csrc/wdsr_rs.cuh, B200SR_BLOCK_IMPL=rs) on ragged shapes and pruned widths:
+@pytest.mark.parametrize("form", ["rs", "rh"])
+def test_row_streaming_block_equals_oracle_and_tile_form(sr, shape, widths, form, monkeypatch):
+    """The row-streaming forms of the fused block (csrc/wdsr_rs.cuh: all tcgen05; csrc/wdsr_rh.cuh: reduce 1x1 on mma.sync out of
+    registers; B200SR_BLOCK_IMPL=rs|rh) on ragged shapes and pruned widths:
     >= 50 dB against the oracle block, and within one bf16 ulp-flip budget of the tile form (same rounding points, different fp32
     summation order)."""
     import tempfile
@@ -197,7 +199,7 @@ def test_row_streaming_block_equals_oracle_and_tile_form(sr, shape, widths, monk
     g = torch.Generator().manual_seed(h * 1000 + w)
     t = (torch.rand(n, c, h, w, generator=g) - 0.5) * 2
     outs = {}
-    for impl in ("rs", "tc5"):
+    for impl in (form, "tc5"):
         m, sd = build(impl)
         plan = m.prepare()
         cp = plan.trunk_channels
@@ -209,16 +211,17 @@ def test_row_streaming_block_equals_oracle_and_tile_form(sr, shape, widths, monk
         torch.cuda.synchronize()
         outs[impl] = o.float().cpu()
     ref = port.wdsr_block(sd, "body.1.", tin.float().cpu()[..., :c].permute(0, 3, 1, 2))
-    got = outs["rs"][..., :c].permute(0, 3, 1, 2)
+    got = outs[form][..., :c].permute(0, 3, 1, 2)
     assert port.psnr_db(got, ref) >= BF16_PSNR
-    assert float(outs["rs"][..., c:].abs().max()) == 0.0 if cp > c else True            # pad channels stay exactly zero
-    d = (outs["rs"] - outs["tc5"]).abs()
+    assert float(outs[form][..., c:].abs().max()) == 0.0 if cp > c else True            # pad channels stay exactly zero
+    d = (outs[form] - outs["tc5"]).abs()
     assert float(d.max()) <= 2 ** -6 * max(1.0, float(ref.abs().max()))                  # <= a couple of bf16 ulps at the output's scale
     assert float((d > 0).float().mean()) < 0.2
 
 
-def test_row_streaming_model_graph_replay_is_deterministic(sr, monkeypatch):
-    monkeypatch.setenv("B200SR_BLOCK_IMPL", "rs")
+@pytest.mark.parametrize("form", ["rs", "rh"])
+def test_row_streaming_model_graph_replay_is_deterministic(sr, form, monkeypatch):
+    monkeypatch.setenv("B200SR_BLOCK_IMPL", form)
     torch.manual_seed(3)
     p = types.SimpleNamespace(image_mean=0.5, num_channels=3, scale=4, num_blocks=4, num_residual_units=24, width_search=False, pretrained=False)
     m = sr.BASIC_MODEL(p).eval().cuda().set_precision("bf16")
@@ -235,7 +238,7 @@ def test_row_streaming_model_graph_replay_is_deterministic(sr, monkeypatch):
 # tested directly: (1) no kernel of the WDSR path writes outside its output / workspace -- every buffer sits between red zones of a
 # canary pattern that must survive; (2) the mbarrier / TMEM pipelines are free of observable races -- the same input gives
 # bit-identical output 12 times in a row while a second stream keeps the SMs and L2 busy with unrelated work.
-@pytest.mark.parametrize("impl", ["tc5", "rs"])
+@pytest.mark.parametrize("impl", ["tc5", "rs", "rh"])
 @pytest.mark.parametrize("shape,scale", [((2, 3, 37, 45), 4), ((1, 3, 130, 66), 2), ((3, 3, 96, 96), 4)])
 def test_red_zones_survive_and_results_repeat_under_load(sr, impl, shape, scale, monkeypatch):
     from mobilesuperresolution_b200 import _lib

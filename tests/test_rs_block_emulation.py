@@ -39,7 +39,8 @@ def layout(m1p):
     b2 = w3 + 12 * sbo3
     b3 = b2 + 128
     tab = b3 + 128
-    return dict(w1=w1, w2=w2, w3=w3, b2=b2, b3=b3, tab=tab, total=tab + 64, sbo2=sbo2, sbo3=sbo3)
+    w2f = tab + 64
+    return dict(w1=w1, w2=w2, w3=w3, b2=b2, b3=b3, tab=tab, w2f=w2f, total=w2f + (m1p // 16) * 3 * 256, sbo2=sbo2, sbo3=sbo3)
 
 
 def operand(buf, start, lbo, sbo, rows):
@@ -250,6 +251,19 @@ def test_replay_matches_block(C, M1, M2, N, H, W, ctas):
     assert lib.b200sr_wdsr_pack_block_image(C, M1, M2, ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(w3), ptr(b3), ptr(img), img.size, ctypes.byref(need)) == 0
     nc2 = 1 if M2 <= 8 else 2 if M2 <= 16 else 3
     pack = 16 < M2 <= 20
+    # the reduce filter as mma.sync.m16n8k16 B fragments in the K order of tcgen05.ld.16x128b (csrc/wdsr_rh.cuh, tc5.cuh): thread (g, j) of
+    # n-tile nt, k-step ks holds w2[8nt + g][16ks + {j, 4 + j}] and [16ks + {8 + j, 12 + j}]; decode the region back into the padded matrix
+    frag = img[layout(m1p)["w2f"]:].view(np.uint16).reshape(m1p // 16, 3, 32, 4)
+    dec = np.zeros((24, m1p), dtype=np.float32)
+    for ks in range(m1p // 16):
+        for nt in range(3):
+            for lane in range(32):
+                g, j = lane // 4, lane % 4
+                for i, k in enumerate((j, j + 4, j + 8, j + 12)):
+                    dec[8 * nt + g, 16 * ks + k] = bits_f32(frag[ks, nt, lane, i:i + 1])[0]
+    exp = np.zeros((24, m1p), dtype=np.float32)
+    exp[:M2, :M1] = bf16_round(w2)
+    assert np.array_equal(dec, exp)
     x = np.zeros((N, 24, H, W), dtype=np.float32)
     x[:, :C] = bf16_round(rng.standard_normal((N, C, H, W)))
     got = from_planar(replay(img, m1p, nc2, pack, to_planar(x), N, H, W, ctas))

@@ -61,6 +61,38 @@ __global__ void __launch_bounds__(544, 1) bench(int mode, int nw, int iters, int
     if (warp == 0) tc5::tmem_free(tmem, 512);
 }
 
+// the register footprint of wdsr_rh.cuh's E1: A[2][9][4] and B[9][3][2] all distinct registers (slot 2 of g_out)
+__global__ void __launch_bounds__(512, 1) bench_full(int nw, int iters, int two_sets) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long t0 = clock64();
+    long long t1 = t0;
+    if (warp < nw) {
+        float c[6][4], c1[6][4];
+        uint32_t a[2][9][4], b[9][3][2];
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 4; ++j) c[i][j] = 0.f, c1[i][j] = 0.f;
+        for (int m = 0; m < 2; ++m) for (int k = 0; k < 9; ++k) for (int j = 0; j < 4; ++j) a[m][k][j] = 0x3c003c00u + lane + m * 7 + k * 3 + j;
+        for (int k = 0; k < 9; ++k) for (int n = 0; n < 3; ++n) for (int j = 0; j < 2; ++j) b[k][n][j] = 0x3c003c00u + lane * 3 + k * 5 + n + j;
+#pragma unroll 1
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int n = 0; n < 3; ++n) {
+                        if (two_sets && (k & 1)) hmma(c1[m * 3 + n], a[m][k], b[k][n]);
+                        else hmma(c[m * 3 + n], a[m][k], b[k][n]);
+                    }
+            }
+        }
+        float s = 0.f;
+        for (int i = 0; i < 6; ++i) for (int j = 0; j < 4; ++j) s += c[i][j] + c1[i][j];
+        if (s == 12345.f) g_out[63] = 1;
+        t1 = clock64();
+    }
+    if (lane == 0 && warp < 16) g_out[40 + warp] = (unsigned long long)(t1 - t0);
+}
+
 int main() {
     const size_t smem = 64 * 1024;
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -89,6 +121,15 @@ int main() {
     run(3, 4, 6, "both, 4 warps");
     run(3, 8, 6, "both, 8 warps");
     run(3, 16, 6, "both, 16 warps");
+    for (int two = 0; two < 2; ++two)
+        for (int nw : {4, 8, 16}) {
+            for (int rep = 0; rep < 2; ++rep) bench_full<<<1, 512>>>(nw, iters, two);
+            printf("%s ", cudaGetErrorString(cudaDeviceSynchronize()));
+            cudaMemcpyFromSymbol(out, g_out, sizeof out);
+            unsigned long long mx = 0;
+            for (int w = 0; w < nw; ++w) mx = out[40 + w] > mx ? out[40 + w] : mx;
+            printf("full footprint (126 operand registers), %2d warps, %d accumulator set(s): %5.2f clk per HMMA per SMSP\n", nw, two + 1, (double)mx / (iters * 54.0 * ((nw + 3) / 4)));
+        }
     // whole chip: power / clock effects are not visible from one SM -- repeat "both" on every SM
     for (int rep = 0; rep < 2; ++rep) bench<<<148, 544, smem>>>(3, 16, iters * 10, ummas * 10, 6, 1);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
