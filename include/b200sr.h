@@ -277,6 +277,12 @@ B200SR_API int b200sr_nchw3_to_nhwc(const void *x_dev, int x_dtype, int64_t x_ns
 B200SR_API int b200sr_vsr_base_add(const void *a_dev, int a_dtype, int cs, const void *img_dev, int img_dtype, int64_t img_nstride,
                                    float *y_dev, int64_t y_nstride, int n, int h, int w, void *stream);
 
+/* out[n,c,4h,4w] = PixelShuffle(4)(a)[n,c,4h,4w] + F.interpolate(img, scale_factor=4, 'bilinear', align_corners=False): the tail of
+ * Naive_model (models/naive_multi_model_easy.py:141-144, `self.shuf(self.decode(x_)) + base`); a NHWC (n,h,w,cs >= 48), channel 16c + 4i + j
+ * of a low-resolution pixel is output (c, 4y + i, 4x + j); out float32 with image stride y_nstride elements */
+B200SR_API int b200sr_vsr_shuffle4_base_add(const void *a_dev, int a_dtype, int cs, const void *img_dev, int img_dtype, int64_t img_nstride,
+                                            float *y_dev, int64_t y_nstride, int n, int h, int w, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ from .split import Conv_sep, MyAggregationLayer, Split_Block  # noqa: F401
 from .graph import Graphed  # noqa: F401
 from .frames import forward_u8_frames, psnr_u8, ssd_u8, u8_to_unit  # noqa: F401
 from .video import (BasicVSR, BasicVSR_origin, MotionVectorVSR, SpyNet, flow_warp)  # noqa: F401
+from .naive import Naive_model, NaiveBlock  # noqa: F401
 
 __version__ = "0.1.0"
 

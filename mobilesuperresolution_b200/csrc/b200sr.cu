@@ -667,7 +667,7 @@ struct b200sr_conv {
 
 int b200sr_conv_create(int cin, int cout, int k, const float *w, const float *bias, b200sr_conv_t **out) {
     if (!w || !out) return fail(B200SR_E_INVAL, "conv_create: null argument");
-    if (cin < 1 || cout < 1 || (k != 1 && k != 3 && k != 7)) return fail(B200SR_E_UNSUPPORTED, "conv_create: cin=%d cout=%d k=%d (k in {1,3,7})", cin, cout, k);
+    if (cin < 1 || cout < 1 || (k != 1 && k != 3 && k != 5 && k != 7)) return fail(B200SR_E_UNSUPPORTED, "conv_create: cin=%d cout=%d k=%d (k in {1,3,5,7})", cin, cout, k);
     if (b200sr_device_count() <= 0) return fail(B200SR_E_STATE, "conv_create: no CUDA device (this library has no CPU fallback)");
     b200sr_conv *c = new (std::nothrow) b200sr_conv();
     if (!c) return fail(B200SR_E_INVAL, "conv_create: out of memory");
@@ -990,6 +990,13 @@ int b200sr_vsr_base_add(const void *a, int a_dtype, int cs, const void *img, int
                         int n, int h, int w, void *stream) {
     if (!a || !img || !y || cs < 3) return fail(B200SR_E_INVAL, "vsr_base_add: bad argument");
     CU(launch_vsr_base_add(a, a_dtype, cs, img, img_dtype, img_nstride, y, y_nstride, n, h, w, (cudaStream_t)stream));
+    return 0;
+}
+
+int b200sr_vsr_shuffle4_base_add(const void *a, int a_dtype, int cs, const void *img, int img_dtype, int64_t img_nstride, float *y, int64_t y_nstride,
+                                 int n, int h, int w, void *stream) {
+    if (!a || !img || !y || cs < 48) return fail(B200SR_E_INVAL, "vsr_shuffle4_base_add: bad argument (a has at least 3 x 16 channels)");
+    CU(launch_vsr_base_add(a, a_dtype, cs, img, img_dtype, img_nstride, y, y_nstride, n, h, w, (cudaStream_t)stream, true));
     return 0;
 }
 

@@ -51,6 +51,7 @@ cudaError_t launch_conv(const ConvArgs &a, int k, int nt, int in_dtype, int out_
         switch (k) {
             case 1: return conv_f32_t<1, float>(a, st);
             case 3: return conv_f32_t<3, float>(a, st);
+            case 5: return conv_f32_t<5, float>(a, st);
             case 7: return conv_f32_t<7, float>(a, st);
         }
         return cudaErrorInvalidValue;
@@ -58,6 +59,7 @@ cudaError_t launch_conv(const ConvArgs &a, int k, int nt, int in_dtype, int out_
     switch (k) {
         case 1: return conv_bf16_io<1>(nt, in_dtype, out_dtype, a, st);
         case 3: return conv_bf16_io<3>(nt, in_dtype, out_dtype, a, st);
+        case 5: return conv_bf16_io<5>(nt, in_dtype, out_dtype, a, st);
         case 7: return conv_bf16_io<7>(nt, in_dtype, out_dtype, a, st);
     }
     return cudaErrorInvalidValue;

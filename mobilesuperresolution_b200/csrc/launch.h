@@ -89,6 +89,6 @@ cudaError_t launch_nhwc_plus_nchw(const float *a, const float *b, float *y, int 
 cudaError_t launch_nchw3_to_nhwc(const void *x, int x_dtype, long long x_nstride, void *y, int y_dtype, int n, int h, int w, int cs, int co,
                                  cudaStream_t st);
 cudaError_t launch_vsr_base_add(const void *a, int a_dtype, int cs, const void *img, int img_dtype, long long img_nstride, float *y,
-                                long long y_nstride, int n, int h, int w, cudaStream_t st);
+                                long long y_nstride, int n, int h, int w, cudaStream_t st, bool shuffle4 = false);
 
 }  // namespace b200sr

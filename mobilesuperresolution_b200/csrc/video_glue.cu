@@ -194,7 +194,9 @@ cudaError_t launch_nchw3_to_nhwc(const void *x, int x_dtype, long long x_nstride
 }
 
 // out_nchw[n,c,Y,X] = a_nhwc[n,Y,X,c] + bilinear_x4(img)[n,c,Y,X]   (conv_last + F.interpolate(x_i, scale 4, align False), :90-92)
-template <typename TA, typename TIMG>
+// PS: a is the LR tensor (n,h,w,CS) of 3 x 16 channels and PixelShuffle(4) is applied on the fly: a_hr[n,c,Y,X] = a[n,Y/4,X/4,16c + 4(Y%4) + X%4]
+// (models/naive_multi_model_easy.py:141-144: shuf(decode(x)) + base)
+template <typename TA, typename TIMG, bool PS>
 __global__ void __launch_bounds__(256) vsr_base_add_kernel(const TA *__restrict__ a, int CS, const TIMG *__restrict__ img, long long img_nstride,
                                                            float *__restrict__ y, long long y_nstride, int N, int h, int w) {
     const int OH = 4 * h, OW = 4 * w;
@@ -208,24 +210,28 @@ __global__ void __launch_bounds__(256) vsr_base_add_kernel(const TA *__restrict_
         const TIMG *p = img + n * img_nstride + (long long)c * h * w;
         const float base = (1.f - ly) * ((1.f - lx) * to_f32<TIMG>(p[y0 * w + x0]) + lx * to_f32<TIMG>(p[y0 * w + x1])) +
                            ly * ((1.f - lx) * to_f32<TIMG>(p[y1 * w + x0]) + lx * to_f32<TIMG>(p[y1 * w + x1]));
-        y[n * y_nstride + ((long long)c * OH + oy) * OW + ox] = to_f32<TA>(a[(((long long)n * OH + oy) * OW + ox) * CS + c]) + base;
+        const long long ai = PS ? (((long long)n * h + (oy >> 2)) * w + (ox >> 2)) * CS + 16 * c + 4 * (oy & 3) + (ox & 3)
+                                : (((long long)n * OH + oy) * OW + ox) * CS + c;
+        y[n * y_nstride + ((long long)c * OH + oy) * OW + ox] = to_f32<TA>(a[ai]) + base;
     }
 }
 cudaError_t launch_vsr_base_add(const void *a, int a_dtype, int cs, const void *img, int img_dtype, long long img_nstride, float *y,
-                                long long y_nstride, int n, int h, int w, cudaStream_t st) {
+                                long long y_nstride, int n, int h, int w, cudaStream_t st, bool shuffle4) {
     const long long total = (long long)n * 3 * 16 * h * w;
     if (total == 0) return cudaSuccess;
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
-    if (a_dtype == kF32 && img_dtype == kF32)
-        vsr_base_add_kernel<float, float><<<(unsigned)blocks, 256, 0, st>>>((const float *)a, cs, (const float *)img, img_nstride, y, y_nstride, n, h, w);
-    else if (a_dtype == kBF16 && img_dtype == kF32)
-        vsr_base_add_kernel<bf16, float><<<(unsigned)blocks, 256, 0, st>>>((const bf16 *)a, cs, (const float *)img, img_nstride, y, y_nstride, n, h, w);
-    else if (a_dtype == kBF16 && img_dtype == kBF16)
-        vsr_base_add_kernel<bf16, bf16><<<(unsigned)blocks, 256, 0, st>>>((const bf16 *)a, cs, (const bf16 *)img, img_nstride, y, y_nstride, n, h, w);
-    else
-        return cudaErrorInvalidValue;
-    return cudaGetLastError();
+#define B200SR_BA_CASE(TD, ID, TA, TI)                                                                                                      \
+    if (a_dtype == TD && img_dtype == ID) {                                                                                                 \
+        if (shuffle4) vsr_base_add_kernel<TA, TI, true><<<(unsigned)blocks, 256, 0, st>>>((const TA *)a, cs, (const TI *)img, img_nstride, y, y_nstride, n, h, w); \
+        else vsr_base_add_kernel<TA, TI, false><<<(unsigned)blocks, 256, 0, st>>>((const TA *)a, cs, (const TI *)img, img_nstride, y, y_nstride, n, h, w);      \
+        return cudaGetLastError();                                                                                                          \
+    }
+    B200SR_BA_CASE(kF32, kF32, float, float)
+    B200SR_BA_CASE(kBF16, kF32, bf16, float)
+    B200SR_BA_CASE(kBF16, kBF16, bf16, bf16)
+#undef B200SR_BA_CASE
+    return cudaErrorInvalidValue;
 }
 
 // Tail of the fork's BasicVSR / MotionVectorVSR after conv_last = ConvTranspose2d(2nf, 3, 5, stride 4) evaluated as a 3x3 convolution with

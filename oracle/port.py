@@ -400,3 +400,38 @@ def psnr_db(y: torch.Tensor, ref: torch.Tensor, peak: float | None = None) -> fl
         peak = float(ref.max() - ref.min())
     mse = float(((y - ref) ** 2).mean())
     return float("inf") if mse == 0 else 10.0 * math.log10(peak * peak / mse)
+
+
+def naive_model_forward(sd: SD, x: torch.Tensor, num_blocks: int) -> torch.Tensor:
+    """Naive_model.forward, models/naive_multi_model_easy.py:110-147 (scale 4): flows between consecutive frames (:114-116), per frame
+    encode (weight-normed 3x3), block 0 on cat(flow, warp(previous encode output), current) -- frame 0: zero flow and its own features
+    (:123-127) -- then conv-ReLU-conv residual blocks (:137, Block :157-183 without weight norm), decode (weight-normed), PixelShuffle(4)
+    plus the x4 bilinear base of the frame (:140-144).  The model's 5x5 `skip` conv and the blocks' 1x1 `skip` are never applied."""
+    B, N, C, H, W = x.shape
+    if N > 1:
+        lqs_1 = x[:, :-1].reshape(-1, C, H, W)
+        lqs_2 = x[:, 1:].reshape(-1, C, H, W)
+        flows_forward = spynet_forward(sd, lqs_2, lqs_1, "flownet.").view(B, N - 1, 2, H, W)
+    kenc = sd["encode.weight_v"].shape[-1]
+    kdec = sd["decode.weight_v"].shape[-1]
+    outs, pre = [], None
+    for i in range(N):
+        xi = x[:, i]
+        x_ = _wn_conv(sd, "encode.", xi, kenc // 2)
+        for b in range(num_blocks):
+            if b == 0:
+                if i == 0:
+                    x_warp, flow, pre = x_, torch.zeros(B, 2, H, W, dtype=x.dtype), x_
+                else:
+                    x_pre, pre = pre, x_
+                    flow = flows_forward[:, i - 1]
+                    x_warp = flow_warp(x_pre, flow.permute(0, 2, 3, 1))
+                x_c = torch.cat((flow, x_warp, x_), dim=1)
+            else:
+                x_c = x_
+            w0, w2 = sd[f"body.{b}.body.0.weight"], sd[f"body.{b}.body.2.weight"]
+            t = F.relu(F.conv2d(x_c, w0, sd[f"body.{b}.body.0.bias"], padding=w0.shape[-1] // 2))
+            x_ = F.conv2d(t, w2, sd[f"body.{b}.body.2.bias"], padding=w2.shape[-1] // 2) + x_
+        base = F.interpolate(xi, scale_factor=4, mode="bilinear", align_corners=False)
+        outs.append(F.pixel_shuffle(_wn_conv(sd, "decode.", x_, kdec // 2), 4) + base)
+    return torch.stack(outs, dim=1)

@@ -77,3 +77,26 @@ def modules():
     ns.wdsr_b, ns.ops, ns.spynet_arch, ns.export_onnx = wdsr_b, ops, sa, export_onnx
     ns.basicvsr_origin, ns.basicvsr_fork = origin, fork
     return ns
+
+
+def naive_model():
+    """models/naive_multi_model_easy.Naive_model.  The module imports the whole training stack at its top (tensorboard, torchvision,
+    skimage, mmedit's metrics, ...): everything that is missing is replaced by an empty stub module -- none of it is touched by the class."""
+    install()
+    import importlib
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return object
+
+    for n in list(sys.modules):
+        if n.startswith("mmedit.core"):
+            sys.modules[n].psnr = sys.modules[n].ssim = object
+    for _ in range(40):
+        try:
+            return importlib.import_module("models.naive_multi_model_easy").Naive_model
+        except ModuleNotFoundError as e:
+            sys.modules[e.name] = _Any(e.name)
+    raise RuntimeError("could not import models.naive_multi_model_easy")

@@ -170,6 +170,36 @@ def test_spynet_bf16_in_db_at_cfg4_size(sr):
     assert port.psnr_db(f16[..., ::s, ::s], ref) >= BF16_PSNR
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_naive_model_golden(sr, precision, tmp_path):
+    """Naive_model (models/naive_multi_model_easy.py:110-147): SPyNet flows, warp of the previous frame's encoded features into the first
+    block's input window, conv-ReLU-conv residual blocks (kernel sizes 3, 3, 5), 5x5 decode + PixelShuffle(4) + bilinear base -- against the
+    vectors the unmodified reference produced (oracle/make_golden_r3.py)."""
+    from oracle import port
+    meta, arrs, sd, x = golden_case("naive_model")
+    f = tmp_path / "naive_index.txt"
+    f.write_text(repr((list(range(len(meta["blocks"]))), meta["blocks"])) + "\n")
+    m = sr.Naive_model(meta["scale"], str(f)).eval()
+    m.load_state_dict(_t(sd), strict=True)
+    m = m.cuda().set_precision(precision)
+    with torch.no_grad():
+        y = m(torch.from_numpy(x).cuda()).cpu()
+    assert tuple(y.shape) == (1, 3, 3, 144, 208)
+    s = meta["stride"]
+    ref_s, ref_c = torch.from_numpy(arrs["y_strided"]), torch.from_numpy(arrs["y_corner"])
+    if precision == "fp32":
+        assert float((y[..., ::s, ::s] - ref_s).abs().max()) <= FP32_TOL * max(1.0, float(ref_s.abs().max()))
+        assert float((y[..., :16, :16] - ref_c).abs().max()) <= FP32_TOL * max(1.0, float(ref_s.abs().max()))
+    else:
+        assert port.psnr_db(y[..., ::s, ::s], ref_s, peak=float(ref_s.max() - ref_s.min())) >= BF16_PSNR
+    # frame 0 alone takes the zero-flow / own-features branch; a width the warp kernel's window form does not serve takes the NCHW kernel
+    with torch.no_grad():
+        y0 = m(torch.from_numpy(x[:, :1]).cuda()).cpu()
+    assert torch.equal(y0[:, 0], y[:, 0])
+    with pytest.raises(RuntimeError):
+        sr.Naive_model(2, str(f)).eval().cuda()(torch.from_numpy(x).cuda())     # x4 base on a x2 model: the reference's shape error
+
+
 # ------------------------------------------------------------------------------------------------ row-streaming block
 @pytest.mark.parametrize("shape", [(1, 24, 16, 32), (2, 24, 37, 45), (3, 24, 96, 96), (1, 24, 5, 300), (2, 24, 1, 1), (1, 24, 131, 7)])
 @pytest.mark.parametrize("widths", [(24, 144, 20), (24, 144, 24), (20, 100, 13), (9, 91, 7)])

@@ -21,7 +21,7 @@ def _t(sd):
     return {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
 
 
-@pytest.mark.parametrize("cin,cout,k", [(8, 32, 7), (32, 64, 7), (16, 2, 7), (67, 64, 3), (64, 64, 3), (128, 64, 1), (64, 256, 3), (64, 3, 3), (5, 9, 3)])
+@pytest.mark.parametrize("cin,cout,k", [(8, 32, 7), (32, 64, 7), (16, 2, 7), (67, 64, 3), (64, 64, 3), (128, 64, 1), (64, 256, 3), (64, 3, 3), (5, 9, 3), (16, 48, 5), (34, 16, 5)])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_conv_vs_torch(V, cin, cout, k, precision):
     g = torch.Generator().manual_seed(cin * 100 + cout + k)

@@ -74,7 +74,7 @@ def test_abi_error_codes_conv_and_split_without_device(sr):
     h = ctypes.c_void_p()
     z = np.zeros(4096, np.float32)
     p = z.ctypes.data_as(ctypes.c_void_p)
-    assert L.b200sr_conv_create(8, 8, 5, p, p, ctypes.byref(h)) == -4 and b"k in" in L.b200sr_last_error()
+    assert L.b200sr_conv_create(8, 8, 9, p, p, ctypes.byref(h)) == -4 and b"k in" in L.b200sr_last_error()
     assert L.b200sr_conv_create(8, 8, 3, None, p, ctypes.byref(h)) == -1
     assert L.b200sr_split_create(12, p, p, p, p, p, p, p, p, ctypes.byref(h)) == -4 and b"channels=12" in L.b200sr_last_error()
     assert L.b200sr_split_create(24, p, p, p, p, p, p, p, None, ctypes.byref(h)) == -1
@@ -249,3 +249,23 @@ def test_fork_nas_model_state_dict_and_seeded_construction(sr):
     assert m.get_block_status() == [0, 1, 2] and all(len(t) == 3 and t[2] in (3, 5, 7) for t in m.get_width_from_block_idx([0, 1, 2]))
     with pytest.raises(RuntimeError):
         m.eval()(torch.rand(1, 3, 8, 8))            # CPU tensor: no fallback
+
+
+def test_naive_model_state_dict_and_seeded_construction(sr, tmp_path):
+    """Naive_model (models/naive_multi_model_easy.py:33-108): same keys in the same order as the reference's state_dict (flownet, the
+    never-used block / model `skip` convs included), `decode` inherits the last block's kernel size, and a constructor that consumes the RNG
+    exactly like the reference's (weight sum under torch.manual_seed(0) recorded by oracle/make_golden_r3.py)."""
+    from conftest import load_golden
+    meta, _ = load_golden("naive_model")
+    f = tmp_path / "naive_index.txt"
+    f.write_text(repr((list(range(len(meta["blocks"]))), meta["blocks"])) + "\n")
+    torch.manual_seed(0)
+    m = sr.Naive_model(meta["scale"], str(f))
+    sd = m.state_dict()
+    assert list(sd.keys()) == meta["keys"]
+    assert {k: list(v.shape) for k, v in sd.items()} == meta["shapes"]
+    assert tuple(sd["decode.weight_v"].shape) == (48, 16, 5, 5) and tuple(sd["body.0.body.0.weight"].shape) == (16, 34, 3, 3)
+    assert abs(float(sum(v.double().sum() for v in sd.values())) - meta["seed0_weights_sum"]) < 1e-9
+    with pytest.raises(RuntimeError):
+        m.eval()(torch.rand(1, 2, 3, 40, 40))       # CPU tensor: no fallback
+

@@ -106,3 +106,23 @@ def test_basicvsr_ports():
     assert torch.equal(fk(clip, 70, 120), port.basicvsr_fork_forward(sd, clip, 70, 120))
     with pytest.raises(RuntimeError):
         R.basicvsr_fork.BasicVSR(num_feat=8, num_block=1).eval()(clip, 70, 120)     # broken as committed for num_feat != 3
+
+
+@torch.no_grad()
+def test_naive_model_port(tmp_path):
+    """oracle.port.naive_model_forward == the live reference Naive_model (harness shims: stub modules for the training stack its file imports,
+    Tensor.to('cuda') as a no-op on this CPU-only box -- the reference hard-codes it at models/naive_multi_model_easy.py:127)."""
+    Naive = ref_import.naive_model()
+    blocks = [[8, 0, 3], [8, 0, 5]]
+    f = tmp_path / "naive_index.txt"
+    f.write_text(repr(([0, 1], blocks)) + "\n")
+    real_to = torch.Tensor.to
+    torch.Tensor.to = lambda self, *a, **k: self if (a and a[0] == "cuda") else real_to(self, *a, **k)
+    try:
+        m = Naive(4, str(f)).eval()
+        sd = _load_synth(m, 45)
+        clip = torch.from_numpy(synth.synth_input((2, 3, 3, 64, 64), 46))
+        assert torch.equal(m(clip), port.naive_model_forward(sd, clip, len(blocks)))
+    finally:
+        torch.Tensor.to = real_to
+
