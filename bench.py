@@ -352,8 +352,9 @@ def run_b200(args, rank, local_rank, world):
     # is max(FLOP / peak, bytes / HBM) and `roof_frac` = T_roof / T_measured.
     t_tensor = lr_px * FLOP_PER_LR_PX_BLOCK / (peaks["bf16_tflops"] * 1e12)
     t_hbm = lr_px * BYTES_PER_LR_PX_BLOCK / (peaks["hbm_gbs"] * 1e9)
-    roofline = {"kernel": f"fused residual block ({os.environ.get('B200SR_BLOCK_IMPL', 'tc5')}: "
-                          f"{'wdsr_block_rs_kernel' if os.environ.get('B200SR_BLOCK_IMPL') == 'rs' else 'wdsr_block_tc5p_kernel'}, tcgen05)",
+    impl = os.environ.get("B200SR_BLOCK_IMPL", "tc5")
+    roofline = {"kernel": f"fused residual block ({impl}: "
+                          f"{ {'rs': 'wdsr_block_rs_kernel', 'rh': 'wdsr_block_rh_kernel'}.get(impl, 'wdsr_block_tc5p_kernel') }, tcgen05)",
                 "bound": "tensor", "achieved": ach_tflops,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tflops / peaks["bf16_tflops"],
                 "peak_sustained": peaks["bf16_tflops_sustained"], "frac_sustained": ach_tflops / peaks["bf16_tflops_sustained"],
