@@ -179,6 +179,9 @@ B200SR_API int b200sr_flow_warp_nhwc(const void *x_dev, const float *flow_nchw_d
  * directly inside the trunk's input (torch.cat([x_i, feat_prop], 1), models/basicvsr_arch_origin.py:69,81) -- no copy. */
 B200SR_API int b200sr_flow_warp_nhwc_into(const void *x_dev, const float *flow_nchw_dev, void *y_dev, int y_cstride, int y_coff, int n, int c,
                                           int h, int w, int padding_mode, int dtype, void *stream);
+/* ... and x read from channels [x_coff, x_coff + c) of a wider tensor (n,h,w,x_cstride) as well */
+B200SR_API int b200sr_flow_warp_nhwc_windows(const void *x_dev, int x_cstride, int x_coff, const float *flow_nchw_dev, void *y_dev, int y_cstride,
+                                             int y_coff, int n, int c, int h, int w, int padding_mode, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Video path building blocks (SPyNet + BasicVSR).  The Python mirror (mobilesuperresolution_b200/video.py)
@@ -222,6 +225,12 @@ B200SR_API int b200sr_conv_set_max_ctas(b200sr_conv_t *conv, int max_ctas);
  * on `stream`, no synchronisation.  Fails (B200SR_E_UNSUPPORTED) if a conv is not served by the tcgen05 kernel. */
 B200SR_API int b200sr_vsr_trunk_forward(const b200sr_conv_t *first, const b200sr_conv_t *const *blocks, int num_block, const void *buf_dev,
                                         int buf_cstride, void *t_dev, void *o_dev, void *out_dev, int n, int h, int w, void *stream);
+/* the same with the NHWC features written into channels [out_coff, out_coff + 64) of a wider tensor (n,h,w,out_cstride): the backward and
+ * forward trunks of a frame fill the two halves of ONE tensor, `torch.cat([out_l[i], feat_prop], dim=1)` (models/basicvsr_arch_origin.py:84)
+ * without the copy */
+B200SR_API int b200sr_vsr_trunk_forward_into(const b200sr_conv_t *first, const b200sr_conv_t *const *blocks, int num_block, const void *buf_dev,
+                                             int buf_cstride, void *t_dev, void *o_dev, void *out_dev, int out_cstride, int out_coff, int n, int h,
+                                             int w, void *stream);
 
 /* conv_last + base of BasicVSR_origin's reconstruction in ONE kernel (models/basicvsr_arch_origin.py:90-92):
  *   y[n,c,Y,X] = conv3x3(x)[n,c,Y,X] + F.interpolate(base, scale_factor=4, mode='bilinear', align_corners=False)[n,c,Y,X]

@@ -58,6 +58,9 @@ SYMBOLS = {
     "b200sr_nas_forward": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                    c_size_t, c_void_p]),
     "b200sr_flow_warp_nhwc_into": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sr_flow_warp_nhwc_windows": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200sr_vsr_trunk_forward_into": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                              c_void_p]),
     "b200sr_conv_create": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, POINTER(c_void_p)]),
     "b200sr_conv_destroy": (None, [c_void_p]),
     "b200sr_conv_forward_layout": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,

@@ -558,6 +558,18 @@ int b200sr_flow_warp_nhwc_into(const void *x, const float *flow, void *y, int y_
     return 0;
 }
 
+int b200sr_flow_warp_nhwc_windows(const void *x, int x_cs, int x_co, const float *flow, void *y, int y_cs, int y_co, int n, int c, int h, int w,
+                                  int padding_mode, int dtype, void *stream) {
+    if (!x || !flow || !y) return fail(B200SR_E_INVAL, "flow_warp_nhwc_windows: null tensor");
+    if (padding_mode != B200SR_PAD_ZEROS && padding_mode != B200SR_PAD_BORDER)
+        return fail(B200SR_E_UNSUPPORTED, "flow_warp_nhwc_windows: padding_mode %d", padding_mode);
+    if (y_cs < c || y_co < 0 || y_co + c > y_cs || x_cs < c || x_co < 0 || x_co + c > x_cs)
+        return fail(B200SR_E_INVAL, "flow_warp_nhwc_windows: channel window outside tensor");
+    cudaError_t e = launch_flow_warp_nhwc(x, flow, y, n, c, h, w, padding_mode == B200SR_PAD_BORDER, dtype, (cudaStream_t)stream, y_cs, y_co, x_cs, x_co);
+    if (e != cudaSuccess) return cuda_fail(e, "flow_warp_nhwc_windows (c, strides, offsets multiples of 8 (bf16) / 4 (f32); c*esize/16 in {1,2,3,4,6,8,16})");
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Split_Block (the fork's searchable block body)
 // ---------------------------------------------------------------------------------------------------------
@@ -828,15 +840,21 @@ int b200sr_vsr_conv_last_base(const b200sr_conv_t *c, const void *x, int x_layou
 
 int b200sr_vsr_trunk_forward(const b200sr_conv_t *first, const b200sr_conv_t *const *blocks, int num_block, const void *buf, int buf_cs,
                              void *t, void *o, void *out, int n, int h, int w, void *stream) {
+    return b200sr_vsr_trunk_forward_into(first, blocks, num_block, buf, buf_cs, t, o, out, 64, 0, n, h, w, stream);
+}
+
+int b200sr_vsr_trunk_forward_into(const b200sr_conv_t *first, const b200sr_conv_t *const *blocks, int num_block, const void *buf, int buf_cs,
+                                  void *t, void *o, void *out, int out_cs, int out_co, int n, int h, int w, void *stream) {
     if (!first || !blocks || num_block < 1 || !buf || !t || !o || !out) return fail(B200SR_E_INVAL, "vsr_trunk_forward: bad argument");
+    if (out_cs < 64 || out_co < 0 || out_co + 64 > out_cs || out_cs % 8 || out_co % 8) return fail(B200SR_E_INVAL, "vsr_trunk_forward: output channel window");
     const int P = B200SR_TRUNK_PLANAR8, N_ = B200SR_TRUNK_NHWC, bf = B200SR_BF16;
     int rc = b200sr_conv_forward_layout(first, buf, N_, buf_cs, 0, t, P, 64, 0, nullptr, 0, 0, n, h, w, B200SR_ACT_LRELU01, 1, bf, bf, bf, stream);
     for (int k = 0; k < num_block && !rc; ++k) {
         rc = b200sr_conv_forward_layout(blocks[2 * k], t, P, 64, 0, o, P, 64, 0, nullptr, 0, 0, n, h, w, B200SR_ACT_RELU, 1, bf, bf, bf, stream);
         if (rc) break;
         const bool last = k + 1 == num_block;   // conv2 adds its residual in place (y = t + conv(o)); the last one writes the NHWC features
-        rc = b200sr_conv_forward_layout(blocks[2 * k + 1], o, P, 64, 0, last ? out : t, last ? N_ : P, 64, 0, t, 64, 0, n, h, w,
-                                        B200SR_ACT_NONE, 1, bf, bf, bf, stream);
+        rc = b200sr_conv_forward_layout(blocks[2 * k + 1], o, P, 64, 0, last ? out : t, last ? N_ : P, last ? out_cs : 64, last ? out_co : 0, t, 64, 0,
+                                        n, h, w, B200SR_ACT_NONE, 1, bf, bf, bf, stream);
     }
     return rc;
 }

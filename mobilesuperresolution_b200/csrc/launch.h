@@ -55,7 +55,7 @@ cudaError_t launch_tail_bf16(int CP, int S, int x_dtype, int y_dtype, const void
 cudaError_t launch_flow_warp_nchw(const float *x, const float *flow, long long fs_n, long long fs_h, long long fs_w,
                                   long long fs_c, float *y, int n, int c, int h, int w, int border, cudaStream_t st);
 cudaError_t launch_flow_warp_nhwc(const void *x, const float *flow_nchw, void *y, int n, int c, int h, int w, int border,
-                                  int dtype, cudaStream_t st, int y_cs = 0, int y_co = 0);   // y_cs > 0: y is a channel window
+                                  int dtype, cudaStream_t st, int y_cs = 0, int y_co = 0, int x_cs = 0, int x_co = 0);   // y_cs > 0: y is a channel window
 
 struct ConvArgs;
 // generic NHWC convolution (conv.cuh); nt = output-channel n-tiles per CTA of the bf16 kernel (1,2,4,8)

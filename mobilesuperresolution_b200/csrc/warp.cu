@@ -119,7 +119,7 @@ cudaError_t launch_flow_warp_nchw(const float *x, const float *flow, long long f
 template <typename T, int Q>
 __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const T *__restrict__ x, const float *__restrict__ flow,
                                                              T *__restrict__ y, int N, int C, int H, int W, int border,
-                                                             int tiles_x, int tiles_y, int y_cs, int y_co) {
+                                                             int tiles_x, int tiles_y, int y_cs, int y_co, int x_cs, int x_co) {
     constexpr int VEC = 16 / sizeof(T);
     constexpr bool kPow2 = (Q & (Q - 1)) == 0 && Q <= 32;
     constexpr int PPS = kPow2 ? 32 / Q : 1;            // pixels per step
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const T *__restrict
         const int cx0 = min(max(b.x0, 0), W - 1), cx1 = min(max(b.x0 + 1, 0), W - 1);
         const int cy0 = min(max(b.y0, 0), H - 1), cy1 = min(max(b.y0 + 1, 0), H - 1);
         const int o00 = cy0 * W + cx0, o01 = cy0 * W + cx1, o10 = cy1 * W + cx0, o11 = cy1 * W + cx1;   // < 2^31: per-image pixel index
-        const T *xi = x + (long long)n * H * W * C;
+        const T *xi = x + (long long)n * H * W * x_cs + x_co;   // x may be a channel window of a wider tensor too
         T *yrow = y + (((long long)n * H + yh) * W + (long long)tx * WTX) * y_cs + y_co;   // y may be a channel window of a wider tensor
         const int npx = min(WTX, W - tx * WTX);
 #pragma unroll 2
@@ -159,10 +159,10 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const T *__restrict
                 const int q = kPow2 ? (lane % LPP) : lane + 32 * sub;
                 if (!kPow2 && q >= Q) break;
                 const T *base = xi + q * VEC;
-                const uint4 v00 = __ldg(reinterpret_cast<const uint4 *>(base + (long long)p00 * C));
-                const uint4 v01 = __ldg(reinterpret_cast<const uint4 *>(base + (long long)p01 * C));
-                const uint4 v10 = __ldg(reinterpret_cast<const uint4 *>(base + (long long)p10 * C));
-                const uint4 v11 = __ldg(reinterpret_cast<const uint4 *>(base + (long long)p11 * C));
+                const uint4 v00 = __ldg(reinterpret_cast<const uint4 *>(base + (long long)p00 * x_cs));
+                const uint4 v01 = __ldg(reinterpret_cast<const uint4 *>(base + (long long)p01 * x_cs));
+                const uint4 v10 = __ldg(reinterpret_cast<const uint4 *>(base + (long long)p10 * x_cs));
+                const uint4 v11 = __ldg(reinterpret_cast<const uint4 *>(base + (long long)p11 * x_cs));
                 float acc[VEC];
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
@@ -203,38 +203,39 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const T *__restrict
 
 template <typename T, int Q>
 static cudaError_t warp_nhwc_t(const void *x, const float *flow, void *y, int n, int c, int h, int w, int border, int y_cs, int y_co,
-                               cudaStream_t st) {
+                               int x_cs, int x_co, cudaStream_t st) {
     const int tx = ceil_div(w, WTX), ty = ceil_div(h, WTY);
     long long blocks = (long long)n * tx * ty;
     const long long cap = (long long)sm_count() * 32;
     if (blocks > cap) blocks = cap;
-    flow_warp_nhwc_kernel<T, Q><<<(unsigned)blocks, 256, 0, st>>>((const T *)x, flow, (T *)y, n, c, h, w, border, tx, ty, y_cs, y_co);
+    flow_warp_nhwc_kernel<T, Q><<<(unsigned)blocks, 256, 0, st>>>((const T *)x, flow, (T *)y, n, c, h, w, border, tx, ty, y_cs, y_co, x_cs, x_co);
     return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t warp_nhwc_q(int Q, const void *x, const float *flow, void *y, int n, int c, int h, int w, int border, int y_cs, int y_co,
-                               cudaStream_t st) {
+                               int x_cs, int x_co, cudaStream_t st) {
     switch (Q) {
-        case 1: return warp_nhwc_t<T, 1>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
-        case 2: return warp_nhwc_t<T, 2>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
-        case 3: return warp_nhwc_t<T, 3>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
-        case 4: return warp_nhwc_t<T, 4>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
-        case 6: return warp_nhwc_t<T, 6>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
-        case 8: return warp_nhwc_t<T, 8>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
-        case 16: return warp_nhwc_t<T, 16>(x, flow, y, n, c, h, w, border, y_cs, y_co, st);
+        case 1: return warp_nhwc_t<T, 1>(x, flow, y, n, c, h, w, border, y_cs, y_co, x_cs, x_co, st);
+        case 2: return warp_nhwc_t<T, 2>(x, flow, y, n, c, h, w, border, y_cs, y_co, x_cs, x_co, st);
+        case 3: return warp_nhwc_t<T, 3>(x, flow, y, n, c, h, w, border, y_cs, y_co, x_cs, x_co, st);
+        case 4: return warp_nhwc_t<T, 4>(x, flow, y, n, c, h, w, border, y_cs, y_co, x_cs, x_co, st);
+        case 6: return warp_nhwc_t<T, 6>(x, flow, y, n, c, h, w, border, y_cs, y_co, x_cs, x_co, st);
+        case 8: return warp_nhwc_t<T, 8>(x, flow, y, n, c, h, w, border, y_cs, y_co, x_cs, x_co, st);
+        case 16: return warp_nhwc_t<T, 16>(x, flow, y, n, c, h, w, border, y_cs, y_co, x_cs, x_co, st);
     }
     return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_flow_warp_nhwc(const void *x, const float *flow_nchw, void *y, int n, int c, int h, int w, int border,
-                                  int dtype, cudaStream_t st, int y_cs, int y_co) {
+                                  int dtype, cudaStream_t st, int y_cs, int y_co, int x_cs, int x_co) {
     if ((long long)n * h * w == 0) return cudaSuccess;
     if (y_cs <= 0) y_cs = c, y_co = 0;
-    const int vec = dtype == kF32 ? 4 : 8;     // the window must keep the 16-byte stores aligned
-    if (c % vec || y_cs % vec || y_co % vec || y_co + c > y_cs) return cudaErrorInvalidValue;
-    if (dtype == kF32) return warp_nhwc_q<float>(c / 4, x, flow_nchw, y, n, c, h, w, border, y_cs, y_co, st);
-    return warp_nhwc_q<bf16>(c / 8, x, flow_nchw, y, n, c, h, w, border, y_cs, y_co, st);
+    if (x_cs <= 0) x_cs = c, x_co = 0;
+    const int vec = dtype == kF32 ? 4 : 8;     // the windows must keep the 16-byte loads / stores aligned
+    if (c % vec || y_cs % vec || y_co % vec || y_co + c > y_cs || x_cs % vec || x_co % vec || x_co + c > x_cs) return cudaErrorInvalidValue;
+    if (dtype == kF32) return warp_nhwc_q<float>(c / 4, x, flow_nchw, y, n, c, h, w, border, y_cs, y_co, x_cs, x_co, st);
+    return warp_nhwc_q<bf16>(c / 8, x, flow_nchw, y, n, c, h, w, border, y_cs, y_co, x_cs, x_co, st);
 }
 
 }  // namespace b200sr

@@ -47,20 +47,33 @@ def flow_warp(x: torch.Tensor, flow: torch.Tensor, interp_mode: str = "bilinear"
 
 def flow_warp_nhwc(x: torch.Tensor, flow_nchw: torch.Tensor, padding_mode: str = "zeros", out: Optional[torch.Tensor] = None,
                    out_coff: int = 0) -> torch.Tensor:
-    """Internal-layout warp: ``x`` (n,h,w,c) float32|bfloat16 contiguous, ``flow_nchw`` (n,2,h,w) float32.  ``out``: write into
-    channels [out_coff, out_coff + c) of this wider (n,h,w,C) tensor instead of a new one (a concatenation without the copy)."""
+    """Internal-layout warp: ``x`` (n,h,w,c) float32|bfloat16, contiguous or a channel window ``wide[..., a:a+c]`` of a contiguous
+    (n,h,w,C) tensor; ``flow_nchw`` (n,2,h,w) float32.  ``out``: write into channels [out_coff, out_coff + c) of this wider (n,h,w,C)
+    tensor instead of a new one (a concatenation without the copy)."""
     _lib.require_cuda_tensor(x, "x")
-    assert x.is_contiguous() and flow_nchw.is_contiguous() and flow_nchw.dtype == torch.float32
+    assert flow_nchw.is_contiguous() and flow_nchw.dtype == torch.float32
     n, h, w, c = x.shape
+    x_cs = x.stride(2) if h * w > 1 else c
+    assert x.stride(3) == 1 and x_cs >= c and (n * h * w <= 1 or x.stride() == (h * w * x_cs, w * x_cs, x_cs, 1)), "x: NHWC or a channel window of NHWC"
     assert tuple(flow_nchw.shape) == (n, 2, h, w)
-    y = torch.empty_like(x) if out is None else out
+    y = torch.empty((n, h, w, c), dtype=x.dtype, device=x.device) if out is None else out
     assert y.is_contiguous() and y.dtype == x.dtype and tuple(y.shape[:3]) == (n, h, w)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().b200sr_flow_warp_nhwc_into(
-            _ptr(x), _ptr(flow_nchw), _ptr(y), y.shape[-1], out_coff, n, c, h, w,
+        _lib.check(_lib.lib().b200sr_flow_warp_nhwc_windows(
+            _ptr(x), x_cs, 0, _ptr(flow_nchw), _ptr(y), y.shape[-1], out_coff, n, c, h, w,
             _lib.PAD_BORDER if padding_mode == "border" else _lib.PAD_ZEROS, _lib.dtype_code(x.dtype),
             _lib.current_stream_ptr(x.device)))
     return y
+
+
+def _cat_feats(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """``torch.cat([a, b], dim=-1)`` -- for free when the two are the adjacent channel windows of one tensor (propagate lays them out so)."""
+    base = a._base
+    if (base is not None and base is b._base and base.is_contiguous() and base.dim() == 4 and base.shape[-1] == a.shape[-1] + b.shape[-1]
+            and a.stride() == base.stride() == b.stride() and a.storage_offset() == base.storage_offset()
+            and b.storage_offset() == base.storage_offset() + a.shape[-1]):
+        return base
+    return torch.cat([a, b], dim=-1)
 
 
 # ======================================================================================================
@@ -288,7 +301,8 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
         flows_forward = flows[m:].view(b, n - 1, 2, h, w)
         return flows_forward, flows_backward
 
-    def _trunk(self, convs, name: str, buf: torch.Tensor, num_block: int) -> torch.Tensor:
+    def _trunk(self, convs, name: str, buf: torch.Tensor, num_block: int, out: Optional[torch.Tensor] = None, out_coff: int = 0) -> torch.Tensor:
+        """``out``: a wider (n,h,w,C) tensor whose channels [out_coff, out_coff + num_feat) receive the features; returns that window."""
         first = convs[f"{name}.main.0"]
         # bf16 on the tcgen05 kernel: the trunk's private 64-channel tensors live in the planar-8 layout (TMA box rows of 512
         # contiguous bytes instead of one request per pixel and chunk); the last conv writes the NHWC features the callers read
@@ -299,22 +313,27 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
             for k in range(num_block):
                 o = convs[f"{name}.main.2.{k}.conv1"](t, self.precision, ACT_RELU)
                 t = convs[f"{name}.main.2.{k}.conv2"](o, self.precision, ACT_NONE, residual=t)
-            return t
+            if out is None:
+                return t
+            win = out[..., out_coff:out_coff + t.shape[-1]]
+            win.copy_(t)
+            return win
         # 2 * num_block + 1 dependent launches of a few microseconds each: the host side is ONE ABI call (b200sr_vsr_trunk_forward
         # sequences them in C), two planar-8 buffers (conv2 adds its residual in place: y = t + conv(o))
         n, h, w, cs = buf.shape
         dev = buf.device
         t = torch.empty((n, 8, h, w, 8), dtype=torch.bfloat16, device=dev)
         o = torch.empty_like(t)
-        out = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=dev)
+        if out is None:
+            out, out_coff = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=dev), 0
         hkey = "__handles__:" + name   # lives and dies with this set of conv handles
         if hkey not in convs:
             hs = [convs[f"{name}.main.2.{k}.{c}"]._h for k in range(num_block) for c in ("conv1", "conv2")]
             convs[hkey] = (ctypes.c_void_p * len(hs))(*[h.value for h in hs])
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().b200sr_vsr_trunk_forward(first._h, convs[hkey], num_block, buf.data_ptr(), cs, t.data_ptr(), o.data_ptr(),
-                                                           out.data_ptr(), n, h, w, _lib.current_stream_ptr(dev)))
-        return out
+            _lib.check(_lib.lib().b200sr_vsr_trunk_forward_into(first._h, convs[hkey], num_block, buf.data_ptr(), cs, t.data_ptr(), o.data_ptr(),
+                                                                out.data_ptr(), out.shape[-1], out_coff, n, h, w, _lib.current_stream_ptr(dev)))
+        return out if out.shape[-1] == 64 else out[..., out_coff:out_coff + 64]
 
     def propagate(self, x: torch.Tensor, flows_forward: torch.Tensor, flows_backward: torch.Tensor):
         """The two recurrent loops (models/basicvsr_arch_origin.py:61-82) -> per-frame NHWC features (backward, forward).
@@ -334,12 +353,18 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
         feat_first = self._feat_first()
         xco = nf if feat_first else 0
 
-        def run(trunk: str, order, flows, flow_index):
+        # per frame ONE tensor [backward features | forward features]: the two trunks write its halves in place, so the reconstruction's
+        # torch.cat([out_l[i], feat_prop], dim=1) (:84) is free (_cat_feats)
+        fused = [torch.empty((b, h, w, 2 * nf), dtype=adt, device=dev) for _ in range(n)]
+
+        def run(trunk: str, order, flows, flow_index, coff):
             feats: List[Optional[torch.Tensor]] = [None] * n
             feat = None
             st = _lib.current_stream_ptr(dev)   # the stream this direction was forked onto
+            # ONE trunk input per direction, zero-filled once: every frame rewrites its x_i channels and (from the second step on) its feature
+            # channels; the first step needs zero features, the pad channels stay zero
+            buf = torch.zeros((b, h, w, cs), dtype=adt, device=dev)
             for step, i in enumerate(order):
-                buf = torch.zeros((b, h, w, cs), dtype=adt, device=dev)
                 xi = x[:, i]
                 with torch.cuda.device(dev):
                     _lib.check(L.b200sr_nchw3_to_nhwc(_ptr(xi), _lib.dtype_code(x.dtype), x.stride(0), _ptr(buf), _lib.dtype_code(adt),
@@ -353,7 +378,7 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
                     else:   # odd feature counts (the fork's BasicVSR only runs for num_feat = 3): the reference-layout NCHW kernel, fp32
                         wv = flow_warp(feat.float().permute(0, 3, 1, 2).contiguous(), fl.permute(0, 2, 3, 1))
                         buf[..., 3:3 + nf] = wv.permute(0, 2, 3, 1).to(adt)
-                feat = self._trunk(convs, trunk, buf, nb)
+                feat = self._trunk(convs, trunk, buf, nb, out=fused[i], out_coff=coff)
                 feats[i] = feat
             return feats
 
@@ -369,12 +394,12 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
             if name.startswith(("backward_trunk.", "forward_trunk.")):
                 c.set_max_ctas(half)
         side.wait_stream(main)
-        back = run("backward_trunk", range(n - 1, -1, -1), flows_backward, lambda i: i)
+        back = run("backward_trunk", range(n - 1, -1, -1), flows_backward, lambda i: i, 0)
         with torch.cuda.stream(side):
-            fwd = run("forward_trunk", range(0, n), flows_forward, lambda i: i - 1)
+            fwd = run("forward_trunk", range(0, n), flows_forward, lambda i: i - 1, nf)
         main.wait_stream(side)
-        for f in fwd:
-            f.record_stream(main)
+        for f in fused:
+            f.record_stream(side)
         return back, fwd
 
     # ---- tail of the fork's BasicVSR and of MotionVectorVSR: lrelu(fusion) -> conv_last = ConvTranspose2d(2nf, 3, 5, stride 4) -> bilinear
@@ -392,7 +417,7 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
         L, st = _lib.lib(), _lib.current_stream_ptr(dev)
         out = torch.empty((b, n, 3, height, weight), dtype=torch.float32, device=dev)
         for i in range(n):
-            o = convs["fusion"](torch.cat([back[i], fwd[i]], dim=-1), p, ACT_LRELU)
+            o = convs["fusion"](_cat_feats(back[i], fwd[i]), p, ACT_LRELU)
             o = torch.nn.functional.pad(o, (0, 0, 0, 1, 0, 1))              # one zero row / column: the fifth tap's outputs
             t = tail(o, p, ACT_NONE, out_dtype=torch.float32)               # (b, h+1, w+1, 3*16)
             xi = x[:, i]
@@ -441,8 +466,7 @@ class BasicVSR_origin(_VsrBase):
         x = x.contiguous()
         out = torch.empty((b, n, 3, height, weight), dtype=torch.float32, device=dev)
         for i in range(n):
-            o = torch.cat([back[i], fwd[i]], dim=-1)
-            o = convs["fusion"](o, p, ACT_LRELU)
+            o = convs["fusion"](_cat_feats(back[i], fwd[i]), p, ACT_LRELU)
             o = convs["upconv1"](o, p, ACT_LRELU, shuffle=2)          # lrelu(pixel_shuffle(conv)) == shuffle(lrelu(conv))
             hr_planar = p != "fp32" and convs["upconv2"].tcgen05_ok() and convs["conv_hr"].tcgen05_ok() and convs["conv_hr"].cin == 64
             # conv_last + bilinear base in one tcgen05 launch (fp32 accumulators straight to the fp32 NCHW frame, no bf16 round trip)
