@@ -317,12 +317,13 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
     }
     {
         // default: the tcgen05 kernel wherever a block is eligible (trunk padded to 24, M2 <= 24), the mma.sync kernel
-        // elsewhere.  B200SR_BLOCK_IMPL = mma | tc5seq | tc5 | rs | rh is a developer switch (A/B timing, reference form):
+        // elsewhere.  B200SR_BLOCK_IMPL = mma | tc5seq | tc5 | tc5q | rs | rh is a developer switch (A/B timing, reference form):
         // tc5 = the tile form (wdsr_tc5p.cuh, the default); rs = the row-streaming form (wdsr_rs.cuh; cfg2 28.4 vs 26.9 us, 1080p 74-82 vs
         // 80 us per launch); rh = row-streaming with the reduce 1x1 on mma.sync out of registers (wdsr_rh.cuh; 32.5 / 94 us: bound by the
-        // legacy HMMA rate, profiles/r02_block_rh.md).  All three are parity-green against the oracle and each other.
+        // legacy HMMA rate, profiles/r02_block_rh.md); tc5q = the tile form with decoupled expand staging (wdsr_tc5q.cuh; 28.7 / 90 us).
+        // All of them are parity-green against the oracle and each other.
         const char *e = getenv("B200SR_BLOCK_IMPL");
-        p->block_impl = !e ? 2 : !strcmp(e, "mma") ? 0 : !strcmp(e, "tc5seq") ? 1 : !strcmp(e, "rs") ? 3 : !strcmp(e, "rh") ? 4 : 2;
+        p->block_impl = !e ? 2 : !strcmp(e, "mma") ? 0 : !strcmp(e, "tc5seq") ? 1 : !strcmp(e, "rs") ? 3 : !strcmp(e, "rh") ? 4 : !strcmp(e, "tc5q") ? 5 : 2;
     }
     const int NO = p->no;
     {   // tail fp32: Wt[9][CP][NOP4] | Ws[75][NOP4] | bias[NOP4]
@@ -464,7 +465,7 @@ int b200sr_wdsr_block(const b200sr_wdsr_t *p, int i, const void *tin, void *tout
     else if (p->tc5_path() && p->block_impl == 4 && block_rs_eligible(n, h, w))
         CU(launch_block_rh(tin, tout, p->d_blk_rs[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
     else if (p->tc5_path())
-        CU(launch_block_tc5(1, tin, tout, p->d_blk_tc5[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
+        CU(launch_block_tc5(p->block_impl == 5 ? 2 : 1, tin, tout, p->d_blk_tc5[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
     else if (p->block_impl == 1 && p->d_blk_tc5[i] && p->m2[i] > 16)   // sequential tcgen05 reference form (NHWC trunk, all 27 w3 slices; developer switch)
         CU(launch_block_tc5(0, tin, tout, p->d_blk_tc5[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
     else

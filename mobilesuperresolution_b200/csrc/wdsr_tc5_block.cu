@@ -6,6 +6,7 @@
 #include "launch.h"
 #include "wdsr_tc5.cuh"
 #include "wdsr_tc5p.cuh"
+#include "wdsr_tc5q.cuh"
 #include "tma_map.h"
 
 namespace b200sr {
@@ -41,15 +42,20 @@ cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8
         mapp = &c.map;
     }
     const int nc2 = M2 <= 8 ? 1 : M2 <= 16 ? 2 : 3;   // 8-channel chunks of t2 (the image was packed for exactly these, b200sr.cu)
-    auto kern = nc2 == 3 ? wdsr_block_tc5p_kernel<3> : nc2 == 2 ? wdsr_block_tc5p_kernel<2> : wdsr_block_tc5p_kernel<1>;
+    // variant 1: wdsr_tc5p.cuh (expand accumulator re-used in place as the reduce operand); 2: wdsr_tc5q.cuh (decoupled staging halves)
+    const bool q = variant == 2;
+    auto kern = q ? (nc2 == 3 ? wdsr_block_tc5q_kernel<3> : nc2 == 2 ? wdsr_block_tc5q_kernel<2> : wdsr_block_tc5q_kernel<1>)
+                  : (nc2 == 3 ? wdsr_block_tc5p_kernel<3> : nc2 == 2 ? wdsr_block_tc5p_kernel<2> : wdsr_block_tc5p_kernel<1>);
     const size_t smem = tc5v3::smem_bytes(M1P);
-    static thread_local size_t smem_set[64][3] = {};
+    static_assert(tc5v3::CTRL_BYTES == tc5v4::CTRL_BYTES, "the two forms share one shared-memory layout");
+    static thread_local size_t smem_set[64][6] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || smem_set[dev][nc2 - 1] < smem) {
+    const int ki = nc2 - 1 + (q ? 3 : 0);
+    if (dev < 0 || dev >= 64 || smem_set[dev][ki] < smem) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) smem_set[dev][nc2 - 1] = smem;
+        if (dev >= 0 && dev < 64) smem_set[dev][ki] = smem;
     }
     const CUtensorMap &map = *mapp;
     // programmatic stream serialization: this grid may start (and run its prologue) while the previous kernel in the stream

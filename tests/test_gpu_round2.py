@@ -203,7 +203,7 @@ def test_naive_model_golden(sr, precision, tmp_path):
 # ------------------------------------------------------------------------------------------------ row-streaming block
 @pytest.mark.parametrize("shape", [(1, 24, 16, 32), (2, 24, 37, 45), (3, 24, 96, 96), (1, 24, 5, 300), (2, 24, 1, 1), (1, 24, 131, 7)])
 @pytest.mark.parametrize("widths", [(24, 144, 20), (24, 144, 24), (20, 100, 13), (9, 91, 7)])
-@pytest.mark.parametrize("form", ["rs", "rh"])
+@pytest.mark.parametrize("form", ["rs", "rh", "tc5q"])
 def test_row_streaming_block_equals_oracle_and_tile_form(sr, shape, widths, form, monkeypatch):
     """The row-streaming forms of the fused block (csrc/wdsr_rs.cuh: all tcgen05; csrc/wdsr_rh.cuh: reduce 1x1 on mma.sync out of
     registers; B200SR_BLOCK_IMPL=rs|rh) on ragged shapes and pruned widths:
@@ -249,7 +249,7 @@ def test_row_streaming_block_equals_oracle_and_tile_form(sr, shape, widths, form
     assert float((d > 0).float().mean()) < 0.2
 
 
-@pytest.mark.parametrize("form", ["rs", "rh"])
+@pytest.mark.parametrize("form", ["rs", "rh", "tc5q"])
 def test_row_streaming_model_graph_replay_is_deterministic(sr, form, monkeypatch):
     monkeypatch.setenv("B200SR_BLOCK_IMPL", form)
     torch.manual_seed(3)
@@ -268,7 +268,7 @@ def test_row_streaming_model_graph_replay_is_deterministic(sr, form, monkeypatch
 # tested directly: (1) no kernel of the WDSR path writes outside its output / workspace -- every buffer sits between red zones of a
 # canary pattern that must survive; (2) the mbarrier / TMEM pipelines are free of observable races -- the same input gives
 # bit-identical output 12 times in a row while a second stream keeps the SMs and L2 busy with unrelated work.
-@pytest.mark.parametrize("impl", ["tc5", "rs", "rh"])
+@pytest.mark.parametrize("impl", ["tc5", "rs", "rh", "tc5q"])
 @pytest.mark.parametrize("shape,scale", [((2, 3, 37, 45), 4), ((1, 3, 130, 66), 2), ((3, 3, 96, 96), 4)])
 def test_red_zones_survive_and_results_repeat_under_load(sr, impl, shape, scale, monkeypatch):
     from mobilesuperresolution_b200 import _lib
