@@ -323,7 +323,7 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
         // legacy HMMA rate, profiles/r02_block_rh.md); tc5q = the tile form with decoupled expand staging (wdsr_tc5q.cuh; 28.7 / 90 us).
         // All of them are parity-green against the oracle and each other.
         const char *e = getenv("B200SR_BLOCK_IMPL");
-        p->block_impl = !e ? 2 : !strcmp(e, "mma") ? 0 : !strcmp(e, "tc5seq") ? 1 : !strcmp(e, "rs") ? 3 : !strcmp(e, "rh") ? 4 : !strcmp(e, "tc5q") ? 5 : 2;
+        p->block_impl = !e ? 2 : !strcmp(e, "mma") ? 0 : !strcmp(e, "tc5seq") ? 1 : !strcmp(e, "rs") ? 3 : !strcmp(e, "rh") ? 4 : !strcmp(e, "tc5q") ? 5 : !strcmp(e, "chain") ? 6 : 2;
     }
     const int NO = p->no;
     {   // tail fp32: Wt[9][CP][NOP4] | Ws[75][NOP4] | bias[NOP4]
@@ -427,7 +427,7 @@ int b200sr_wdsr_pack_block_image(int c, int m1, int m2, const float *w1, const f
 size_t b200sr_wdsr_workspace_bytes(const b200sr_wdsr_t *p, int n, int h, int w, int precision) {
     if (!p || n <= 0 || h <= 0 || w <= 0) return 0;
     const size_t trunk = round_up((int)(((size_t)n * h * w * p->cp * esize(precision) + 255) / 256), 1) * (size_t)256;
-    return 2 * trunk;
+    return 2 * trunk + 256;   // two ping-pong trunk buffers + the layer counter of the chained block launch (wdsr_tc5c.cuh)
 }
 
 static int check_common(const b200sr_wdsr_t *p, int n, int h, int w, int precision, const char *who) {
@@ -499,11 +499,25 @@ int b200sr_wdsr_forward(const b200sr_wdsr_t *p, const void *x, int x_dtype, void
     if (!x || !y || !ws) return fail(B200SR_E_INVAL, "wdsr_forward: null tensor/workspace");
     const size_t need = b200sr_wdsr_workspace_bytes(p, n, h, w, precision);
     if (ws_bytes < need) return fail(B200SR_E_WORKSPACE, "wdsr_forward: workspace %zu < %zu bytes", ws_bytes, need);
-    uint8_t *a = (uint8_t *)ws, *b = a + need / 2;
+    const size_t trunk = (need - 256) / 2;
+    uint8_t *a = (uint8_t *)ws, *b = a + trunk;
     int launches = 0;
     if ((rc = b200sr_wdsr_head(p, x, x_dtype, a, n, h, w, precision, stream))) return rc;
     ++launches;
-    for (int i = 0; i < p->nb; ++i) {
+    bool chained = false;
+    if (precision == B200SR_BF16 && p->block_impl == 6 && p->tc5_path() && p->nb >= 1 && p->nb <= 32) {
+        // every block in ONE persistent cooperative launch (wdsr_tc5c.cuh) when they all have the same shape
+        bool uniform = true;
+        for (int i = 0; i < p->nb; ++i) uniform = uniform && p->d_blk_tc5[i] && p->m1p[i] == p->m1p[0] && p->m2[i] == p->m2[0];
+        if (uniform) {
+            CU(launch_block_chain_tc5(a, b, p->d_blk_tc5.data(), p->nb, (unsigned *)((uint8_t *)ws + 2 * trunk), p->m1p[0], p->m2[0], n, h, w,
+                                      (cudaStream_t)stream));
+            launches += 2;   // the counter's memset node + the kernel
+            if (p->nb & 1) a = b;
+            chained = true;
+        }
+    }
+    for (int i = 0; i < p->nb && !chained; ++i) {
         if ((rc = b200sr_wdsr_block(p, i, a, b, n, h, w, precision, stream))) return rc;
         ++launches;
         uint8_t *t = a;

@@ -37,6 +37,9 @@ cudaError_t launch_block_bf16(int CP, int M2P, const void *in, void *out, const 
 // tcgen05 form of the fused block (CP == 24, M2 <= 24): variant 0 = sequential reference form, 1 = pipelined
 cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8_t *wimg, int M1P, int M2, int N, int H, int W,
                              cudaStream_t st);
+// every block of a run of same-shaped blocks in one persistent cooperative launch (wdsr_tc5c.cuh); gsync: 4 bytes of device memory
+cudaError_t launch_block_chain_tc5(void *buf_a, void *buf_b, const uint8_t *const *wimgs, int nlayers, unsigned *gsync, int M1P, int M2, int N,
+                                   int H, int W, cudaStream_t st);
 // row-streaming tcgen05 form of the fused block (wdsr_rs.cuh; planar-8 trunk, CP == 24, M2 <= 24, M1P <= 144)
 bool block_rs_eligible(int N, int H, int W);
 cudaError_t launch_block_rs(const void *in, void *out, const uint8_t *wimg, int M1P, int M2, int N, int H, int W, cudaStream_t st);

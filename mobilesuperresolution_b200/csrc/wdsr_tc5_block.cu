@@ -7,6 +7,7 @@
 #include "wdsr_tc5.cuh"
 #include "wdsr_tc5p.cuh"
 #include "wdsr_tc5q.cuh"
+#include "wdsr_tc5c.cuh"
 #include "tma_map.h"
 
 namespace b200sr {
@@ -67,6 +68,57 @@ cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, map, (const bf16 *)in, (bf16 *)out, wimg, M1P, N, H, W, tx, ty, ntiles);
+}
+
+// All `nlayers` blocks (same M1P / M2) in ONE persistent cooperative launch (wdsr_tc5c.cuh): layer l reads buf[l & 1], writes buf[(l + 1) & 1].
+cudaError_t launch_block_chain_tc5(void *buf_a, void *buf_b, const uint8_t *const *wimgs, int nlayers, unsigned *gsync, int M1P, int M2, int N,
+                                   int H, int W, cudaStream_t st) {
+    using namespace tc5cfg;
+    if (nlayers < 1 || nlayers > tc5v5::MAX_LAYERS) return cudaErrorInvalidValue;
+    const int tx = ceil_div(W, TW), ty = ceil_div(H, TH);
+    const int ntiles = tx * ty * N;
+    int ctas = sm_count();
+    if (ctas > ntiles) ctas = ntiles;
+    struct MapKey { const void *p; int n, h, w; CUtensorMap map; };
+    static thread_local MapKey cache[8];
+    static thread_local int next_slot = 0;
+    auto get_map = [&](const void *ptr, const CUtensorMap **out) -> cudaError_t {
+        for (auto &c : cache)
+            if (c.p == ptr && c.n == N && c.h == H && c.w == W) { *out = &c.map; return cudaSuccess; }
+        MapKey &c = cache[next_slot++ & 7];
+        cudaError_t e = make_trunk_map(&c.map, ptr, N, H, W);
+        if (e != cudaSuccess) { c.p = nullptr; return e; }
+        c.p = ptr, c.n = N, c.h = H, c.w = W;
+        *out = &c.map;
+        return cudaSuccess;
+    };
+    const CUtensorMap *ma = nullptr, *mb = nullptr;
+    cudaError_t e;
+    if ((e = get_map(buf_a, &ma)) != cudaSuccess) return e;
+    const CUtensorMap map_a = *ma;   // (copied: the second lookup may evict the first entry)
+    if ((e = get_map(buf_b, &mb)) != cudaSuccess) return e;
+    const CUtensorMap map_b = *mb;
+    const int nc2 = M2 <= 8 ? 1 : M2 <= 16 ? 2 : 3;
+    auto kern = nc2 == 3 ? wdsr_chain_tc5_kernel<3> : nc2 == 2 ? wdsr_chain_tc5_kernel<2> : wdsr_chain_tc5_kernel<1>;
+    const size_t smem = tc5v5::smem_bytes(M1P);
+    static thread_local size_t smem_set[64][3] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || smem_set[dev][nc2 - 1] < smem) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) smem_set[dev][nc2 - 1] = smem;
+    }
+    tc5v5::ChainImages imgs = {};
+    for (int i = 0; i < nlayers; ++i) imgs.img[i] = wimgs[i];
+    if ((e = cudaMemsetAsync(gsync, 0, sizeof(unsigned), st)) != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas), cfg.blockDim = dim3(tc5v5::NTHREADS), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;   // the layer barrier needs every CTA resident
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, map_a, map_b, (bf16 *)buf_a, (bf16 *)buf_b, imgs, nlayers, gsync, M1P, N, H, W, tx, ty, ntiles);
 }
 
 }  // namespace b200sr

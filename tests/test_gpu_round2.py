@@ -249,7 +249,7 @@ def test_row_streaming_block_equals_oracle_and_tile_form(sr, shape, widths, form
     assert float((d > 0).float().mean()) < 0.2
 
 
-@pytest.mark.parametrize("form", ["rs", "rh", "tc5q"])
+@pytest.mark.parametrize("form", ["rs", "rh", "tc5q", "chain"])
 def test_row_streaming_model_graph_replay_is_deterministic(sr, form, monkeypatch):
     monkeypatch.setenv("B200SR_BLOCK_IMPL", form)
     torch.manual_seed(3)
@@ -263,12 +263,32 @@ def test_row_streaming_model_graph_replay_is_deterministic(sr, form, monkeypatch
             assert torch.equal(g(x), ref)
 
 
+@pytest.mark.parametrize("nb,scale,shape", [(1, 4, (1, 3, 16, 32)), (2, 2, (2, 3, 37, 45)), (5, 2, (1, 3, 131, 200)), (16, 4, (4, 3, 96, 96))])
+def test_chained_block_launch_is_bit_identical(sr, nb, scale, shape, monkeypatch):
+    """All residual blocks in one persistent cooperative launch with a grid-wide layer barrier (csrc/wdsr_tc5c.cuh, B200SR_BLOCK_IMPL=chain):
+    the same tiles through the same pipeline, so the output must equal the one-launch-per-block forward bit for bit -- odd and even block
+    counts (the result lands in either ping-pong buffer), one-tile-per-CTA grids (every tile is a layer boundary), eager and graph replay."""
+    outs = {}
+    for impl in ("tc5", "chain"):
+        monkeypatch.setenv("B200SR_BLOCK_IMPL", impl)
+        torch.manual_seed(11)
+        m = sr.BASIC_MODEL(_nas_params(scale, nb, ws=False)).eval().cuda().set_precision("bf16")
+        torch.manual_seed(12)
+        x = torch.rand(*shape, device="cuda").bfloat16()
+        with torch.no_grad():
+            y = m(x).clone()
+            g = sr.Graphed(m, x)
+            assert torch.equal(g(x), y) and torch.equal(g(x), y)
+        outs[impl] = y
+    assert torch.equal(outs["tc5"], outs["chain"])
+
+
 # ------------------------------------------------------------------------------------------------ our own memcheck / racecheck
 # compute-sanitizer is closed on this GPU pool (profiles/r02_compute_sanitizer_closed.txt), so the two properties it would check are
 # tested directly: (1) no kernel of the WDSR path writes outside its output / workspace -- every buffer sits between red zones of a
 # canary pattern that must survive; (2) the mbarrier / TMEM pipelines are free of observable races -- the same input gives
 # bit-identical output 12 times in a row while a second stream keeps the SMs and L2 busy with unrelated work.
-@pytest.mark.parametrize("impl", ["tc5", "rs", "rh", "tc5q"])
+@pytest.mark.parametrize("impl", ["tc5", "rs", "rh", "tc5q", "chain"])
 @pytest.mark.parametrize("shape,scale", [((2, 3, 37, 45), 4), ((1, 3, 130, 66), 2), ((3, 3, 96, 96), 4)])
 def test_red_zones_survive_and_results_repeat_under_load(sr, impl, shape, scale, monkeypatch):
     from mobilesuperresolution_b200 import _lib
