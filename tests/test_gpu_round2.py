@@ -200,6 +200,30 @@ def test_naive_model_golden(sr, precision, tmp_path):
         sr.Naive_model(2, str(f)).eval().cuda()(torch.from_numpy(x).cuda())     # x4 base on a x2 model: the reference's shape error
 
 
+@pytest.mark.parametrize("IN,ks,precision", [(12, (3, 7), "fp32"), (8, (5,), "bf16"), (24, (3, 3), "bf16")])
+def test_naive_model_widths_and_batches_against_the_oracle(sr, IN, ks, precision, tmp_path):
+    """Naive_model at widths the golden does not cover, batch 2, against the oracle port on the same seeded weights: IN = 12 is not a
+    multiple of the warp kernel's 16-byte channel slices in bf16 / takes the 3-slice window form in fp32, k = 7 blocks, a single 5x5 block
+    (decode inherits 5)."""
+    from oracle import port, synth
+    blocks = [[IN, 0, k] for k in ks]
+    f = tmp_path / "naive_index.txt"
+    f.write_text(repr((list(range(len(blocks))), blocks)) + "\n")
+    m = sr.Naive_model(4, str(f)).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = _t(synth.synth_state_dict(shapes, 500 + IN))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().set_precision(precision)
+    x = torch.from_numpy(synth.synth_input((2, 3, 3, 40, 72), 501))
+    ref = port.naive_model_forward(sd, x, len(blocks))
+    with torch.no_grad():
+        y = m(x.cuda()).cpu()
+    if precision == "fp32":
+        assert float((y - ref).abs().max()) <= FP32_TOL * max(1.0, float(ref.abs().max()))
+    else:
+        assert port.psnr_db(y, ref) >= BF16_PSNR
+
+
 # ------------------------------------------------------------------------------------------------ row-streaming block
 @pytest.mark.parametrize("shape", [(1, 24, 16, 32), (2, 24, 37, 45), (3, 24, 96, 96), (1, 24, 5, 300), (2, 24, 1, 1), (1, 24, 131, 7)])
 @pytest.mark.parametrize("widths", [(24, 144, 20), (24, 144, 24), (20, 100, 13), (9, 91, 7)])
