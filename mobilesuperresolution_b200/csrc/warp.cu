@@ -6,6 +6,8 @@
 //   zeros : each of the 4 corners contributes only if it lies inside the image
 //   border: the coordinate is clamped to [0, size-1] before it is split into corners.
 // Coordinates and blend weights are always fp32, also when the features are bf16 (bf16 resolves only 2 px at x~300).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -201,6 +203,81 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const T *__restrict
     }
 }
 
+// bf16, Q = C / 8 an even power of two (C = 16, 32, 64, 128): the instruction-lean form.  The general kernel above is issue bound (64 % of
+// the issue slots for 3.3-3.8 TB/s at C = 64): ~97 instructions per 16 output bytes, 68 of them the fp32 blend of unpacked bf16 pairs.  Here
+//   * a lane owns TWO adjacent 16-byte slices of a pixel (32 bytes): the per-pixel set-up is fetched once per 32 output bytes,
+//   * the set-up (four clamped corner offsets, four weights already zeroed for out-of-image corners) goes through shared memory -- two
+//     broadcast LDS.128 instead of nine shuffles,
+//   * the high bf16 of a pair is used as an fp32 WITHOUT masking its low half (the stray bits are < 2^-7 of a bf16 ulp of the operand;
+//     the output is rounded to bf16 anyway); the low one costs one shift.
+// Zero weights replace the validity predicates: an out-of-image corner adds v * 0 (finite inputs, like everywhere in this path).
+template <int Q>
+__global__ void __launch_bounds__(256) flow_warp_nhwc_bf16_lean_kernel(const bf16 *__restrict__ x, const float *__restrict__ flow,
+                                                                       bf16 *__restrict__ y, int N, int C, int H, int W, int border, int tiles_x,
+                                                                       int tiles_y, int y_cs, int y_co, int x_cs, int x_co) {
+    constexpr int LPP = Q / 2;          // lanes per pixel
+    constexpr int PPS = 32 / LPP;       // pixels per step
+    __shared__ int4 s_off[WTY][32];
+    __shared__ float4 s_w[WTY][32];
+    const int lane = threadIdx.x & 31, wrow = threadIdx.x >> 5;
+    const long long ntiles = (long long)N * tiles_x * tiles_y;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tx = (int)(t % tiles_x), ty = (int)((t / tiles_x) % tiles_y), n = (int)(t / ((long long)tiles_x * tiles_y));
+        const int yh = ty * WTY + wrow;
+        if (yh >= H) continue;  // whole warp
+        const int xw = tx * WTX + lane;
+        Bilin b = {};
+        if (xw < W) {
+            const float *f = flow + ((long long)n * 2 * H + yh) * W + xw;
+            b = bilinear_setup(__ldg(f), __ldg(f + (long long)H * W), xw, yh, W, H, border != 0);
+        }
+        const int cx0 = min(max(b.x0, 0), W - 1), cx1 = min(max(b.x0 + 1, 0), W - 1);
+        const int cy0 = min(max(b.y0, 0), H - 1), cy1 = min(max(b.y0 + 1, 0), H - 1);
+        __syncwarp();   // the previous tile's reads of this warp's rows are done
+        s_off[wrow][lane] = make_int4((cy0 * W + cx0) * x_cs, (cy0 * W + cx1) * x_cs, (cy1 * W + cx0) * x_cs, (cy1 * W + cx1) * x_cs);
+        s_w[wrow][lane] = make_float4(b.v00 ? b.w00 : 0.f, b.v01 ? b.w01 : 0.f, b.v10 ? b.w10 : 0.f, b.v11 ? b.w11 : 0.f);
+        __syncwarp();
+        const bf16 *xi = x + (long long)n * H * W * x_cs + x_co + (lane % LPP) * 16;
+        bf16 *yrow = y + (((long long)n * H + yh) * W + (long long)tx * WTX) * y_cs + y_co + (lane % LPP) * 16;
+        const int npx = min(WTX, W - tx * WTX);
+#pragma unroll 2
+        for (int s0 = 0; s0 < 32; s0 += PPS) {
+            const int src = s0 + lane / LPP;
+            if (src >= npx) continue;
+            const int4 o = s_off[wrow][src];
+            const float4 wv = s_w[wrow][src];
+            uint4 v[4][2];
+            const int off[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint4 *pk = reinterpret_cast<const uint4 *>(xi + off[k]);
+                v[k][0] = __ldg(pk), v[k][1] = __ldg(pk + 1);
+            }
+            const float wk[4] = {wv.x, wv.y, wv.z, wv.w};
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // same order and association as the general kernel: ((v00 w00 + v01 w01) + v10 w10) + v11 w11
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t *u = reinterpret_cast<const uint32_t *>(&v[k][h]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[8 * h + 2 * i] = fmaf(__uint_as_float(u[i] << 16), wk[k], acc[8 * h + 2 * i]);
+                        acc[8 * h + 2 * i + 1] = fmaf(__uint_as_float(u[i]), wk[k], acc[8 * h + 2 * i + 1]);
+                    }
+                }
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(acc[0], acc[1]), o0.y = pack_bf16x2(acc[2], acc[3]), o0.z = pack_bf16x2(acc[4], acc[5]), o0.w = pack_bf16x2(acc[6], acc[7]);
+            o1.x = pack_bf16x2(acc[8], acc[9]), o1.y = pack_bf16x2(acc[10], acc[11]), o1.z = pack_bf16x2(acc[12], acc[13]), o1.w = pack_bf16x2(acc[14], acc[15]);
+            uint4 *dst = reinterpret_cast<uint4 *>(yrow + (long long)src * y_cs);
+            __stcs(dst, o0);
+            __stcs(dst + 1, o1);
+        }
+    }
+}
+
 template <typename T, int Q>
 static cudaError_t warp_nhwc_t(const void *x, const float *flow, void *y, int n, int c, int h, int w, int border, int y_cs, int y_co,
                                int x_cs, int x_co, cudaStream_t st) {
@@ -235,7 +312,25 @@ cudaError_t launch_flow_warp_nhwc(const void *x, const float *flow_nchw, void *y
     const int vec = dtype == kF32 ? 4 : 8;     // the windows must keep the 16-byte loads / stores aligned
     if (c % vec || y_cs % vec || y_co % vec || y_co + c > y_cs || x_cs % vec || x_co % vec || x_co + c > x_cs) return cudaErrorInvalidValue;
     if (dtype == kF32) return warp_nhwc_q<float>(c / 4, x, flow_nchw, y, n, c, h, w, border, y_cs, y_co, x_cs, x_co, st);
-    return warp_nhwc_q<bf16>(c / 8, x, flow_nchw, y, n, c, h, w, border, y_cs, y_co, x_cs, x_co, st);
+    const int Q = c / 8;
+    // lean bf16 form: two slices per lane need 32-byte aligned windows and int32 element offsets into one image
+    if ((Q == 2 || Q == 4 || Q == 8 || Q == 16) && x_cs % 16 == 0 && x_co % 16 == 0 && y_cs % 16 == 0 && y_co % 16 == 0 &&
+        (long long)h * w * x_cs < (1ll << 31) && !getenv("B200SR_WARP_GENERAL")) {
+        const int tx = ceil_div(w, WTX), ty = ceil_div(h, WTY);
+        long long blocks = (long long)n * tx * ty;
+        static const int per_sm = [] { const char *e = getenv("B200SR_WARP_CTAS_PER_SM"); return e ? atoi(e) : 4; }();   // (developer sweep: 2 / 3 / 4 / 5 / 6 / 8 / 16 / 32 per SM -> 3.3 / 4.3 / 4.9 / 3.6 / 3.9 / 4.7 / 4.7 / 4.6 TB/s at 8x720x1280x64)
+        const long long cap = (long long)sm_count() * per_sm;   // resident CTAs walk the tile list
+        if (blocks > cap) blocks = cap;
+#define B200SR_WARP_LEAN(QQ)                                                                                                      \
+    if (Q == QQ) {                                                                                                                \
+        flow_warp_nhwc_bf16_lean_kernel<QQ><<<(unsigned)blocks, 256, 0, st>>>((const bf16 *)x, flow_nchw, (bf16 *)y, n, c, h, w, border, tx, ty, \
+                                                                               y_cs, y_co, x_cs, x_co);                           \
+        return cudaGetLastError();                                                                                                \
+    }
+        B200SR_WARP_LEAN(2) B200SR_WARP_LEAN(4) B200SR_WARP_LEAN(8) B200SR_WARP_LEAN(16)
+#undef B200SR_WARP_LEAN
+    }
+    return warp_nhwc_q<bf16>(Q, x, flow_nchw, y, n, c, h, w, border, y_cs, y_co, x_cs, x_co, st);
 }
 
 }  // namespace b200sr
