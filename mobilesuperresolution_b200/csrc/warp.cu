@@ -283,7 +283,8 @@ static cudaError_t warp_nhwc_t(const void *x, const float *flow, void *y, int n,
                                int x_cs, int x_co, cudaStream_t st) {
     const int tx = ceil_div(w, WTX), ty = ceil_div(h, WTY);
     long long blocks = (long long)n * tx * ty;
-    const long long cap = (long long)sm_count() * 32;
+    static const int per_sm = [] { const char *e = getenv("B200SR_WARPG_CTAS_PER_SM"); return e ? atoi(e) : 4; }();   // (developer sweep, fp32 C = 64 at 720p: 2 / 4 / 8 / 32 per SM -> 2.6 / 4.4 / 4.0 / 4.2 TB/s)
+    const long long cap = (long long)sm_count() * per_sm;
     if (blocks > cap) blocks = cap;
     flow_warp_nhwc_kernel<T, Q><<<(unsigned)blocks, 256, 0, st>>>((const T *)x, flow, (T *)y, n, c, h, w, border, tx, ty, y_cs, y_co, x_cs, x_co);
     return cudaGetLastError();
