@@ -106,7 +106,8 @@ cudaError_t launch_flow_warp_nchw(const float *x, const float *flow, long long f
     if (P == 0 || c == 0) return cudaSuccess;
     const int tx = ceil_div(w, WTX), ty = ceil_div(h, WTY);
     long long blocks = (long long)n * tx * ty;
-    const long long cap = (long long)sm_count() * 32;
+    static const int per_sm = [] { const char *e = getenv("B200SR_WARPN_CTAS_PER_SM"); return e ? atoi(e) : 8; }();   // (developer sweep, 4 x 64 x 720 x 1280: 4 / 8 / 16 / 32 per SM -> 1.9 / 3.1 / 3.0 / 2.8 TB/s)
+    const long long cap = (long long)sm_count() * per_sm;
     if (blocks > cap) blocks = cap;
     flow_warp_nchw_kernel<<<(unsigned)blocks, WTX * WTY, 0, st>>>(x, flow, fs_n, fs_h, fs_w, fs_c, y, n, c, h, w, border, tx, ty);
     return cudaGetLastError();
