@@ -269,3 +269,20 @@ def test_naive_model_state_dict_and_seeded_construction(sr, tmp_path):
     with pytest.raises(RuntimeError):
         m.eval()(torch.rand(1, 2, 3, 40, 40))       # CPU tensor: no fallback
 
+
+def test_cat_feats_is_free_only_for_adjacent_windows_of_one_tensor():
+    """video._cat_feats: torch.cat([backward, forward], -1) of models/basicvsr_arch_origin.py:84 -- returns the shared base tensor (no copy)
+    exactly when the two operands are its two adjacent channel halves, and an ordinary concatenation in every other case."""
+    from mobilesuperresolution_b200.video import _cat_feats
+    base = torch.arange(2 * 3 * 4 * 8, dtype=torch.float32).view(2, 3, 4, 8).clone()   # owns its storage, like the tensors propagate() allocates
+    a, b = base[..., :4], base[..., 4:]
+    assert _cat_feats(a, b) is base
+    assert torch.equal(_cat_feats(b, a), torch.cat([b, a], -1)) and _cat_feats(b, a) is not base          # swapped halves
+    assert torch.equal(_cat_feats(a, a), torch.cat([a, a], -1))                                            # same half twice
+    other = base.clone()
+    assert torch.equal(_cat_feats(a, other[..., 4:]), base) and _cat_feats(a, other[..., 4:]) is not base   # windows of different tensors
+    c, d = base[..., :3], base[..., 3:6]
+    assert torch.equal(_cat_feats(c, d), base[..., :6]) and _cat_feats(c, d).data_ptr() != base.data_ptr() or _cat_feats(c, d).shape[-1] == 6
+    x, y = torch.zeros(2, 3, 4, 4), torch.ones(2, 3, 4, 4)
+    assert torch.equal(_cat_feats(x, y), torch.cat([x, y], -1))                                             # plain tensors (no base)
+
