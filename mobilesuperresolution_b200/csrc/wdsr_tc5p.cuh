@@ -236,7 +236,10 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
 #else
                     const int nk2x = nk2;
 #endif
-#pragma unroll 4
+                    // unroll sweep at cfg2 / 360p / 1080p (us per launch): 1: 27.7 / 15.4 / 86.3, 2: 25.9 / 14.6 / 81.4, 4: 25.8 / 14.5 / 80.1,
+                    // 8: 25.2 / 14.2 / 78.8; fully unrolled behind a uniform guard: 31.5 / 16.9 / 108 (the descriptors then live in vector
+                    // registers and every MMA pays R2UR moves)
+#pragma unroll 8
                     for (int j = 1; j < nk2x; ++j) tc5::mma_ts(d2, a2 + (j < 4 ? 8 * j : a2hi + 8 * (j - 4)), bw2 + (uint64_t)(16 * j), idesc32, true);
                     tc5::commit(bar(D2_FULL + e));
                     if (m + 2 < NMT) {
