@@ -57,7 +57,7 @@ def test_stages_against_oracle(G, precision):
     if precision == "fp32":
         assert G.maxabs(got, ref_blk) <= 2e-5
     else:
-        assert G.psnr(got, ref_blk) >= 45.0        # single stage, looser than the end-to-end gate on purpose
+        assert G.psnr(got, ref_blk) >= 50.0        # the same gate as end to end (measured ~69 dB)
     # tail
     ref_tail = F.pixel_shuffle(
         F.conv2d(ref_blk, port.weight_norm_fold(sd["tail.weight_g"], sd["tail.weight_v"]), sd["tail.bias"], padding=1) +
@@ -70,7 +70,7 @@ def test_stages_against_oracle(G, precision):
     if precision == "fp32":
         assert G.maxabs(got, ref_tail) <= 2e-5
     else:
-        assert G.psnr(got, ref_tail) >= 45.0
+        assert G.psnr(got, ref_tail) >= 50.0
 
 
 # ---------------------------------------------------------------- golden fixtures -----------------------
