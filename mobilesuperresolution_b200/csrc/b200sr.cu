@@ -320,7 +320,7 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
         // elsewhere.  B200SR_BLOCK_IMPL = mma | tc5seq | tc5 | tc5q | rs | rh is a developer switch (A/B timing, reference form):
         // tc5 = the tile form (wdsr_tc5p.cuh, the default); rs = the row-streaming form (wdsr_rs.cuh; cfg2 28.4 vs 26.9 us, 1080p 74-82 vs
         // 80 us per launch); rh = row-streaming with the reduce 1x1 on mma.sync out of registers (wdsr_rh.cuh; 32.5 / 94 us: bound by the
-        // legacy HMMA rate, profiles/r02_block_rh.md); tc5q = the tile form with decoupled expand staging (wdsr_tc5q.cuh; 28.7 / 90 us).
+        // legacy HMMA rate, profiles/r02_block_rh.md); tc5q = the tile form with decoupled expand staging (wdsr_tc5q.cuh; 27.7 / 86 us).
         // All of them are parity-green against the oracle and each other.
         const char *e = getenv("B200SR_BLOCK_IMPL");
         p->block_impl = !e ? 2 : !strcmp(e, "mma") ? 0 : !strcmp(e, "tc5seq") ? 1 : !strcmp(e, "rs") ? 3 : !strcmp(e, "rh") ? 4 : !strcmp(e, "tc5q") ? 5 : !strcmp(e, "chain") ? 6 : 2;

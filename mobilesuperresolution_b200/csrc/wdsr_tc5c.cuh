@@ -145,7 +145,7 @@ wdsr_chain_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 #ifdef B200SR_TC5_PROF
       tc5::setmaxnreg_dec<56>();   // the probe counters need registers; paid for by the E2 warpgroups (see below)
 #else
-      tc5::setmaxnreg_dec<40>();
+      tc5::setmaxnreg_dec<48>();   // (one more issuer warp / per-layer descriptors: 40 registers spilled, and a spill in an issuer thread stalls the MMA stream)
 #endif
       if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -500,7 +500,7 @@ wdsr_chain_tc5_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
                 }
             }
         } else {
-            tc5::setmaxnreg_dec<72>();
+            tc5::setmaxnreg_dec<64>();
             // WG5: E3 of 3x3 M-tiles k = 0..3 of every tile
 #pragma unroll
             for (int k = 0; k < 4; ++k) tc5::mbar_arrive(bar(G3_READY + k));  // stand-ins for "previous tile's E3 drained D3[k]"
