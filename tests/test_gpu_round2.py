@@ -224,6 +224,19 @@ def test_naive_model_widths_and_batches_against_the_oracle(sr, IN, ks, precision
         assert port.psnr_db(y, ref) >= BF16_PSNR
 
 
+def test_naive_model_graph_replay(sr, tmp_path):
+    """Naive_model's forward (SPyNet on its cached workspace, windowed warp, convs, tail) is CUDA-graph capturable and replays bit-identically."""
+    f = tmp_path / "naive_index.txt"
+    f.write_text(repr(([0, 1], [[16, 0, 3], [16, 0, 3]])) + "\n")
+    torch.manual_seed(21)
+    m = sr.Naive_model(4, str(f)).eval().cuda().set_precision("bf16")
+    x = torch.rand(1, 3, 3, 64, 96, device="cuda")
+    with torch.no_grad():
+        y = m(x).clone()
+        g = sr.Graphed(m, x)
+        assert torch.equal(g(x), y) and torch.equal(g(x), y)
+
+
 # ------------------------------------------------------------------------------------------------ row-streaming block
 @pytest.mark.parametrize("shape", [(1, 24, 16, 32), (2, 24, 37, 45), (3, 24, 96, 96), (1, 24, 5, 300), (2, 24, 1, 1), (1, 24, 131, 7)])
 @pytest.mark.parametrize("widths", [(24, 144, 20), (24, 144, 24), (20, 100, 13), (9, 91, 7)])
