@@ -92,3 +92,23 @@ def test_flow_warp_full_size_identity_and_shift(V):
     for mode in ("zeros", "border"):
         ref = port.flow_warp(xc, fl, padding_mode=mode)
         assert float((V.flow_warp(x, fl.cuda(), padding_mode=mode).cpu() - ref).abs().max()) <= 2e-5
+
+
+@pytest.mark.parametrize("dtype,c,xc,xo,yc,yo", [(torch.bfloat16, 64, 128, 64, 80, 16), (torch.bfloat16, 32, 64, 0, 64, 32), (torch.bfloat16, 24, 48, 24, 32, 8),
+                                                (torch.float32, 16, 24, 8, 20, 4), (torch.bfloat16, 16, 48, 32, 16, 0)])
+def test_flow_warp_nhwc_channel_windows(V, dtype, c, xc, xo, yc, yo):
+    """x read from channels [xo, xo + c) of a wider tensor and y written into channels [yo, yo + c) of another one (the in-place concatenations
+    of the BasicVSR propagation): equal to the contiguous call bit for bit, and the other channels of y untouched.  Covers the lean bf16 kernel
+    (c = 64, 32, 16 with 32-byte aligned windows), its fallback (a 16-byte aligned window) and the general kernel (c = 24, fp32)."""
+    g = torch.Generator().manual_seed(14)
+    wide = torch.randn(2, 37, 53, xc, generator=g).to(dtype).cuda()
+    fl = ((torch.rand(2, 2, 37, 53, generator=g) - 0.5) * 12).cuda()
+    xwin = wide[..., xo:xo + c]
+    ref = V.flow_warp_nhwc(xwin.contiguous(), fl)
+    out = torch.full((2, 37, 53, yc), 7.0, dtype=dtype, device="cuda")
+    V.flow_warp_nhwc(xwin, fl, out=out, out_coff=yo)
+    torch.cuda.synchronize()
+    assert torch.equal(out[..., yo:yo + c], ref)
+    rest = torch.cat([out[..., :yo], out[..., yo + c:]], -1)
+    assert rest.numel() == 0 or bool((rest == 7.0).all())
+
