@@ -45,14 +45,17 @@ cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8
     const int nc2 = M2 <= 8 ? 1 : M2 <= 16 ? 2 : 3;   // 8-channel chunks of t2 (the image was packed for exactly these, b200sr.cu)
     // variant 1: wdsr_tc5p.cuh (expand accumulator re-used in place as the reduce operand); 2: wdsr_tc5q.cuh (decoupled staging halves)
     const bool q = variant == 2;
-    auto kern = q ? (nc2 == 3 ? wdsr_block_tc5q_kernel<3> : nc2 == 2 ? wdsr_block_tc5q_kernel<2> : wdsr_block_tc5q_kernel<1>)
-                  : (nc2 == 3 ? wdsr_block_tc5p_kernel<3> : nc2 == 2 ? wdsr_block_tc5p_kernel<2> : wdsr_block_tc5p_kernel<1>);
+    // the decoupled form takes two staging slots per expand half where TMEM has room for them (3 M1P + 128 <= 512 columns: the pruned widths)
+    const bool q2 = q && M1P <= 128;
+    auto kern = q2 ? (nc2 == 3 ? wdsr_block_tc5q_kernel<3, 2> : nc2 == 2 ? wdsr_block_tc5q_kernel<2, 2> : wdsr_block_tc5q_kernel<1, 2>)
+                : q ? (nc2 == 3 ? wdsr_block_tc5q_kernel<3, 1> : nc2 == 2 ? wdsr_block_tc5q_kernel<2, 1> : wdsr_block_tc5q_kernel<1, 1>)
+                    : (nc2 == 3 ? wdsr_block_tc5p_kernel<3> : nc2 == 2 ? wdsr_block_tc5p_kernel<2> : wdsr_block_tc5p_kernel<1>);
     const size_t smem = tc5v3::smem_bytes(M1P);
     static_assert(tc5v3::CTRL_BYTES == tc5v4::CTRL_BYTES, "the two forms share one shared-memory layout");
-    static thread_local size_t smem_set[64][6] = {};
+    static thread_local size_t smem_set[64][9] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const int ki = nc2 - 1 + (q ? 3 : 0);
+    const int ki = nc2 - 1 + (q2 ? 6 : q ? 3 : 0);
     if (dev < 0 || dev >= 64 || smem_set[dev][ki] < smem) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -4,7 +4,7 @@
 // wdsr_tc5p.cuh keeps two 144-column fp32 expand accumulators D1[2] and writes relu(t1) back IN PLACE as the bf16 A operand of G2: a buffer
 // is busy from G1's issue until G2 has read it -- G1 + commit -> E1 wake + tcgen05.ld + cvt + tcgen05.st + arrive -> issuer wake + G2,
 // ~2 k clk with the queueing behind the 3x3 stream -- and two of them make one 128-pixel M-tile per ~1.08 k clk however the stages are
-// tuned (Little's law).  Here:
+// tuned (the hypothesis this file tests; DESIGN.md 4.1b records that neither one nor two staging slots per half beat the in-place form).  Here:
 //   * the expand is issued as two N-halves (channels 0..63 / 64..M1P-1) into ONE 64- and ONE 80-column fp32 staging area D1H[a], D1H[b];
 //     a half is released as soon as its E1 warpgroup's tcgen05.ld has RETIRED (G1 + commit -> wake + ld + arrive -> issuer: ~0.75 k clk),
 //   * relu(t1) goes to separate bf16 buffers T1[2] x 72 columns (the A operand of G2; free again when the G2 that read it has retired =
@@ -25,31 +25,39 @@ constexpr int XS_BUF = 3 * XS_PLANE;           // 30,720 B of tile data per buff
 constexpr int XS_ONE = XS_NBUF * XS_BUF;       // byte offset of the constant-one plane
 constexpr int XS_BYTES_ALL = XS_ONE + XS_PLANE;
 constexpr int TMA_BYTES = 3 * HP * 16;         // 29,376 B per tile
-__host__ __device__ constexpr int d1h_col(int half) { return half * 64; }   // fp32 staging of the expand halves: a = channels 0..63, b = 64..M1P-1
-__host__ __device__ constexpr int t1_col(int e) { return 144 + e * 72; }     // packed bf16 relu(t1): K step j of G2 at column 8 j
-__host__ __device__ constexpr int d2_col(int e) { return 288 + e * 32; }
-__host__ __device__ constexpr int d3_col(int k) { return 352 + k * 32; }
+// TMEM column map.  NS = staging slots per expand half:
+//   NS = 1 (any M1P <= 144):  D1H[a] 0..63 | D1H[b] 64..143 | T1[2] x 72 at 144 | D2[2] x 32 at 288 | D3[4] x 32 at 352
+//   NS = 2 (M1P <= 128, the pruned widths): D1H[slot] x M1P (a at +0, b at +64) | T1[2] x M1P/2 | D2[2] x 32 | D3[2] x 32  = 3 M1P + 128 <= 512:
+//           two M-tiles of each half in flight through the short G1 -> ld -> release trip, paid for with two of the four 3x3 accumulators
+template <int NS> struct Cols {
+    int m1p;
+    __device__ int d1h(int half, int slot) const { return NS == 1 ? half * 64 : slot * m1p + half * 64; }   // fp32 staging: a = channels 0..63, b = 64..M1P-1
+    __device__ int t1(int e) const { return NS == 1 ? 144 + e * 72 : 2 * m1p + e * (m1p / 2); }            // packed bf16 relu(t1): K step j of G2 at column 8 j
+    __device__ int d2(int e) const { return (NS == 1 ? 288 : 3 * m1p) + e * 32; }
+    __device__ int d3(int k) const { return NS == 1 ? 352 + k * 32 : 3 * m1p + 64 + (k & 1) * 32; }
+};
 // Everything a group of MMAs needs is folded into ONE barrier per issuer step:
 //   D1H_FREE[half] (128) = the E1 warpgroup of that half has read D1H[half] of the current M-tile: the next G1 half may be issued
 //   G2_READY[e] (384)    = both E1 warpgroups wrote their K steps of T1[e]  +  E2 of the previous M-tile on this buffer drained D2[e]
 //   G3_READY[k] (384)    = E2 of M-tiles k and k+1 wrote their t2 rows  +  E3 of the previous tile drained D3[k]
 //   D2_FULL[e] (1)       = commit after G2: D2[e] is complete AND T1[e] has been read (E1 waits for it before overwriting T1[e])
-enum Bar { XS_FULL = 0 /*3*/, XS_EMPTY = 3 /*3*/, D1H_FULL = 6 /*2*/, G2_READY = 8, D2_FULL = 10, G3_READY = 12 /*4*/, T2R_FREE = 16 /*4*/,
-           D3_FULL = 20 /*4*/, D1H_FREE = 24 /*2*/, NBARS = 26 };
-constexpr int CTRL_BYTES = 256;  // 26 mbarriers (208 B) + tmem base pointer at byte 240
+enum Bar { XS_FULL = 0 /*3*/, XS_EMPTY = 3 /*3*/, G2_READY = 6, D2_FULL = 8, G3_READY = 10 /*4*/, T2R_FREE = 14 /*4*/, D3_FULL = 18 /*4*/,
+           D1H_FULL = 22 /*half * 2 + slot*/, D1H_FREE = 26 /*half * 2 + slot*/, NBARS = 30 };
+constexpr int CTRL_BYTES = 256;  // 30 mbarriers (240 B) + tmem base pointer at byte 240
 constexpr size_t smem_bytes(int M1P) { return (size_t)tc5v4::CTRL_BYTES + XS_BYTES_ALL + T2_BYTES + (size_t)BlockTc5Layout(M1P).total; }
 }  // namespace tc5v4
 
 // NC2 = 8-channel chunks of t2 the block really has (3 dense; 2 / 1 for pruned M2 <= 16 / <= 8): the host packs only those
 // (tap, chunk) slices of w3 (b200sr.cu) and the 3x3 issues 14 / 9 / 5 MMAs.  A template parameter, not a run-time value: the
 // dense instantiation is then exactly the code that was tuned (a run-time switch cost it 3-5 %).
-template <int NC2>
+template <int NC2, int NS>
 __global__ void __launch_bounds__(tc5v4::NTHREADS, 1)
 wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *__restrict__ in, bf16 *__restrict__ out,
                        const uint8_t *__restrict__ wimg, int M1P, int N, int H, int W, int tiles_x, int tiles_y, int ntiles) {
     using namespace tc5v4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const BlockTc5Layout L(M1P);
+    const tc5v4::Cols<NS> col{M1P};
     uint8_t *ctrl = smem_raw;
     uint8_t *xs = smem_raw + tc5v4::CTRL_BYTES;  // XS_NBUF x XS_BUF + constant-one plane
     uint8_t *t2 = xs + XS_BYTES_ALL;      // T2_BYTES
@@ -91,8 +99,10 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             tc5::mbar_init(bar(XS_EMPTY + b), 129);  // commit after the last G1 + the 128 threads of WG5 after the tile's last E3
         }
         for (int e = 0; e < 2; ++e) {
-            tc5::mbar_init(bar(D1H_FULL + e), 1);
-            tc5::mbar_init(bar(D1H_FREE + e), 128);
+            for (int sl = 0; sl < 2; ++sl) {
+                tc5::mbar_init(bar(D1H_FULL + 2 * e + sl), 1);
+                tc5::mbar_init(bar(D1H_FREE + 2 * e + sl), 128);
+            }
             tc5::mbar_init(bar(G2_READY + e), 384);
             tc5::mbar_init(bar(D2_FULL + e), 1);
         }
@@ -157,15 +167,15 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         const uint64_t bw1a = tc5::smem_desc(w_u + L.w1, 128, 512), bw1b = tc5::smem_desc(w_u + L.w1 + 256, 128, 512);
         const uint64_t half_b = (uint64_t)((8 * 512) >> 4);
         const uint64_t ax0 = tc5::smem_desc(xs_u, XS_PLANE, 128);  // planes paired through LBO
-        auto issue_g1 = [&](int xb, int m, int half) {  // leader only
+        auto issue_g1 = [&](int xb, int m, int half, int slot) {  // leader only
             const uint32_t off = xb * XS_BUF + m * 2048;
-            const uint32_t d = tmem + d1h_col(half);
+            const uint32_t d = tmem + col.d1h(half, slot);
             const uint64_t hb = half ? half_b : 0;
             const uint32_t idesc = half ? idesc_b : idesc_a;
             tc5::mma_ss(d, ax0 + (uint64_t)(off >> 4), bw1a + hb, idesc, false);  // planes 0,1
             // plane 2 paired with the shared constant-one plane: LBO = their distance
             tc5::mma_ss(d, tc5::smem_desc(xs_u + off + 2 * XS_PLANE, XS_ONE - xb * XS_BUF - 2 * XS_PLANE, 128), bw1b + hb, idesc, true);
-            tc5::commit(bar(D1H_FULL + half));
+            tc5::commit(bar(D1H_FULL + 2 * half + slot));
         };
         V3_T0();
         uint32_t g = 0;   // M-tiles issued so far: D1H_FREE[half] completes once per M-tile
@@ -176,11 +186,13 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     if (half == 1 && NB == 0) break;
-                    if (g > 0) V3_WAIT(0, bar(D1H_FREE + half), (g - 1) & 1);
+                    // slot g % NS was last used by M-tile g - NS: its E1 warpgroup must have read it (phase (g - NS) / NS of that slot)
+                    const int slot = NS == 1 ? 0 : (int)(g & 1);
+                    if (g >= (uint32_t)NS) V3_WAIT(0, bar(D1H_FREE + 2 * half + slot), ((g - NS) / NS) & 1);
                     tc5::fence_after_sync();
                     V3_EVT(100 + m);
                     if (leader) {
-                        issue_g1(xb, m, half);
+                        issue_g1(xb, m, half, slot);
                         if (m == NMT - 1 && (half == 1 || NB == 0)) tc5::commit(bar(XS_EMPTY + xb));  // all G1 reads of XS[xb] retired
                     }
                     __syncwarp();
@@ -188,7 +200,7 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             }
         }
         V3_ADD(5);
-        if (nmine > 0) tc5::mbar_wait(bar(D1H_FULL + (NB > 0 ? 1 : 0)), (g - 1) & 1);  // the last G1 and all before it retired
+        if (nmine > 0) tc5::mbar_wait(bar(D1H_FULL + 2 * (NB > 0 ? 1 : 0) + (NS == 1 ? 0 : (int)((g - 1) & 1))), ((g - 1) / NS) & 1);  // the last G1 and all before it retired
       } else if (warp == 3) {
         // ============================== MMA issuer C: the reduce (G2) ==============================
         const bool leader = tc5::elect_one();
@@ -204,7 +216,7 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                 tc5::fence_after_sync();
                 V3_EVT(110 + m);
                 if (leader) {
-                    const uint32_t d2 = tmem + d2_col(e), a2 = tmem + t1_col(e);
+                    const uint32_t d2 = tmem + col.d2(e), a2 = tmem + col.t1(e);
                     tc5::mma_ts(d2, a2, bw2, idesc32, false);
 #pragma unroll 4
                     for (int j = 1; j < nk2; ++j) tc5::mma_ts(d2, a2 + 8 * j, bw2 + (uint64_t)(16 * j), idesc32, true);
@@ -222,7 +234,7 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         auto issue_g3_nc = [&](int k, auto ncc) {  // leader only; NC = chunks of t2 (3 dense; 2 or 1 for pruned M2 <= 16 / <= 8)
             constexpr int NC = decltype(ncc)::value, NS = 9 * NC, NM = (NS + 1) / 2;
             const uint64_t abase = at0 + (uint64_t)((k * 4 * T2_ROW) >> 4);
-            const uint32_t d3 = tmem + d3_col(k);
+            const uint32_t d3 = tmem + col.d3(k);
 #ifdef B200SR_EXP_G3SHORT
             constexpr int NG3 = 2;   // (timing experiment: results are wrong)
 #else
@@ -267,18 +279,18 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         // ---- E1 of one expand half: fp32 staging -> registers (the half is released as soon as the loads have retired) -> relu -> bf16x2 ->
         //      this half's K steps of T1[eb].  WG1: channels 0..63 -> T1 columns 0..31; WG2: channels 64..M1P-1 -> columns 32...
         //      N32 / R16: 32-column loads and a 16-column remainder (compile-time shapes: the arrays stay in registers).
-        auto e1_half = [&](int eb, int nth, int half, auto n32c, auto r16c) {
+        auto e1_half = [&](int eb, int nth, int half, int slot, auto n32c, auto r16c) {
             constexpr int N32 = decltype(n32c)::value;
             constexpr bool R16 = decltype(r16c)::value != 0;
-            const uint32_t d1 = tmem + lane_base + d1h_col(half);
-            const uint32_t t1 = tmem + lane_base + t1_col(eb) + (half ? 32 : 0);
+            const uint32_t d1 = tmem + lane_base + col.d1h(half, slot);
+            const uint32_t t1 = tmem + lane_base + col.t1(eb) + (half ? 32 : 0);
             uint32_t va[32], vb[32], vc[16];
             if constexpr (N32 >= 1) tc5::tmem_ld32(d1, va);
             if constexpr (N32 >= 2) tc5::tmem_ld32(d1 + 32, vb);
             if constexpr (R16) tc5::tmem_ld16(d1 + 32 * N32, vc);
             tc5::tmem_wait_ld();
             tc5::fence_before_sync();
-            tc5::mbar_arrive_relaxed(bar(D1H_FREE + half));   // the staging area may take the next M-tile's half
+            tc5::mbar_arrive_relaxed(bar(D1H_FREE + 2 * half + slot));   // the staging slot may take a later M-tile's half
             V3_EVT(302);
             if constexpr (N32 >= 1) {
 #pragma unroll
@@ -301,7 +313,7 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             if constexpr (N32 >= 2) tc5::tmem_st16(t1 + 16, *reinterpret_cast<uint32_t(*)[16]>(&vb[0]));
             if constexpr (R16) tc5::tmem_st8(t1 + 16 * N32, *reinterpret_cast<uint32_t(*)[8]>(&vc[0]));
         };
-        auto e1 = [&](int eb, int nth) {
+        auto e1 = [&](int eb, int nth, int slot) {
             using std::integral_constant;
             tc5::fence_after_sync();
             V3_T0();
@@ -309,11 +321,11 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             const int half = wg - 1;
             const int ncol = half == 0 ? (M1P < 64 ? M1P : 64) : (M1P > 64 ? M1P - 64 : 0);
             switch (ncol) {
-                case 80: e1_half(eb, nth, half, integral_constant<int, 2>{}, integral_constant<int, 1>{}); break;
-                case 64: e1_half(eb, nth, half, integral_constant<int, 2>{}, integral_constant<int, 0>{}); break;
-                case 48: e1_half(eb, nth, half, integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
-                case 32: e1_half(eb, nth, half, integral_constant<int, 1>{}, integral_constant<int, 0>{}); break;
-                case 16: e1_half(eb, nth, half, integral_constant<int, 0>{}, integral_constant<int, 1>{}); break;
+                case 80: e1_half(eb, nth, half, slot, integral_constant<int, 2>{}, integral_constant<int, 1>{}); break;
+                case 64: e1_half(eb, nth, half, slot, integral_constant<int, 2>{}, integral_constant<int, 0>{}); break;
+                case 48: e1_half(eb, nth, half, slot, integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
+                case 32: e1_half(eb, nth, half, slot, integral_constant<int, 1>{}, integral_constant<int, 0>{}); break;
+                case 16: e1_half(eb, nth, half, slot, integral_constant<int, 0>{}, integral_constant<int, 1>{}); break;
                 default:   // M1P <= 64: nothing in the upper half -- keep in step with the buffer's phases all the same
                     if (nth > 0) tc5::mbar_wait(bar(D2_FULL + eb), (nth - 1) & 1);
                     break;
@@ -331,7 +343,7 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             V3_T0();
             V3_EVT(500 + k);
             uint32_t v[32];
-            tc5::tmem_ld32(tmem + lane_base + d3_col(k), v);
+            tc5::tmem_ld32(tmem + lane_base + col.d3(k), v);
             const int ly = 4 * k + (row >> 5), lx = row & 31;
             const int gy = y0 + 1 + ly, gx = x0 + 1 + lx;
             const uint8_t *res = xs + xb * XS_BUF + ((ly + 1) * HW_ + lx + 1) * 16;
@@ -342,7 +354,9 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             tc5::tmem_wait_ld();
             V3_EVT(530 + k);
             tc5::fence_before_sync();
-            tc5::mbar_arrive_relaxed(bar(G3_READY + k));
+            // D3 buffer drained: counts towards the G3 that uses it next (NS = 1: G3(k) of the next tile; NS = 2, two buffers: G3(k + 2) of this
+            // tile for k < 2, G3(k - 2) of the next one otherwise)
+            tc5::mbar_arrive_relaxed(bar(G3_READY + (NS == 1 ? k : ((k + 2) & 3))));
             V3_EVT(540 + k);  // D3[k] drained (wait::ld): counts towards the next tile's G3(k)
 #ifdef B200SR_EXP_NOSTORE
             if (gy < H && gx < W && v[0] == 0x7fc12345u) {   // (timing experiment)
@@ -376,7 +390,7 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             V3_T0();
             V3_EVT(400 + m);
             uint32_t v[32];
-            tc5::tmem_ld32(tmem + lane_base + d2_col(e), v);
+            tc5::tmem_ld32(tmem + lane_base + col.d2(e), v);
             const int p = m * 128 + row;
             const int r = p / HW_, hx = p - r * HW_;
             const int gy = y0 + r, gx = x0 + hx;
@@ -421,8 +435,9 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             const int hbar = (wg == 2 && M1P > 64) ? 1 : 0;   // (an absent upper half paces itself on the lower half's barrier)
             for (int i1 = 0; i1 < NMT * nmine; ++i1) {
                 const int mm = i1 % NMT, eb = mm & 1, nth = (i1 / NMT) * (eb == 0 ? 3 : 2) + (mm >> 1);
-                V3_WAIT(0, bar(D1H_FULL + hbar), i1 & 1);
-                e1(eb, nth);
+                const int slot = NS == 1 ? 0 : (i1 & 1);
+                V3_WAIT(0, bar(D1H_FULL + 2 * hbar + slot), (i1 / NS) & 1);
+                e1(eb, nth, slot);
             }
         } else if (wg <= 4) {
 #ifdef B200SR_TC5_PROF
@@ -448,7 +463,7 @@ wdsr_block_tc5q_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             tc5::setmaxnreg_dec<64>();
             // WG5: E3 of 3x3 M-tiles k = 0..3 of every tile
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc5::mbar_arrive(bar(G3_READY + k));  // stand-ins for "previous tile's E3 drained D3[k]"
+            for (int k = 0; k < (NS == 1 ? 4 : 2); ++k) tc5::mbar_arrive(bar(G3_READY + k));  // stand-ins: the first G3s find their D3 buffer free
             for (int it = 0; it < nmine; ++it) {
                 int x0, y0, n;
                 tile_origin(it, x0, y0, n);

@@ -19,7 +19,7 @@ int main(int argc, char **argv) {
     const int tx = ceil_div(W, 32), ty = ceil_div(H, 16), ntiles = tx * ty * N;
     CUtensorMap map; if (make_trunk_map(&map, din, N, H, W) != cudaSuccess) { printf("map failed\n"); return 1; }
     size_t smem = tc5v3::smem_bytes(M1P);
-    auto kern = which ? wdsr_block_tc5q_kernel<3> : wdsr_block_tc5p_kernel<3>;
+    auto kern = which ? wdsr_block_tc5q_kernel<3, 1> : wdsr_block_tc5p_kernel<3>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int rep = 0; rep < 4; ++rep) {
         cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
