@@ -84,7 +84,8 @@ struct b200sr_wdsr {
     float *d_head = nullptr;
     std::vector<float *> d_blk_f32;
     std::vector<uint8_t *> d_blk_bf16;
-    std::vector<uint8_t *> d_blk_tc5;  // tcgen05 operand images (nullptr where the block is not eligible)
+    std::vector<uint8_t *> d_blk_tc5;  // tcgen05 operand images (nullptr where the block is not eligible); w3 in the form launch_block_tc5 variant 1 expects
+    std::vector<uint8_t *> d_blk_tc5u; // the same with the plain 27-slice w3 (sequential / decoupled / chained forms): == d_blk_tc5[i] unless that one is packed
     std::vector<uint8_t *> d_blk_rs;   // row-streaming tcgen05 operand images (wdsr_rs.cuh), same eligibility
     int block_impl = 0;                // 0 = mma.sync kernel, 1 = tcgen05 sequential form, 2 = tcgen05 tile form, 3 = tcgen05 row-streaming form, 4 = row-streaming with the reduce on mma.sync (wdsr_rh.cuh)
     float *d_tail_f32 = nullptr;
@@ -106,11 +107,13 @@ struct b200sr_wdsr {
         if (d_head) cudaFree(d_head), d_head = nullptr;
         for (auto p : d_blk_f32) cudaFree(p);
         for (auto p : d_blk_bf16) cudaFree(p);
+        for (size_t i = 0; i < d_blk_tc5u.size(); ++i)
+            if (d_blk_tc5u[i] && d_blk_tc5u[i] != d_blk_tc5[i]) cudaFree(d_blk_tc5u[i]);
         for (auto p : d_blk_tc5)
             if (p) cudaFree(p);
         for (auto p : d_blk_rs)
             if (p) cudaFree(p);
-        d_blk_f32.clear(), d_blk_bf16.clear(), d_blk_tc5.clear(), d_blk_rs.clear();
+        d_blk_f32.clear(), d_blk_bf16.clear(), d_blk_tc5.clear(), d_blk_tc5u.clear(), d_blk_rs.clear();
         if (d_tail_f32) cudaFree(d_tail_f32), d_tail_f32 = nullptr;
         if (d_tail_bf16) cudaFree(d_tail_bf16), d_tail_bf16 = nullptr;
         if (d_tail_tc5) cudaFree(d_tail_tc5), d_tail_tc5 = nullptr;
@@ -291,19 +294,39 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
                 for (int m = 0; m < M1; ++m)
                     at(L.w2 + (j / 8) * L.sbo2 + (m / 8) * 128 + (j % 8) * 16)[m % 8] = f2bf(k.w2[(size_t)j * M1 + m]);
             const int NC2 = (M2 + 7) / 8;   // 8-channel chunks of t2 (3 dense; pruned blocks skip the 3x3 MMAs of absent chunks)
-            for (int o = 0; o < C; ++o)
-                for (int j = 0; j < M2; ++j)
-                    for (int dy = 0; dy < 3; ++dy)
-                        for (int dx = 0; dx < 3; ++dx) {
-                            const int q = (dx * 3 + dy) * NC2 + j / 8;   // only the (tap, chunk) slices t2 really has
-                            at(L.w3 + (o / 8) * (28 * 128) + q * 128 + (o % 8) * 16)[j % 8] = f2bf(k.w3[((size_t)o * M2 + j) * 9 + dy * 3 + dx]);
-                        }
+            auto pack_w3 = [&](bool packed) {   // (re)writes the w3 region
+                memset(img.data() + L.w3, 0, (size_t)4 * 28 * 128);
+                for (int o = 0; o < C; ++o)
+                    for (int j = 0; j < M2; ++j)
+                        for (int dy = 0; dy < 3; ++dy)
+                            for (int dx = 0; dx < 3; ++dx) {
+                                int q, kk;
+                                if (packed && j >= 16) {
+                                    // last chunk (channels 16..19) packed two horizontal taps per K = 8 half (wdsr_tc5p.cuh, NC2 = 4): slice 18 + 2 dy
+                                    // = [tap dx 0 | tap dx 1], slice 19 + 2 dy = [tap dx 2 | zero]
+                                    q = 18 + 2 * dy + (dx == 2 ? 1 : 0);
+                                    kk = (j - 16) + (dx == 1 ? 4 : 0);
+                                } else if (packed) {
+                                    q = (dx * 3 + dy) * 2 + j / 8, kk = j % 8;
+                                } else {
+                                    q = (dx * 3 + dy) * NC2 + j / 8, kk = j % 8;   // only the (tap, chunk) slices t2 really has
+                                }
+                                at(L.w3 + (o / 8) * (28 * 128) + q * 128 + (o % 8) * 16)[kk] = f2bf(k.w3[((size_t)o * M2 + j) * 9 + dy * 3 + dx]);
+                            }
+            };
+            pack_w3(false);
             float *b2 = (float *)(img.data() + L.b2), *b3 = (float *)(img.data() + L.b3);
             for (int j = 0; j < M2; ++j) b2[j] = k.b2[j];
             b2[31] = (float)NC2;   // informational (the launcher derives the same count from M2 and picks the kernel instantiation)
             for (int o = 0; o < C; ++o) b3[o] = k.b3[o];
             uint8_t *d = nullptr;
             if ((rc = upload(img.data(), img.size(), (void **)&d))) return rc;
+            p->d_blk_tc5u.push_back(d);
+            if (block_tc5_g3_packed(M2)) {   // the tile form's packed 3x3 (12 instead of 14 MMAs per M-tile) reads its own image
+                pack_w3(true);
+                d = nullptr;
+                if ((rc = upload(img.data(), img.size(), (void **)&d))) return rc;
+            }
             p->d_blk_tc5.push_back(d);
             std::vector<uint8_t> rimg;   // row-streaming form: same w1 / w2 images, the 3x3 with dy stacked in N (wdsr_rs_pack.h)
             pack_block_rs(rimg, C, M1, M2, M1P, k.w1.data(), k.b1.data(), k.w2.data(), k.b2.data(), k.w3.data(), k.b3.data());
@@ -312,6 +335,7 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
             p->d_blk_rs.push_back(d);
         } else {
             p->d_blk_tc5.push_back(nullptr);
+            p->d_blk_tc5u.push_back(nullptr);
             p->d_blk_rs.push_back(nullptr);
         }
     }
@@ -465,9 +489,10 @@ int b200sr_wdsr_block(const b200sr_wdsr_t *p, int i, const void *tin, void *tout
     else if (p->tc5_path() && p->block_impl == 4 && block_rs_eligible(n, h, w))
         CU(launch_block_rh(tin, tout, p->d_blk_rs[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
     else if (p->tc5_path())
-        CU(launch_block_tc5(p->block_impl == 5 ? 2 : 1, tin, tout, p->d_blk_tc5[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
+        CU(launch_block_tc5(p->block_impl == 5 ? 2 : 1, tin, tout, p->block_impl == 5 ? p->d_blk_tc5u[i] : p->d_blk_tc5[i], p->m1p[i], p->m2[i], n, h, w,
+                            (cudaStream_t)stream));
     else if (p->block_impl == 1 && p->d_blk_tc5[i] && p->m2[i] > 16)   // sequential tcgen05 reference form (NHWC trunk, all 27 w3 slices; developer switch)
-        CU(launch_block_tc5(0, tin, tout, p->d_blk_tc5[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
+        CU(launch_block_tc5(0, tin, tout, p->d_blk_tc5u[i], p->m1p[i], p->m2[i], n, h, w, (cudaStream_t)stream));
     else
         CU(launch_block_bf16(p->cp, p->m2p_bf16[i], tin, tout, p->d_blk_bf16[i], p->m1p[i], n, h, w, (cudaStream_t)stream));
     return 0;
@@ -510,7 +535,7 @@ int b200sr_wdsr_forward(const b200sr_wdsr_t *p, const void *x, int x_dtype, void
         bool uniform = true;
         for (int i = 0; i < p->nb; ++i) uniform = uniform && p->d_blk_tc5[i] && p->m1p[i] == p->m1p[0] && p->m2[i] == p->m2[0];
         if (uniform) {
-            CU(launch_block_chain_tc5(a, b, p->d_blk_tc5.data(), p->nb, (unsigned *)((uint8_t *)ws + 2 * trunk), p->m1p[0], p->m2[0], n, h, w,
+            CU(launch_block_chain_tc5(a, b, p->d_blk_tc5u.data(), p->nb, (unsigned *)((uint8_t *)ws + 2 * trunk), p->m1p[0], p->m2[0], n, h, w,
                                       (cudaStream_t)stream));
             launches += 2;   // the counter's memset node + the kernel
             if (p->nb & 1) a = b;

@@ -35,6 +35,9 @@ cudaError_t launch_block_f32(int CP, int M2P, const float *in, float *out, const
 cudaError_t launch_block_bf16(int CP, int M2P, const void *in, void *out, const uint8_t *wimg, int M1P, int N, int H, int W,
                               cudaStream_t st);
 // tcgen05 form of the fused block (CP == 24, M2 <= 24): variant 0 = sequential reference form, 1 = pipelined
+// true when launch_block_tc5(variant 1) runs the packed 3x3 for this reduce width (M2 = 17..20; B200SR_G3_NOPACK=1 switches it off): the operand
+// image must then carry the packed w3
+bool block_tc5_g3_packed(int M2);
 cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8_t *wimg, int M1P, int M2, int N, int H, int W,
                              cudaStream_t st);
 // every block of a run of same-shaped blocks in one persistent cooperative launch (wdsr_tc5c.cuh); gsync: 4 bytes of device memory

@@ -1,6 +1,8 @@
 // wdsr_tc5_block.cu -- launchers of the tcgen05 fused residual-block kernels.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include <mutex>
 
 #include "launch.h"
@@ -11,6 +13,11 @@
 #include "tma_map.h"
 
 namespace b200sr {
+
+bool block_tc5_g3_packed(int M2) {
+    static const bool off = [] { const char *e = getenv("B200SR_G3_NOPACK"); return e && e[0] == '1'; }();   // developer A/B switch
+    return !off && M2 > 16 && M2 <= 20;
+}
 
 cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8_t *wimg, int M1P, int M2, int N, int H, int W,
                              cudaStream_t st) {
@@ -49,13 +56,14 @@ cudaError_t launch_block_tc5(int variant, const void *in, void *out, const uint8
     const bool q2 = q && M1P <= 128;
     auto kern = q2 ? (nc2 == 3 ? wdsr_block_tc5q_kernel<3, 2> : nc2 == 2 ? wdsr_block_tc5q_kernel<2, 2> : wdsr_block_tc5q_kernel<1, 2>)
                 : q ? (nc2 == 3 ? wdsr_block_tc5q_kernel<3, 1> : nc2 == 2 ? wdsr_block_tc5q_kernel<2, 1> : wdsr_block_tc5q_kernel<1, 1>)
-                    : (nc2 == 3 ? wdsr_block_tc5p_kernel<3> : nc2 == 2 ? wdsr_block_tc5p_kernel<2> : wdsr_block_tc5p_kernel<1>);
+                    : (nc2 == 3 ? (block_tc5_g3_packed(M2) ? wdsr_block_tc5p_kernel<4> : wdsr_block_tc5p_kernel<3>)
+                                : nc2 == 2 ? wdsr_block_tc5p_kernel<2> : wdsr_block_tc5p_kernel<1>);
     const size_t smem = tc5v3::smem_bytes(M1P);
     static_assert(tc5v3::CTRL_BYTES == tc5v4::CTRL_BYTES, "the two forms share one shared-memory layout");
-    static thread_local size_t smem_set[64][9] = {};
+    static thread_local size_t smem_set[64][10] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const int ki = nc2 - 1 + (q2 ? 6 : q ? 3 : 0);
+    const int ki = (!q && nc2 == 3 && block_tc5_g3_packed(M2)) ? 9 : nc2 - 1 + (q2 ? 6 : q ? 3 : 0);
     if (dev < 0 || dev >= 64 || smem_set[dev][ki] < smem) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

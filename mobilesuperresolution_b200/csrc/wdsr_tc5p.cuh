@@ -81,6 +81,9 @@ constexpr int CTRL_BYTES = 256;  // 22 mbarriers (176 B) + tmem base pointer at 
 constexpr size_t smem_bytes(int M1P) { return (size_t)tc5v3::CTRL_BYTES + XS_BYTES_ALL + T2_BYTES + (size_t)BlockTc5Layout(M1P).total; }
 }  // namespace tc5v3
 
+// NC2 = 4: three chunks whose last one holds <= 4 channels (M2 = 17..20, the dense block), "packed": the two copies of that chunk hold
+//          [pixel | right neighbour] x 4 channels per 16-byte entry, so two horizontal taps share one K = 8 half and the 3x3 is 24 slices =
+//          12 MMAs per M-tile instead of 27 slices = 14 (the operand image must be the packed one: b200sr.cu, pack_w3_tc5).
 // NC2 = 8-channel chunks of t2 the block really has (3 dense; 2 / 1 for pruned M2 <= 16 / <= 8): the host packs only those
 // (tap, chunk) slices of w3 (b200sr.cu) and the 3x3 issues 14 / 9 / 5 MMAs.  A template parameter, not a run-time value: the
 // dense instantiation is then exactly the code that was tuned (a run-time switch cost it 3-5 %).
@@ -89,6 +92,8 @@ __global__ void __launch_bounds__(tc5v3::NTHREADS, 1)
 wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *__restrict__ in, bf16 *__restrict__ out,
                        const uint8_t *__restrict__ wimg, int M1P, int N, int H, int W, int tiles_x, int tiles_y, int ntiles) {
     using namespace tc5v3;
+    constexpr bool PK = NC2 == 4;            // packed last chunk
+    constexpr int NCH = PK ? 3 : NC2;        // chunks E2 produces
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const BlockTc5Layout L(M1P);
     uint8_t *ctrl = smem_raw;
@@ -158,7 +163,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
     for (int i = tid; i < XS_PLANE / 16; i += NTHREADS)                       // constant-one plane: 1.0 in channels 0,1
         *reinterpret_cast<uint4 *>(xs + XS_ONE + i * 16) = make_uint4(0x3F803F80u, 0u, 0u, 0u);
     for (int i = tid; i < 16; i += NTHREADS) *reinterpret_cast<uint4 *>(t2 + 3 * T2_COPY + i * 16) = make_uint4(0u, 0u, 0u, 0u);
-    if (NC2 < 3)   // a pruned block never writes the absent chunks, and the zero-weight dummy half of its last 3x3 instruction reads
+    if (NCH < 3)   // a pruned block never writes the absent chunks, and the zero-weight dummy half of its last 3x3 instruction reads
                    // one chunk past the last slice: t2 must start as zeros (the dense block pays nothing)
         for (int i = tid; i < T2_BYTES / 16; i += NTHREADS) *reinterpret_cast<uint4 *>(t2 + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     cp_async_wait<0>();
@@ -262,7 +267,13 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
         const uint64_t bw3 = tc5::smem_desc(w_u + L.w3, 128, 28 * 128);
         const uint64_t at0 = tc5::smem_desc(t2_u, 0, T2_GROUP);    // LBO added per instruction
         auto issue_g3_nc = [&](int k, auto ncc) {  // leader only; NC = chunks of t2 (3 dense; 2 or 1 for pruned M2 <= 16 / <= 8)
-            constexpr int NC = decltype(ncc)::value, NS = 9 * NC, NM = (NS + 1) / 2;
+            constexpr int NCX = decltype(ncc)::value;
+            constexpr bool PKX = NCX == 4;
+            constexpr int NC = PKX ? 2 : NCX, NS = PKX ? 24 : 9 * NC, NM = (NS + 1) / 2;
+            // slice address: q < 9 NC: (dx, dy, chunk) = (q / (3 NC), (q / NC) % 3, q % NC); packed: slices 18 + 2 dy + w = chunk 2 of copy 0 (w = 0:
+            // taps dx 0 | 1) or of copy 2 (w = 1: tap dx 2 | zero weights) at row dy
+            auto sl = [](int q) constexpr { return q < 9 * NC ? (q / (3 * NC)) * T2_COPY + ((q / NC) % 3) * T2_ROW + (q % NC) * 128
+                                                            : ((q - 18) % 2 ? 2 : 0) * T2_COPY + ((q - 18) / 2) * T2_ROW + 2 * 128; };
             const uint64_t abase = at0 + (uint64_t)((k * 4 * T2_ROW) >> 4);
             const uint32_t d3 = tmem + d3_col(k);
 #ifdef B200SR_EXP_G3SHORT
@@ -273,8 +284,8 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
 #pragma unroll
             for (int i = 0; i < NG3; ++i) {   // slice q = (dx * 3 + dy) * NC + chunk, two slices per K = 16 instruction through LBO
                 const int q0 = 2 * i, q1 = 2 * i + 1;
-                const int a0 = (q0 / (3 * NC)) * T2_COPY + ((q0 / NC) % 3) * T2_ROW + (q0 % NC) * 128;
-                const int a1 = q1 < NS ? (q1 / (3 * NC)) * T2_COPY + ((q1 / NC) % 3) * T2_ROW + (q1 % NC) * 128 : a0 + 128;
+                const int a0 = sl(q0);
+                const int a1 = q1 < NS ? sl(q1) : a0 + 128;
                 tc5::mma_ss(d3, abase + (uint64_t)(a0 >> 4) + ((uint64_t)((a1 - a0) >> 4) << 16), bw3 + (uint64_t)(16 * i), idesc32,
                             i > 0);
             }
@@ -453,10 +464,10 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
 #else
             if (p < HP) {
 #endif
-                uint4 c[NC2];   // only the chunks this block has (compile-time sized: a partly used array went to local memory)
+                uint4 c[NCH];   // only the chunks this block has (compile-time sized: a partly used array went to local memory)
                 uint32_t *cw = reinterpret_cast<uint32_t *>(c);
 #pragma unroll
-                for (int j4 = 0; j4 < 2 * NC2; ++j4) {
+                for (int j4 = 0; j4 < 2 * NCH; ++j4) {
                     const float4 bb = *reinterpret_cast<const float4 *>(b2s + 4 * j4);  // broadcast read
                     cw[2 * j4] = ok ? pack_bf16x2(__uint_as_float(v[4 * j4]) + bb.x, __uint_as_float(v[4 * j4 + 1]) + bb.y) : 0u;
                     cw[2 * j4 + 1] = ok ? pack_bf16x2(__uint_as_float(v[4 * j4 + 2]) + bb.z, __uint_as_float(v[4 * j4 + 3]) + bb.w) : 0u;
@@ -467,7 +478,10 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                     if (xi >= 0 && xi < TW) {
                         uint8_t *dst = t2 + d * T2_COPY + r * T2_ROW + (xi >> 3) * T2_GROUP + (xi & 7) * 16;
 #pragma unroll
-                        for (int q = 0; q < NC2; ++q) *reinterpret_cast<uint4 *>(dst + q * 128) = c[q];
+                        for (int q = 0; q < (PK ? 2 : NCH); ++q) *reinterpret_cast<uint4 *>(dst + q * 128) = c[q];
+                        if (PK && d == 0) *reinterpret_cast<uint2 *>(dst + 2 * 128) = make_uint2(cw[8], cw[9]);            // own 4 channels: low half, taps dx 0
+                        if (PK && d == 1) *reinterpret_cast<uint2 *>(dst - 1 * T2_COPY + 2 * 128 + 8) = make_uint2(cw[8], cw[9]);   // copy 0, slot hx - 1: high half, tap dx 1
+                        if (PK && d == 2) *reinterpret_cast<uint4 *>(dst + 2 * 128) = make_uint4(cw[8], cw[9], 0u, 0u);    // copy 2, slot hx - 2: tap dx 2 | zero weights
                     }
                 }
             }

@@ -301,10 +301,12 @@ def test_row_streaming_model_graph_replay_is_deterministic(sr, form, monkeypatch
 
 
 @pytest.mark.parametrize("nb,scale,shape", [(1, 4, (1, 3, 16, 32)), (2, 2, (2, 3, 37, 45)), (5, 2, (1, 3, 131, 200)), (16, 4, (4, 3, 96, 96))])
-def test_chained_block_launch_is_bit_identical(sr, nb, scale, shape, monkeypatch):
+def test_chained_block_launch_matches_the_per_block_forward(sr, nb, scale, shape, monkeypatch):
     """All residual blocks in one persistent cooperative launch with a grid-wide layer barrier (csrc/wdsr_tc5c.cuh, B200SR_BLOCK_IMPL=chain):
-    the same tiles through the same pipeline, so the output must equal the one-launch-per-block forward bit for bit -- odd and even block
-    counts (the result lands in either ping-pong buffer), one-tile-per-CTA grids (every tile is a layer boundary), eager and graph replay."""
+    the same tiles through the same pipeline as the one-launch-per-block forward -- odd and even block counts (the result lands in either
+    ping-pong buffer), one-tile-per-CTA grids (every tile is a layer boundary), eager and graph replay (bit-identical to itself).  Against
+    the per-block forward: equal up to the fp32 summation order of the 3x3 (the tile form packs its K into 12 MMAs per M-tile, the chained
+    kernel keeps the 27-slice form), i.e. a couple of bf16 ulps after each block."""
     outs = {}
     for impl in ("tc5", "chain"):
         monkeypatch.setenv("B200SR_BLOCK_IMPL", impl)
@@ -317,7 +319,11 @@ def test_chained_block_launch_is_bit_identical(sr, nb, scale, shape, monkeypatch
             g = sr.Graphed(m, x)
             assert torch.equal(g(x), y) and torch.equal(g(x), y)
         outs[impl] = y
-    assert torch.equal(outs["tc5"], outs["chain"])
+    a, b = outs["tc5"].float(), outs["chain"].float()
+    d = (a - b).abs()
+    from oracle import port
+    assert float(d.max()) <= 2 ** -5 * max(1.0, float(a.abs().max())) * max(1, nb // 4)
+    assert port.psnr_db(b, a) >= 55.0          # ulp flips accumulate over the blocks; a misplaced 3x3 slice would be ~20 dB
 
 
 # ------------------------------------------------------------------------------------------------ our own memcheck / racecheck
