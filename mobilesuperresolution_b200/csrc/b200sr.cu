@@ -616,7 +616,27 @@ int b200sr_flow_warp_nhwc_windows(const void *x, int x_cs, int x_co, const float
 struct b200sr_split {
     int c = 0;
     std::vector<float> params;   // packed image, passed to the kernel by value (constant bank)
+    std::vector<uint8_t> tc;     // parameter image of the bf16 tensor-core arm (split_block_tc.cu), derived from params ...
+    void *d_tc = nullptr;        // ... and its copy in device memory (the device that was current at b200sr_split_create)
 };
+
+static int split_upload_tc(b200sr_split *b) {
+    split_tc_pack(b->c, b->params.data(), b->tc);
+    if (b->tc.empty()) return 0;
+    if (!b->d_tc) CU(cudaMalloc(&b->d_tc, b->tc.size()));
+    CU(cudaMemcpy(b->d_tc, b->tc.data(), b->tc.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// bf16 tensors with 16-byte rows take the tensor-core arm; B200SR_SPLIT_IMPL=ffma keeps the fp32-FFMA kernel (developer switch)
+static cudaError_t run_split(const b200sr_split *b, int dtype, const void *x, void *y, int n, int h, int w, cudaStream_t st) {
+    static const bool ffma_only = [] {
+        const char *e = getenv("B200SR_SPLIT_IMPL");
+        return e && !strcmp(e, "ffma");
+    }();
+    if (!ffma_only && b->d_tc && split_tc_eligible(dtype, x, y, w)) return launch_split_block_tc(b->c, x, y, (const uint8_t *)b->d_tc, n, h, w, st);
+    return launch_split_block(b->c, dtype, x, y, b->params.data(), n, h, w, st);
+}
 
 int b200sr_split_create(int C, const float *dw3, const float *dw5, const float *dw7, const float *dwb, const float *pw, const float *pwb,
                         const float *e, const float *prob, b200sr_split_t **out) {
@@ -641,11 +661,16 @@ int b200sr_split_create(int C, const float *dw3, const float *dw5, const float *
     if (!b) return fail(B200SR_E_INVAL, "split_create: out of memory");
     b->c = C;
     b->params.swap(f);
+    if (int rc = split_upload_tc(b)) {
+        b200sr_split_destroy(b);
+        return rc;
+    }
     *out = b;
     return 0;
 }
 
 void b200sr_split_destroy(b200sr_split_t *b) {
+    if (b && b->d_tc) cudaFree(b->d_tc);
     delete b;
 }
 
@@ -653,7 +678,7 @@ int b200sr_split_set_premask(b200sr_split_t *b, const float *g) {
     if (!b) return fail(B200SR_E_INVAL, "split_set_premask: null block");
     float *q = b->params.data() + b->params.size() - b->c;
     for (int c = 0; c < b->c; ++c) q[c] = g ? g[c] : 1.f;
-    return 0;
+    return split_upload_tc(b);   // (synchronous copy: call outside stream capture, before the forward that uses it)
 }
 
 size_t b200sr_nas_workspace_bytes(const b200sr_wdsr_t *p, int n, int h, int w, int precision) {
@@ -684,7 +709,7 @@ int b200sr_nas_forward(const b200sr_wdsr_t *p, const b200sr_split_t *const *bloc
     if (nblocks > 0) {   // the Split_Block kernel works on NCHW planes (depthwise convolutions): two layout changes per forward
         CU(launch_trunk_convert(trunk, tl, a, 2, precision, n, p->cin, p->cp, h, w, st));
         for (int i = 0; i < nblocks; ++i) {
-            CU(launch_split_block(p->cin, precision, a, b, blocks[i]->params.data(), n, h, w, st));
+            CU(run_split(blocks[i], precision, a, b, n, h, w, st));
             uint8_t *t = a;
             a = b, b = t;
         }
@@ -701,7 +726,7 @@ int b200sr_split_forward(const b200sr_split_t *b, const void *x, void *y, int n,
     if (x == y) return fail(B200SR_E_INVAL, "split_forward: x and y must be distinct buffers (a CTA reads a 3-pixel halo that its neighbours overwrite)");
     if (n <= 0 || h <= 0 || w <= 0) return fail(B200SR_E_INVAL, "split_forward: bad shape");
     if (dtype != B200SR_F32 && dtype != B200SR_BF16) return fail(B200SR_E_INVAL, "split_forward: bad dtype %d", dtype);
-    cudaError_t e = launch_split_block(b->c, dtype, x, y, b->params.data(), n, h, w, (cudaStream_t)stream);
+    cudaError_t e = run_split(b, dtype, x, y, n, h, w, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "split_forward");
     return 0;
 }

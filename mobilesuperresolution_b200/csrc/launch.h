@@ -1,5 +1,6 @@
 // launch.h -- internal launcher interface between the C-ABI (b200sr.cu) and the kernel translation units.
 #pragma once
+#include <vector>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -78,6 +79,11 @@ cudaError_t launch_conv7x7_tc5(const ConvArgs &a, const uint8_t *wimg, cudaStrea
 // travels as a kernel argument), C in {8,16,24,32}
 int split_param_floats(int C);
 cudaError_t launch_split_block(int C, int dtype, const void *x, void *y, const float *params, int N, int H, int W, cudaStream_t st);
+// bf16 arm with the 1x1 convolutions on mma.sync (split_block_tc.cu): image = HOST pointer to the kernel-argument image that
+// split_tc_pack derives from the packed float image; eligible: bf16 tensors, W % 8 == 0, 16-byte aligned pointers
+void split_tc_pack(int C, const float *packed, std::vector<uint8_t> &out);
+bool split_tc_eligible(int dtype, const void *x, const void *y, int W);
+cudaError_t launch_split_block_tc(int C, const void *x, void *y, const uint8_t *image, int N, int H, int W, cudaStream_t st);
 // trunk layout conversion (video_glue.cu): layouts 0 = NHWC, 1 = planar-8, 2 = NCHW (c of cp channels)
 cudaError_t launch_trunk_convert(const void *src, int src_layout, void *dst, int dst_layout, int dtype, int n, int c, int cp, int h, int w, cudaStream_t st);
 cudaError_t launch_deconv_tail_resize_add(const void *t, int t_dtype, int cs, const void *img, int img_dtype, long long img_nstride, float *y,
