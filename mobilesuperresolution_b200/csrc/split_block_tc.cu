@@ -14,7 +14,8 @@
 //   * the filter taps are broadcast LDS.128 reads of a shared-memory copy (a register-indexed constant-bank read, LDC, per tap was
 //     what bound both kernels: the channel a warp works on is a run-time value); the folded parameters live in a device-memory
 //     image (SplitTcImage) instead of travelling as an 18 KB kernel argument;
-//   * the halo tile is staged with 8-byte loads (4 pixels) and the result leaves through shared memory as 16-byte stores.
+//   * persistent CTAs: the raw bf16 halo tile of the next work item streams in with cp.async while this one is computed (e * g
+//     is folded into the taps), and the result leaves through shared memory as 16-byte stores.
 // Tensors are the reference's NCHW in bf16.  W must be a multiple of 8 (16-byte rows); b200sr.cu routes everything else to
 // split_block.cu.
 #include <cstring>
@@ -26,128 +27,145 @@
 namespace b200sr {
 
 namespace splittc {
-constexpr int TW = 32, TH = 8, HALO = 3, SH = TH + 2 * HALO, SWU = 40, SWP = 44, NTHREADS = 256;   // xs column j <-> gx = x0 - 4 + j; SWU
-// columns used, pitch SWP: the 8 lanes of a quarter-warp (two tile rows x four 8-pixel segments) then read 8 distinct 16-byte bank groups
+constexpr int TW = 32, TH = 8, HALO = 3, SH = TH + 2 * HALO, SWP = 40, NTHREADS = 256;   // staged column j <-> gx = x0 - 4 + j
+constexpr int XR_ROW = SWP * 2;     // bytes per staged row (bf16)
 constexpr int TAPF = 112;           // floats per channel of the tap image: w7 rows padded to 8 (56) | w5 rows padded to 8 (40) | w3 rows padded to 4 (12) | b3 b5 b7 0
 constexpr int DS_PITCH = 528;       // bytes per channel row of relu(DW_k): 256 px bf16 + 16 (ldmatrix rows land in distinct bank groups)
 constexpr int ST_PITCH = 260;       // floats per channel row of the staged branch sum (conflict-free fragment writes)
-__host__ __device__ constexpr int kregs(int C) { return C / 8; }       // B-fragment registers per n-tile: k16 steps take 2, a k8 step 1
-__host__ __device__ constexpr size_t xs_bytes(int C) { return (size_t)C * SH * SWP * 4; }
+__host__ __device__ constexpr size_t xr_bytes(int C) { return (size_t)C * SH * XR_ROW; }
 __host__ __device__ constexpr size_t ds_bytes(int C) { return (size_t)3 * C * DS_PITCH; }
 __host__ __device__ constexpr size_t tap_bytes(int C) { return (size_t)C * TAPF * 4; }
-__host__ __device__ constexpr size_t smem_bytes(int C) { return xs_bytes(C) + ds_bytes(C) + tap_bytes(C) + (size_t)2 * C * 4; }
+__host__ __device__ constexpr size_t smem_bytes(int C) { return 2 * xr_bytes(C) + ds_bytes(C) + tap_bytes(C) + (size_t)2 * C * 4; }
 }  // namespace splittc
 
 template <int C> struct SplitTcImage {       // device memory, every member a multiple of 16 bytes
-    float taps[C * splittc::TAPF];
+    float taps[C * splittc::TAPF];            // depthwise taps PRE-MULTIPLIED by e * g of their channel (DW_k is linear in x1 = e * g * x), biases plain
     float eg[2 * C];                          // e[C] | g[C]
     uint32_t bfrag[3][C / 8][C / 8][32];      // [branch][n-tile][register][lane]
     float pwb[3 * C];
     float p[4];
 };
 
+// Persistent CTAs (two per SM for C <= 24): the raw bf16 halo tile of the NEXT work item streams into the other staging buffer with
+// cp.async (8-byte pieces, zero-filled outside the image = the convolutions' padding) while this one is computed; the first form staged
+// with plain loads and spent 46 % of its stall samples waiting for them (profiles/r02_split_block_tc_ncu.md).
 template <int C>
 __global__ void __launch_bounds__(splittc::NTHREADS, (C <= 24 ? 2 : 1))
 split_block_tc_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, const SplitTcImage<C> *__restrict__ img, int N, int H, int W,
-                      int tiles_x, int tiles_y) {
+                      int tiles_x, int tiles_y, int ntiles) {
     using namespace splittc;
     constexpr int NT = C / 8;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    float *xs = reinterpret_cast<float *>(smem_raw);               // [C][SH][SWP]  x1 = e * g * x, zero outside the image
-    uint8_t *ds = smem_raw + xs_bytes(C);                          // [3][C][DS_PITCH]  relu(DW_k(x1)) as bf16
+    uint8_t *xr = smem_raw;                                        // [2][C][SH][SWP] bf16: g-less, e-less x, zero outside the image
+    uint8_t *ds = smem_raw + 2 * xr_bytes(C);                      // [3][C][DS_PITCH]  relu(DW_k(x1)) as bf16
     float *taps = reinterpret_cast<float *>(ds + ds_bytes(C));     // [C][TAPF]
     float *eg = taps + C * TAPF;                                   // e[C] | g[C]
-    float *st = xs;                                                // [C][ST_PITCH]  branch sum (aliases xs once the depthwise pass is done)
+    float *st = reinterpret_cast<float *>(ds);                     // [C][ST_PITCH]  branch sum (aliases ds once every warp's MMAs have read it)
+    static_assert((size_t)C * ST_PITCH * 4 <= ds_bytes(C), "st must fit into ds");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
-    const int x0 = (tile % tiles_x) * TW, y0 = ((tile / tiles_x) % tiles_y) * TH, n = tile / (tiles_x * tiles_y);
     const long long plane = (long long)H * W;
-    const bf16 *xn = x + (long long)n * C * plane;
 
+    auto origin = [&](int tile, int &x0, int &y0, int &n) {
+        x0 = (tile % tiles_x) * TW, y0 = ((tile / tiles_x) % tiles_y) * TH, n = tile / (tiles_x * tiles_y);
+    };
+    auto prefetch = [&](int tile, int buf) {   // item = (channel, halo row, 4-pixel piece); W % 4 == 0: a piece is entirely inside or outside
+        int x0, y0, n;
+        origin(tile, x0, y0, n);
+        const bf16 *xn = x + (long long)n * C * plane;
+        const uint32_t dst0 = smem_u32(xr + buf * xr_bytes(C));
+        for (int i = tid; i < C * SH * (SWP / 4); i += NTHREADS) {
+            const int h = i % (SWP / 4), rc = i / (SWP / 4), r = rc % SH, c = rc / SH;
+            const int gy = y0 - HALO + r, gx = x0 - 4 + 4 * h;
+            const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+            const bf16 *src = in ? xn + c * plane + (long long)gy * W + gx : x;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst0 + (uint32_t)(rc * XR_ROW + 8 * h)), "l"(src), "r"(in ? 8 : 0));
+        }
+        cp_async_commit();
+    };
+
+    int tile = blockIdx.x;
+    if (tile < ntiles) prefetch(tile, 0);
     for (int i = tid; i < C * TAPF / 4 + 2 * C / 4; i += NTHREADS)      // taps | e | g are contiguous in the image and in shared memory
         reinterpret_cast<float4 *>(taps)[i] = __ldg(reinterpret_cast<const float4 *>(img->taps) + i);
-    __syncthreads();
-    // ---- stage the halo tile: item = (channel, halo row, 4-pixel chunk); W % 4 == 0 makes a chunk entirely inside or outside
-#pragma unroll 4
-    for (int i = tid; i < C * SH * (SWU / 4); i += NTHREADS) {
-        const int h = i % (SWU / 4), r = (i / (SWU / 4)) % SH, c = i / ((SWU / 4) * SH);
-        const int gy = y0 - HALO + r, gx = x0 - 4 + 4 * h;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            const uint2 raw = *reinterpret_cast<const uint2 *>(xn + c * plane + (long long)gy * W + gx);
-            const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
-            const float gm = eg[C + c], em = eg[c];
-            v = make_float4((a.x * gm) * em, (a.y * gm) * em, (b.x * gm) * em, (b.y * gm) * em);
-        }
-        *reinterpret_cast<float4 *>(xs + (c * SH + r) * SWP + 4 * h) = v;
-    }
-    __syncthreads();
 
-    // ---- depthwise 3x3 + 5x5 + 7x7 in one pass: a warp takes the 32 items of one channel (filter taps are warp-uniform)
-    {
-        const int r = lane >> 2, g4 = lane & 3;
+    for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+        const int cur = it & 1;
+        int x0, y0, n;
+        origin(tile, x0, y0, n);
+        cp_async_wait<0>();
+        __syncthreads();     // this tile's staging buffer is complete; the previous tile's final stage is over (other buffer and ds are free)
+        if (tile + (int)gridDim.x < ntiles) prefetch(tile + gridDim.x, cur ^ 1);
+        const uint8_t *xc = xr + cur * xr_bytes(C);
+
+        // ---- depthwise 3x3 + 5x5 + 7x7 in one pass: a warp takes the 32 items of one channel (filter taps are warp-uniform)
+        {
+            const int r = lane >> 2, g4 = lane & 3;
 #pragma unroll 1
-        for (int c = warp; c < C; c += NTHREADS / 32) {
-            float a3[8], a5[8], a7[8];
-            const float4 *tp = reinterpret_cast<const float4 *>(taps + c * TAPF);   // warp-uniform addresses: broadcast reads
-            {
-                const float4 b = tp[27];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) a3[j] = b.x, a5[j] = b.y, a7[j] = b.z;
-            }
-            const float *xp = xs + (c * SH + r) * SWP + 8 * g4;
-#pragma unroll
-            for (int ky = 0; ky < 7; ++ky) {
-                float v[16];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 t = *reinterpret_cast<const float4 *>(xp + ky * SWP + 4 * q);
-                    v[4 * q] = t.x, v[4 * q + 1] = t.y, v[4 * q + 2] = t.z, v[4 * q + 3] = t.w;
-                }
-                float w7[8], w5[8], w3[4];
+            for (int c = warp; c < C; c += NTHREADS / 32) {
+                float a3[8], a5[8], a7[8];
+                const float4 *tp = reinterpret_cast<const float4 *>(taps + c * TAPF);   // warp-uniform addresses: broadcast reads
                 {
-                    const float4 p0 = tp[2 * ky], p1 = tp[2 * ky + 1];
-                    w7[0] = p0.x, w7[1] = p0.y, w7[2] = p0.z, w7[3] = p0.w, w7[4] = p1.x, w7[5] = p1.y, w7[6] = p1.z, w7[7] = p1.w;
-                    if (ky >= 1 && ky <= 5) {
-                        const float4 q0 = tp[14 + 2 * (ky - 1)], q1 = tp[15 + 2 * (ky - 1)];
-                        w5[0] = q0.x, w5[1] = q0.y, w5[2] = q0.z, w5[3] = q0.w, w5[4] = q1.x, w5[5] = q1.y, w5[6] = q1.z, w5[7] = q1.w;
+                    const float4 b = tp[27];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a3[j] = b.x, a5[j] = b.y, a7[j] = b.z;
+                }
+                const uint8_t *xp = xc + (c * SH + r) * XR_ROW + 16 * g4;
+#pragma unroll
+                for (int ky = 0; ky < 7; ++ky) {
+                    float v[16];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const uint4 t = *reinterpret_cast<const uint4 *>(xp + ky * XR_ROW + 16 * q);
+                        const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            v[8 * q + 2 * j] = __uint_as_float(tw[j] << 16);
+                            v[8 * q + 2 * j + 1] = __uint_as_float(tw[j] & 0xffff0000u);
+                        }
                     }
-                    if (ky >= 2 && ky <= 4) {
-                        const float4 q = tp[24 + (ky - 2)];
-                        w3[0] = q.x, w3[1] = q.y, w3[2] = q.z, w3[3] = q.w;
+                    float w7[8], w5[8], w3[4];
+                    {
+                        const float4 p0 = tp[2 * ky], p1 = tp[2 * ky + 1];
+                        w7[0] = p0.x, w7[1] = p0.y, w7[2] = p0.z, w7[3] = p0.w, w7[4] = p1.x, w7[5] = p1.y, w7[6] = p1.z, w7[7] = p1.w;
+                        if (ky >= 1 && ky <= 5) {
+                            const float4 q0 = tp[14 + 2 * (ky - 1)], q1 = tp[15 + 2 * (ky - 1)];
+                            w5[0] = q0.x, w5[1] = q0.y, w5[2] = q0.z, w5[3] = q0.w, w5[4] = q1.x, w5[5] = q1.y, w5[6] = q1.z, w5[7] = q1.w;
+                        }
+                        if (ky >= 2 && ky <= 4) {
+                            const float4 q = tp[24 + (ky - 2)];
+                            w3[0] = q.x, w3[1] = q.y, w3[2] = q.z, w3[3] = q.w;
+                        }
+                    }
+#pragma unroll
+                    for (int kx = 0; kx < 7; ++kx) {           // dx = kx - 3: window column of output pixel j is j + 4 + dx = j + 1 + kx
+                        const float t7 = w7[kx];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) a7[j] = fmaf(v[j + 1 + kx], t7, a7[j]);
+                        if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) {
+                            const float t5 = w5[kx - 1];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) a5[j] = fmaf(v[j + 1 + kx], t5, a5[j]);
+                        }
+                        if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) {
+                            const float t3 = w3[kx - 2];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) a3[j] = fmaf(v[j + 1 + kx], t3, a3[j]);
+                        }
                     }
                 }
-#pragma unroll
-                for (int kx = 0; kx < 7; ++kx) {           // dx = kx - 3: window column of output pixel j is j + 4 + dx = j + 1 + kx
-                    const float t7 = w7[kx];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) a7[j] = fmaf(v[j + 1 + kx], t7, a7[j]);
-                    if (ky >= 1 && ky <= 5 && kx >= 1 && kx <= 5) {
-                        const float t5 = w5[kx - 1];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) a5[j] = fmaf(v[j + 1 + kx], t5, a5[j]);
-                    }
-                    if (ky >= 2 && ky <= 4 && kx >= 2 && kx <= 4) {
-                        const float t3 = w3[kx - 2];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) a3[j] = fmaf(v[j + 1 + kx], t3, a3[j]);
-                    }
-                }
+                uint8_t *dp = ds + c * DS_PITCH + (r * TW + 8 * g4) * 2;
+                auto put = [&](uint8_t *d, const float(&a)[8]) {
+                    *reinterpret_cast<uint4 *>(d) = make_uint4(pack_bf16x2(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f)), pack_bf16x2(fmaxf(a[2], 0.f), fmaxf(a[3], 0.f)),
+                                                               pack_bf16x2(fmaxf(a[4], 0.f), fmaxf(a[5], 0.f)), pack_bf16x2(fmaxf(a[6], 0.f), fmaxf(a[7], 0.f)));
+                };
+                put(dp, a3);
+                put(dp + C * DS_PITCH, a5);
+                put(dp + 2 * C * DS_PITCH, a7);
             }
-            uint8_t *dp = ds + c * DS_PITCH + (r * TW + 8 * g4) * 2;
-            auto put = [&](uint8_t *d, const float(&a)[8]) {
-                *reinterpret_cast<uint4 *>(d) = make_uint4(pack_bf16x2(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f)), pack_bf16x2(fmaxf(a[2], 0.f), fmaxf(a[3], 0.f)),
-                                                           pack_bf16x2(fmaxf(a[4], 0.f), fmaxf(a[5], 0.f)), pack_bf16x2(fmaxf(a[6], 0.f), fmaxf(a[7], 0.f)));
-            };
-            put(dp, a3);
-            put(dp + C * DS_PITCH, a5);
-            put(dp + 2 * C * DS_PITCH, a7);
         }
-    }
-    __syncthreads();     // ds complete; xs is dead from here on (st aliases it)
+        __syncthreads();     // ds complete
 
-    // ---- pointwise 1x1 of the three branches on mma.sync: warp w owns tile row w (32 pixels = two 16-row M-tiles)
-    {
+        // ---- pointwise 1x1 of the three branches on mma.sync: warp w owns tile row w (32 pixels = two 16-row M-tiles)
         const int g = lane >> 2, t = lane & 3;
         float s[2][NT][4];
 #pragma unroll
@@ -156,48 +174,50 @@ split_block_tc_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, const Sp
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int q = 0; q < 4; ++q) s[mt][nt][q] = 0.f;
-        // ldmatrix.trans row address of this lane: stored row = channel k0 + 8 * (lane bit 4) + (lane & 7), 8 pixels from m0 + 8 * (lane bit 3)
-        const uint32_t ds_u = smem_u32(ds) + (uint32_t)((((lane >> 4) & 1) * 8 + (lane & 7)) * DS_PITCH + (warp * TW + ((lane >> 3) & 1) * 8) * 2);
+        {
+            // ldmatrix.trans row address of this lane: stored row = channel k0 + 8 * (lane bit 4) + (lane & 7), 8 pixels from m0 + 8 * (lane bit 3)
+            const uint32_t ds_u = smem_u32(ds) + (uint32_t)((((lane >> 4) & 1) * 8 + (lane & 7)) * DS_PITCH + (warp * TW + ((lane >> 3) & 1) * 8) * 2);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            uint32_t bf[NT][NT];
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int q = 0; q < NT; ++q) bf[nt][q] = __ldg(&img->bfrag[k][nt][q][lane]);
-            const float pk = __ldg(&img->p[k]);
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                float acc[NT][4];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const float2 bb = __ldg(reinterpret_cast<const float2 *>(&img->pwb[k * C + 8 * nt + 2 * t]));
-                    const float b0 = bb.x, b1 = bb.y;
-                    acc[nt][0] = b0, acc[nt][1] = b1, acc[nt][2] = b0, acc[nt][3] = b1;
-                }
-                const uint32_t ab = ds_u + (uint32_t)(k * C * DS_PITCH + mt * 32);
-#pragma unroll
-                for (int ks = 0; ks < C / 16; ++ks) {       // k16 steps
-                    uint32_t a0, a1, a2, a3;
-                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-                                 : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(ab + ks * 16 * DS_PITCH));
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) mma_16816(acc[nt], a0, a1, a2, a3, bf[nt][2 * ks], bf[nt][2 * ks + 1]);
-                }
-                if (C % 16 == 8) {                           // k8 tail (channels C-8 .. C-1): lanes 0..15 supply the addresses
-                    uint32_t a0, a1;
-                    const uint32_t at = smem_u32(ds) + (uint32_t)((C - 8 + (lane & 7)) * DS_PITCH + (warp * TW + ((lane >> 3) & 1) * 8) * 2 +
-                                                                  k * C * DS_PITCH + mt * 32);
-                    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(a0), "=r"(a1) : "r"(at));
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) mma_1688(acc[nt], a0, a1, bf[nt][NT - 1]);
-                }
+            for (int k = 0; k < 3; ++k) {
+                uint32_t bf[NT][NT];
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) s[mt][nt][q] = fmaf(fmaxf(acc[nt][q], 0.f), pk, s[mt][nt][q]);   // + x_ * pro[i]
+                    for (int q = 0; q < NT; ++q) bf[nt][q] = __ldg(&img->bfrag[k][nt][q][lane]);
+                const float pk = __ldg(&img->p[k]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    float acc[NT][4];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const float2 bb = __ldg(reinterpret_cast<const float2 *>(&img->pwb[k * C + 8 * nt + 2 * t]));
+                        acc[nt][0] = bb.x, acc[nt][1] = bb.y, acc[nt][2] = bb.x, acc[nt][3] = bb.y;
+                    }
+                    const uint32_t ab = ds_u + (uint32_t)(k * C * DS_PITCH + mt * 32);
+#pragma unroll
+                    for (int ks = 0; ks < C / 16; ++ks) {       // k16 steps
+                        uint32_t a0, a1, a2, a3;
+                        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(ab + ks * 16 * DS_PITCH));
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) mma_16816(acc[nt], a0, a1, a2, a3, bf[nt][2 * ks], bf[nt][2 * ks + 1]);
+                    }
+                    if (C % 16 == 8) {                           // k8 tail (channels C-8 .. C-1): lanes 0..15 supply the addresses
+                        uint32_t a0, a1;
+                        const uint32_t at = smem_u32(ds) + (uint32_t)((C - 8 + (lane & 7)) * DS_PITCH + (warp * TW + ((lane >> 3) & 1) * 8) * 2 +
+                                                                      k * C * DS_PITCH + mt * 32);
+                        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(a0), "=r"(a1) : "r"(at));
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) mma_1688(acc[nt], a0, a1, bf[nt][NT - 1]);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) s[mt][nt][q] = fmaf(fmaxf(acc[nt][q], 0.f), pk, s[mt][nt][q]);   // + x_ * pro[i]
+                }
             }
         }
+        __syncthreads();     // every warp has read its columns of ds: st may overwrite it
         // branch sum -> st[channel][pixel] (C fragment: rows g / g + 8, columns 2t / 2t + 1)
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
@@ -209,32 +229,33 @@ split_block_tc_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, const Sp
                 sp[8] = s[mt][nt][2];
                 sp[ST_PITCH + 8] = s[mt][nt][3];
             }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // ---- y = x2 + e * (x2 + sum + x1): item = (channel, tile row, 8-pixel segment), 16-byte loads and stores
-    for (int i = tid; i < C * TH * (TW / 8); i += NTHREADS) {
-        const int sg = i % (TW / 8), r = (i / (TW / 8)) % TH, c = i / ((TW / 8) * TH);
-        const int gy = y0 + r, gx = x0 + 8 * sg;
-        if (gy >= H || gx >= W) continue;
-        const long long off = (long long)n * C * plane + c * plane + (long long)gy * W + gx;
-        const uint4 raw = *reinterpret_cast<const uint4 *>(x + off);
-        const uint32_t *rw = reinterpret_cast<const uint32_t *>(&raw);
-        const float *sp = st + c * ST_PITCH + r * TW + 8 * sg;
-        const float4 sa = *reinterpret_cast<const float4 *>(sp), sb = *reinterpret_cast<const float4 *>(sp + 4);
-        const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-        const float gm = eg[C + c], em = eg[c];
-        uint4 out;
-        uint32_t *ow = reinterpret_cast<uint32_t *>(&out);
+        // ---- y = x2 + e * (x2 + sum + x1): item = (channel, tile row, 8-pixel segment); x comes back from the staged tile, 16-byte stores
+        for (int i = tid; i < C * TH * (TW / 8); i += NTHREADS) {
+            const int sg = i % (TW / 8), r = (i / (TW / 8)) % TH, c = i / ((TW / 8) * TH);
+            const int gy = y0 + r, gx = x0 + 8 * sg;
+            if (gy >= H || gx >= W) continue;
+            const uint8_t *xq = xc + (c * SH + r + HALO) * XR_ROW + (4 + 8 * sg) * 2;
+            const uint2 ra = *reinterpret_cast<const uint2 *>(xq), rb = *reinterpret_cast<const uint2 *>(xq + 8);
+            const uint32_t rw[4] = {ra.x, ra.y, rb.x, rb.y};
+            const float *sp = st + c * ST_PITCH + r * TW + 8 * sg;
+            const float4 sa = *reinterpret_cast<const float4 *>(sp), sb = *reinterpret_cast<const float4 *>(sp + 4);
+            const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+            const float gm = eg[C + c], em = eg[c];
+            uint4 out;
+            uint32_t *ow = reinterpret_cast<uint32_t *>(&out);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 xv = unpack_bf16x2(rw[j]);
-            const float xa = xv.x * gm, xb = xv.y * gm;
-            const float x1a = xa * em, x1b = xb * em, x2a = xa - x1a, x2b = xb - x1b;
-            ow[j] = pack_bf16x2(x2a + ((x2a + sv[2 * j]) + x1a) * em, x2b + ((x2b + sv[2 * j + 1]) + x1b) * em);
+            for (int j = 0; j < 4; ++j) {
+                const float2 xv = unpack_bf16x2(rw[j]);
+                const float xa = xv.x * gm, xb = xv.y * gm;
+                const float x1a = xa * em, x1b = xb * em, x2a = xa - x1a, x2b = xb - x1b;
+                ow[j] = pack_bf16x2(x2a + ((x2a + sv[2 * j]) + x1a) * em, x2b + ((x2b + sv[2 * j + 1]) + x1b) * em);
+            }
+            *reinterpret_cast<uint4 *>(y + (long long)n * C * plane + c * plane + (long long)gy * W + gx) = out;
         }
-        *reinterpret_cast<uint4 *>(y + off) = out;
     }
+    cp_async_wait<0>();
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------------------
@@ -255,12 +276,13 @@ static void pack_t(const float *f, std::vector<uint8_t> &out) {
                 *p = e + C, *g = p + 4;
     for (int c = 0; c < C; ++c) {
         float *t = P->taps + c * splittc::TAPF;
+        const float eg_c = e[c] * g[c];     // the kernel stages raw x: DW_k(e * g * x) = sum (w * e * g) x + b
         for (int ky = 0; ky < 7; ++ky)
-            for (int kx = 0; kx < 7; ++kx) t[8 * ky + kx] = dw7[c * 49 + ky * 7 + kx];
+            for (int kx = 0; kx < 7; ++kx) t[8 * ky + kx] = dw7[c * 49 + ky * 7 + kx] * eg_c;
         for (int ky = 0; ky < 5; ++ky)
-            for (int kx = 0; kx < 5; ++kx) t[56 + 8 * ky + kx] = dw5[c * 25 + ky * 5 + kx];
+            for (int kx = 0; kx < 5; ++kx) t[56 + 8 * ky + kx] = dw5[c * 25 + ky * 5 + kx] * eg_c;
         for (int ky = 0; ky < 3; ++ky)
-            for (int kx = 0; kx < 3; ++kx) t[96 + 4 * ky + kx] = dw3[c * 9 + ky * 3 + kx];
+            for (int kx = 0; kx < 3; ++kx) t[96 + 4 * ky + kx] = dw3[c * 9 + ky * 3 + kx] * eg_c;
         t[108] = dwb[c], t[109] = dwb[C + c], t[110] = dwb[2 * C + c];
         P->eg[c] = e[c], P->eg[C + c] = g[c];
     }
@@ -305,8 +327,10 @@ static cudaError_t split_tc_t(const void *x, void *y, const uint8_t *image /* de
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) set[dev] = true;
     }
-    const int tx = ceil_div(W, TW), ty = ceil_div(H, TH);
-    kern<<<tx * ty * N, NTHREADS, smem_bytes(C), st>>>((const bf16 *)x, (bf16 *)y, reinterpret_cast<const SplitTcImage<C> *>(image), N, H, W, tx, ty);
+    const int tx = ceil_div(W, TW), ty = ceil_div(H, TH), ntiles = tx * ty * N;
+    const int slots = sm_count() * (C <= 24 ? 2 : 1);
+    const int grid = ntiles < slots ? ntiles : slots;   // persistent CTAs walk the tile list with stride gridDim.x
+    kern<<<grid, NTHREADS, smem_bytes(C), st>>>((const bf16 *)x, (bf16 *)y, reinterpret_cast<const SplitTcImage<C> *>(image), N, H, W, tx, ty, ntiles);
     return cudaGetLastError();
 }
 
