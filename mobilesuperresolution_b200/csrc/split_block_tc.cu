@@ -68,23 +68,34 @@ split_block_tc_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, const Sp
     auto origin = [&](int tile, int &x0, int &y0, int &n) {
         x0 = (tile % tiles_x) * TW, y0 = ((tile / tiles_x) % tiles_y) * TH, n = tile / (tiles_x * tiles_y);
     };
+    // staging work split: a piece index (0..9) and a first (channel, row) pair per thread, 25 row-pairs apart per step -- (c, r) and the
+    // addresses advance incrementally (the flat-index form spent ~50 instructions per piece on divisions)
+    const int pf_h = tid % (SWP / 4), pf_rc0 = tid / (SWP / 4);
+    constexpr int PF_STEP = 25, PF_ITERS = (C * SH + PF_STEP - 1) / PF_STEP;
     auto prefetch = [&](int tile, int buf) {   // item = (channel, halo row, 4-pixel piece); W % 4 == 0: a piece is entirely inside or outside
+        if (tid >= PF_STEP * (SWP / 4)) return;
         int x0, y0, n;
         origin(tile, x0, y0, n);
-        const bf16 *xn = x + (long long)n * C * plane;
-        const uint32_t dst0 = smem_u32(xr + buf * xr_bytes(C));
-        for (int i = tid; i < C * SH * (SWP / 4); i += NTHREADS) {
-            const int h = i % (SWP / 4), rc = i / (SWP / 4), r = rc % SH, c = rc / SH;
-            const int gy = y0 - HALO + r, gx = x0 - 4 + 4 * h;
-            const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-            const bf16 *src = in ? xn + c * plane + (long long)gy * W + gx : x;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst0 + (uint32_t)(rc * XR_ROW + 8 * h)), "l"(src), "r"(in ? 8 : 0));
+        const int gx = x0 - 4 + 4 * pf_h;
+        const bool inx = gx >= 0 && gx < W;
+        int c = pf_rc0 / SH, r = pf_rc0 % SH;
+        uint32_t dst = smem_u32(xr + buf * xr_bytes(C)) + (uint32_t)(pf_rc0 * XR_ROW + 8 * pf_h);
+        const bf16 *src = x + ((long long)n * C + c) * plane + (long long)(y0 - HALO + r) * W + gx;
+#pragma unroll 2
+        for (int k = 0; k < PF_ITERS; ++k) {
+            if (c < C) {
+                const int gy = y0 - HALO + r;
+                const bool in = inx && gy >= 0 && gy < H;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(in ? src : x), "r"(in ? 8 : 0));
+            }
+            dst += PF_STEP * XR_ROW;
+            r += PF_STEP - SH, c += 1, src += plane + (long long)(PF_STEP - SH) * W;      // 25 rows on = one channel + 11 rows
+            if (r >= SH) r -= SH, c += 1, src += plane - (long long)SH * W;
         }
-        cp_async_commit();
     };
-
     int tile = blockIdx.x;
     if (tile < ntiles) prefetch(tile, 0);
+    cp_async_commit();
     for (int i = tid; i < C * TAPF / 4 + 2 * C / 4; i += NTHREADS)      // taps | e | g are contiguous in the image and in shared memory
         reinterpret_cast<float4 *>(taps)[i] = __ldg(reinterpret_cast<const float4 *>(img->taps) + i);
 
@@ -95,6 +106,7 @@ split_block_tc_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, const Sp
         cp_async_wait<0>();
         __syncthreads();     // this tile's staging buffer is complete; the previous tile's final stage is over (other buffer and ds are free)
         if (tile + (int)gridDim.x < ntiles) prefetch(tile + gridDim.x, cur ^ 1);
+        cp_async_commit();
         const uint8_t *xc = xr + cur * xr_bytes(C);
 
         // ---- depthwise 3x3 + 5x5 + 7x7 in one pass: a warp takes the 32 items of one channel (filter taps are warp-uniform)
@@ -154,9 +166,13 @@ split_block_tc_kernel(const bf16 *__restrict__ x, bf16 *__restrict__ y, const Sp
                     }
                 }
                 uint8_t *dp = ds + c * DS_PITCH + (r * TW + 8 * g4) * 2;
+                auto rp = [](float lo, float hi) {   // relu + round + pack in one instruction
+                    uint32_t d;
+                    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+                    return d;
+                };
                 auto put = [&](uint8_t *d, const float(&a)[8]) {
-                    *reinterpret_cast<uint4 *>(d) = make_uint4(pack_bf16x2(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f)), pack_bf16x2(fmaxf(a[2], 0.f), fmaxf(a[3], 0.f)),
-                                                               pack_bf16x2(fmaxf(a[4], 0.f), fmaxf(a[5], 0.f)), pack_bf16x2(fmaxf(a[6], 0.f), fmaxf(a[7], 0.f)));
+                    *reinterpret_cast<uint4 *>(d) = make_uint4(rp(a[0], a[1]), rp(a[2], a[3]), rp(a[4], a[5]), rp(a[6], a[7]));
                 };
                 put(dp, a3);
                 put(dp + C * DS_PITCH, a5);
