@@ -11,9 +11,11 @@
 //   * relu(DW_k) is stored as bf16 [k][channel][pixel] and the 1x1 convolutions are mma.sync m16n8k16 / m16n8k8 (bf16 in, fp32
 //     accumulate): the A fragments come straight out of the channel-major image with ldmatrix.trans, the B fragments (the folded
 //     1x1 filters, bf16) are packed per lane on the host;
-//   * the filter taps are broadcast LDS.128 reads of a shared-memory copy (a register-indexed constant-bank read, LDC, per tap was
-//     what bound both kernels: the channel a warp works on is a run-time value); the folded parameters live in a device-memory
-//     image (SplitTcImage) instead of travelling as an 18 KB kernel argument;
+//   * the folded parameters live in a device-memory image (SplitTcImage) instead of travelling as an 18 KB kernel argument: the
+//     per-lane B fragments and biases would be DIVERGENT constant-bank reads (one serialised access per distinct address: the first
+//     form of this kernel, with everything in the constant bank, ran at 128 us); the filter taps are broadcast LDS.128 reads of a
+//     shared-memory copy.  (The same tap copy in the FFMA kernel made it slower, 94 -> 101 us: there the third resident CTA per SM
+//     that the extra shared memory costs matters more than the warp-uniform LDC per tap.);
 //   * persistent CTAs: the raw bf16 halo tile of the next work item streams in with cp.async while this one is computed (e * g
 //     is folded into the taps), and the result leaves through shared memory as 16-byte stores.
 // Tensors are the reference's NCHW in bf16.  W must be a multiple of 8 (16-byte rows); b200sr.cu routes everything else to
