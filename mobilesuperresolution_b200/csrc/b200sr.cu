@@ -93,6 +93,7 @@ struct b200sr_wdsr {
     uint8_t *d_head_tc5 = nullptr;   // tcgen05 head image (trunk padded to 24 channels)
     uint8_t *d_tail_tc5 = nullptr;   // tcgen05 tail image (nullptr unless the trunk is padded to 24 channels)
     int tail_impl = 1;               // 0 = mma.sync kernel, 1 = tcgen05 kernel
+    int head_impl = 0;               // head of the tcgen05 path: 0 = mma.sync kernel (wdsr_head_mma.cu), 1 = tcgen05 kernel (B200SR_HEAD_IMPL=tc5)
     // The bf16 forward is one of two uniform paths: head/block/tail all tcgen05 on a planar-8 trunk [N][3][H][W][8] (tma_map.h), or
     // all mma.sync (+ the sequential tcgen05 reference block) on an NHWC trunk.  Never a mixture: the kernels disagree on the layout.
     bool tc5_path() const {
@@ -422,6 +423,8 @@ int b200sr_wdsr_commit(b200sr_wdsr_t *p) {
     {
         const char *e = getenv("B200SR_TAIL_IMPL");   // developer switch: mma | tc5
         p->tail_impl = (e && !strcmp(e, "mma")) ? 0 : 1;
+        const char *eh = getenv("B200SR_HEAD_IMPL");   // developer switch: mma (default) | tc5
+        p->head_impl = (eh && !strcmp(eh, "tc5")) ? 1 : 0;
     }
     p->committed = true;
     return 0;
@@ -468,9 +471,12 @@ int b200sr_wdsr_head(const b200sr_wdsr_t *p, const void *x, int x_dtype, void *t
     int rc = check_common(p, n, h, w, precision, "wdsr_head");
     if (rc) return rc;
     if (!x || !trunk) return fail(B200SR_E_INVAL, "wdsr_head: null tensor");
-    if (precision == B200SR_BF16 && p->tc5_path())
-        CU(launch_head_tc5(x_dtype, x, trunk, p->d_head_tc5, n, h, w, p->mean, (cudaStream_t)stream));
-    else
+    if (precision == B200SR_BF16 && p->tc5_path()) {
+        if (p->head_impl == 1)
+            CU(launch_head_tc5(x_dtype, x, trunk, p->d_head_tc5, n, h, w, p->mean, (cudaStream_t)stream));
+        else
+            CU(launch_head_mma(x_dtype, x, trunk, p->d_head, n, h, w, p->mean, (cudaStream_t)stream));
+    } else
         CU(launch_head(p->cp, x_dtype, precision, x, trunk, p->d_head, n, h, w, p->mean, (cudaStream_t)stream));
     return 0;
 }
@@ -618,6 +624,7 @@ struct b200sr_split {
     std::vector<float> params;   // packed image, passed to the kernel by value (constant bank)
     std::vector<uint8_t> tc;     // parameter image of the bf16 tensor-core arm (split_block_tc.cu), derived from params ...
     void *d_tc = nullptr;        // ... and its copy in device memory (the device that was current at b200sr_split_create)
+    bool ffma_only = false;      // B200SR_SPLIT_IMPL=ffma at create time: keep the fp32-FFMA kernel for bf16 tensors too (developer switch)
 };
 
 static int split_upload_tc(b200sr_split *b) {
@@ -630,11 +637,7 @@ static int split_upload_tc(b200sr_split *b) {
 
 // bf16 tensors with 16-byte rows take the tensor-core arm; B200SR_SPLIT_IMPL=ffma keeps the fp32-FFMA kernel (developer switch)
 static cudaError_t run_split(const b200sr_split *b, int dtype, const void *x, void *y, int n, int h, int w, cudaStream_t st) {
-    static const bool ffma_only = [] {
-        const char *e = getenv("B200SR_SPLIT_IMPL");
-        return e && !strcmp(e, "ffma");
-    }();
-    if (!ffma_only && b->d_tc && split_tc_eligible(dtype, x, y, w)) return launch_split_block_tc(b->c, x, y, (const uint8_t *)b->d_tc, n, h, w, st);
+    if (!b->ffma_only && b->d_tc && split_tc_eligible(dtype, x, y, w)) return launch_split_block_tc(b->c, x, y, (const uint8_t *)b->d_tc, n, h, w, st);
     return launch_split_block(b->c, dtype, x, y, b->params.data(), n, h, w, st);
 }
 
@@ -661,6 +664,10 @@ int b200sr_split_create(int C, const float *dw3, const float *dw5, const float *
     if (!b) return fail(B200SR_E_INVAL, "split_create: out of memory");
     b->c = C;
     b->params.swap(f);
+    {
+        const char *e = getenv("B200SR_SPLIT_IMPL");
+        b->ffma_only = e && !strcmp(e, "ffma");
+    }
     if (int rc = split_upload_tc(b)) {
         b200sr_split_destroy(b);
         return rc;

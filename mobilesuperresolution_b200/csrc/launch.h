@@ -51,6 +51,8 @@ cudaError_t launch_block_rs(const void *in, void *out, const uint8_t *wimg, int 
 cudaError_t launch_block_rh(const void *in, void *out, const uint8_t *wimg, int M1P, int M2, int N, int H, int W, cudaStream_t st);
 // tcgen05 form of the head (bf16 trunk padded to 24 channels)
 cudaError_t launch_head_tc5(int x_dtype, const void *x, void *trunk, const uint8_t *wimg, int N, int H, int W, float mean, cudaStream_t st);
+// the same head on mma.sync (wdsr_head_mma.cu; the default of the tcgen05 path): wh = the fp32 head image [27][24] | bias[24]
+cudaError_t launch_head_mma(int x_dtype, const void *x, void *trunk, const float *wh, int N, int H, int W, float mean, cudaStream_t st);
 // tcgen05 form of the fused tail (trunk padded to 24 channels)
 cudaError_t launch_tail_tc5(int S, int x_dtype, int y_dtype, const void *trunk, const void *x, void *y, const uint8_t *wimg, int N, int H,
                             int W, float mean, float out_add, cudaStream_t st);

@@ -330,3 +330,30 @@ def test_forward_u8_matches_quantised_forward():
         assert float(d.max()) <= 1.0 and float((d > 0).float().mean()) < 1e-3      # ties at x.5 may round differently after the fp32 mul
     with pytest.raises(RuntimeError):
         m.set_precision("fp32").forward_u8(x)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 37, 45), (1, 3, 96, 96), (1, 3, 5, 300), (3, 3, 1, 1)])
+@pytest.mark.parametrize("xdtype", ["fp32", "bf16"])
+def test_head_mma_and_tcgen05_forms(G, shape, xdtype, monkeypatch):
+    """The head of the tcgen05 path runs on mma.sync by default (csrc/wdsr_head_mma.cu); B200SR_HEAD_IMPL=tc5 keeps the tcgen05 kernel
+    (csrc/wdsr_tc5_head.cuh).  Both round (x - mean) and the filters to bf16 at the same points: each within the bf16 gate of the fp32
+    reference conv, and within a couple of bf16 ulps of each other, on ragged and tiny shapes, fp32 and bf16 input."""
+    from oracle import port
+    sr = G.sr
+    x = torch.from_numpy(G.synth.synth_input(shape, 91))
+    outs = {}
+    for impl in ("mma", "tc5"):
+        monkeypatch.setenv("B200SR_HEAD_IMPL", impl)
+        m = sr.BASIC_MODEL(G.params(4, 1)).eval()
+        sd = G.synth_load(m, 57)
+        plan = m.to(G.DEV).set_precision("bf16").prepare()
+        xd = x.to(G.DEV)
+        if xdtype == "bf16":
+            xd = xd.bfloat16()
+        outs[impl] = plan.head(xd, "bf16").float().cpu().permute(0, 3, 1, 2)
+        torch.cuda.synchronize()
+    xin = x.bfloat16().float() if xdtype == "bf16" else x
+    ref = F.conv2d(xin - 0.5, port.weight_norm_fold(sd["head.weight_g"], sd["head.weight_v"]), sd["head.bias"], padding=1)
+    for impl in outs:
+        assert G.maxabs(outs[impl], ref) <= 2e-2, impl
+    assert G.maxabs(outs["mma"], outs["tc5"]) <= 2 ** -6 * max(1.0, float(ref.abs().max()))
