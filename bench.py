@@ -222,6 +222,19 @@ def north_star_configs(dev, rank, world, peaks, shard):
             out[f"cfg3_P1_b{b}"] = {"us_per_frame": us / b, "frames_per_s": world * b / us * 1e6, "frames_per_s_per_gpu": b / us * 1e6,
                                     "ceiling_frames_per_s_per_gpu": ceil_p1, "frac_of_ceiling": b / us * 1e6 / ceil_p1}
             del g
+        # -- the fork's NAS_MODEL as committed (models/wdsr_b.py:30-137: head -> 16 x Split_Block -> tail, all blocks kept) at 360p x4
+        torch.manual_seed(0)
+        pn = P(4)
+        pn.width_search = True
+        mn = sr.NAS_MODEL(pn).eval().to(dev).set_precision("bf16")
+        for b in (1, 8):
+            x = torch.rand(b, 3, 360, 640, device=dev).bfloat16()
+            us, g = _graph_us(mn, x)
+            us = reduce_us(us)
+            out[f"nas_fork_360p_b{b}"] = {"us_per_frame": us / b, "frames_per_s": world * b / us * 1e6, "frames_per_s_per_gpu": b / us * 1e6,
+                                          "kept_blocks": mn.get_current_blocks(), "out_mpix_s": world * b * 1440 * 2560 / us}
+            del g
+        del mn
         # -- cfg5: WDSR-B x2 1080p -> 2160p, frames sharded over the ranks (4 frames per rank, no collective)
         torch.manual_seed(0)
         m2 = sr.BASIC_MODEL(P(2)).eval().to(dev).set_precision("bf16")

@@ -135,3 +135,39 @@ def test_split_block_bf16_tensor_core_arm(c, n, h, w, monkeypatch):
     kept = torch.from_numpy(np.asarray(sr.rounding(sd["split.weight"], 0))).view(-1) > 0
     assert torch.equal(y[:, ~kept], x.float()[:, ~kept])
     assert port.psnr_db(y, y_env, peak=float(ref.max() - ref.min())) >= 50.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c,n,h,w", [(24, 2, 45, 104), (16, 1, 9, 8), (32, 1, 30, 40), (24, 1, 360, 640)])
+def test_split_block_tc_red_zones_and_repeat_under_load(c, n, h, w):
+    """compute-sanitizer is closed on this pool (profiles/r02_compute_sanitizer_closed.txt): the persistent cp.async kernel of the bf16 arm
+    is checked directly -- x and y sit between canary zones that must survive (partial tiles in both directions, a 3-pixel halo read around
+    every tile), and 10 runs give bit-identical output while a second stream keeps the SMs and L2 busy (the double-buffered staging tile,
+    the ds / st aliasing and the four barriers per tile are the things a race would show in)."""
+    import mobilesuperresolution_b200 as sr
+    from mobilesuperresolution_b200 import _lib
+    from oracle import synth
+    m = sr.Split_Block(num_residual_units=c, kernel_size=3).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.synth_state_dict(shapes, 5 + c).items()})
+    m = m.cuda()
+    xs = torch.from_numpy(synth.synth_input((n, c, h, w), 3 + c, -1.0, 1.0)).bfloat16().cuda()
+    with torch.no_grad():
+        want = m(xs)
+    plan = m._plan_obj
+    nb = xs.numel() * 2
+    RZ = 1 << 16
+    arena = torch.full((RZ + nb + RZ + nb + RZ,), 0xA5, dtype=torch.uint8, device="cuda")
+    xa, ya = arena[RZ:RZ + nb], arena[RZ + nb + RZ:RZ + nb + RZ + nb]
+    xa.copy_(xs.view(torch.uint8).reshape(-1))
+    side, noise = torch.cuda.Stream(), torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    for it in range(10):
+        with torch.cuda.stream(side):
+            for _ in range(1 + it % 3):
+                noise.fill_(it)
+        _lib.check(_lib.lib().b200sr_split_forward(plan._h, xa.data_ptr(), ya.data_ptr(), n, h, w, _lib.BF16, _lib.current_stream_ptr(xs.device)))
+        torch.cuda.synchronize()
+        assert torch.equal(ya.view(torch.bfloat16).view(n, c, h, w), want), f"iteration {it}"
+    for a, b in [(0, RZ), (RZ + nb, RZ + nb + RZ), (RZ + 2 * nb + RZ, RZ + 2 * nb + 2 * RZ)]:
+        assert bool((arena[a:b] == 0xA5).all()), "the kernel wrote outside its output"
+    assert torch.equal(xa.view(torch.bfloat16).view(n, c, h, w), xs)
