@@ -30,7 +30,7 @@ static cudaError_t tail_tc5_t(const void *trunk, const void *x, void *y, const u
     static thread_local SmemOptIn optin;   // per device (launch.h)
     if ((e = optin.ensure(kern, smem)) != cudaSuccess) return e;
     const int tx = ceil_div(W, TW), ty = ceil_div(H, TH), ntiles = tx * ty * N;
-    int ctas = sm_count();
+    int ctas = tc5tail::CTAS_PER_SM * sm_count();
     if (ctas > ntiles) ctas = ntiles;
     kern<<<ctas, NTHREADS, smem, st>>>(*mapp, (const TIN *)x, (TOUT *)y, wimg, N, H, W, tx, ty, ntiles, mean, out_add);
     return cudaGetLastError();

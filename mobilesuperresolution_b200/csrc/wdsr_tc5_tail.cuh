@@ -1,7 +1,7 @@
 // wdsr_tc5_tail.cuh -- fused WDSR-B tail on tcgen05:
 //   y = PixelShuffle_s( conv3x3(trunk, Wt) + conv5x5(x - mean, Ws) + (bt + bs) ) + out_add          models/basic_wdsr_b.py:90-92
 //
-// One persistent CTA per SM, 32 x 8 LR-pixel tiles = two M-tiles of 128 pixels (4 rows x 32).  No stage depends on another
+// One persistent CTA per SM (see NBUF below for the two-CTA experiment), 32 x 8 LR-pixel tiles = two M-tiles of 128 pixels (4 rows x 32).  No stage depends on another
 // CTA-local result, so the pipeline is a plain producer -> MMA -> epilogue chain:
 //   warp 0      TMA      nine cp.async.bulk.tensor.5d per tile: three x-shifted copies (one per horizontal tap) of the three
 //                        8-channel planes of the trunk tile + 1-row halo, so every 3x3 tap is a constant address offset;
@@ -37,6 +37,17 @@ struct TailTc5Layout {  // weight image (bytes); rows = output channel (NOP = 3 
 };
 
 namespace tc5tail {
+// NBUF = trunk-tile / skip-operand buffers per CTA.  2 (default): one CTA per SM, double buffered.  1 (-DB200SR_TAIL_NBUF=1 through
+// B200SR_NVCC_EXTRA): TWO co-resident CTAs per SM, each single buffered (102 KB of shared memory, 128 of the 512 TMEM columns, <= 96
+// registers) -- the test of "a second, independent TMA -> builder -> MMA -> epilogue chain on the same SM fills the first one's bubbles".
+// Measured, parity-green: 34.3 us against 30.3 us per launch at cfg2 (graph replay): SLOWER, like every deeper ring inside one chain was
+// neutral -- the tail is not bound by the latency of its chain (profiles/r02_tail_head_ncu.md).
+#ifndef B200SR_TAIL_NBUF
+#define B200SR_TAIL_NBUF 2
+#endif
+constexpr int NBUF = B200SR_TAIL_NBUF, CTAS_PER_SM = NBUF == 1 ? 2 : 1;
+__host__ __device__ constexpr int buf_of(int it) { return NBUF == 2 ? (it & 1) : 0; }
+__host__ __device__ constexpr int phase_of(int it) { return NBUF == 2 ? ((it >> 1) & 1) : (it & 1); }
 constexpr int TW = 32, TH = 8, NTHREADS = 320;
 constexpr int PLANE = (TH + 2) * TW * 16;  // 5,120 B: 10 rows x 32 px x 16 B
 constexpr int TC_BUF = 9 * PLANE;          // 46,080 B per tile (3 copies x 3 planes)
@@ -48,12 +59,12 @@ constexpr int SK_STRIDE = SK_BUF;
 constexpr int CTRL = 256;
 enum Bar { TC_FULL = 0, TC_EMPTY = 2, SK_FULL = 4, SK_EMPTY = 6, D_FULL = 8, D_EMPTY = 10, NBARS = 12 };
 __host__ __device__ inline size_t smem_bytes(int NOP) {
-    return (size_t)CTRL + 2 * TC_BUF + 2 * SK_STRIDE + X4_BUF + (size_t)TailTc5Layout(NOP).total;
+    return (size_t)CTRL + NBUF * TC_BUF + NBUF * SK_STRIDE + X4_BUF + (size_t)TailTc5Layout(NOP).total;
 }
 }  // namespace tc5tail
 
 template <typename TIN, typename TOUT, int S>
-__global__ void __launch_bounds__(tc5tail::NTHREADS, 1)
+__global__ void __launch_bounds__(tc5tail::NTHREADS, tc5tail::CTAS_PER_SM)
 wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *__restrict__ x, TOUT *__restrict__ y,
                      const uint8_t *__restrict__ wimg, int N, int H, int W, int tiles_x, int tiles_y, int ntiles, float mean, float out_add) {
     using namespace tc5tail;
@@ -61,9 +72,9 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const TailTc5Layout L(NOP);
     uint8_t *ctrl = smem_raw;
-    uint8_t *tc = smem_raw + CTRL;       // 2 x TC_BUF
-    uint8_t *sk = tc + 2 * TC_BUF;       // 2 x SK_STRIDE
-    uint8_t *x4 = sk + 2 * SK_STRIDE;    // X4_BUF
+    uint8_t *tc = smem_raw + CTRL;          // NBUF x TC_BUF
+    uint8_t *sk = tc + NBUF * TC_BUF;       // NBUF x SK_STRIDE
+    uint8_t *x4 = sk + NBUF * SK_STRIDE;    // X4_BUF
     uint8_t *wsm = x4 + X4_BUF;          // L.total
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bars = smem_u32(ctrl);
@@ -86,10 +97,11 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
     if (warp == 0) tc5::tmem_alloc(smem_u32(ctrl + 240), 128);
     for (int i = tid; i < L.total / 16; i += NTHREADS) cp_async16(wsm + i * 16, wimg + i * 16, 16);
     cp_async_commit();
-    for (int i = tid; i < (2 * SK_STRIDE + X4_BUF) / 16; i += NTHREADS) *reinterpret_cast<uint4 *>(sk + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (NBUF * SK_STRIDE + X4_BUF) / 16; i += NTHREADS) *reinterpret_cast<uint4 *>(sk + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     // the zero-weight dummy half of the 14th 3x3 instruction reads one row past the last plane of a buffer: keep it finite
-    // before buffer 1 has ever been loaded (buffer 1 overflows into the zeroed skip area)
-    for (int i = tid; i < 512 / 16; i += NTHREADS) *reinterpret_cast<uint4 *>(tc + TC_BUF + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    // before buffer 1 has ever been loaded (the last buffer overflows into the zeroed -- later: finite -- skip area)
+    if (NBUF == 2)
+        for (int i = tid; i < 512 / 16; i += NTHREADS) *reinterpret_cast<uint4 *>(tc + TC_BUF + i * 16) = make_uint4(0u, 0u, 0u, 0u);
     cp_async_wait<0>();
     tc5::fence_proxy_async();
     tc5::fence_before_sync();
@@ -110,8 +122,8 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
             for (int it = 0; it < nmine; ++it) {
                 int x0, y0, n;
                 tile_origin(it, x0, y0, n);
-                const int b = it & 1;
-                tc5::mbar_wait(bar(TC_EMPTY + b), ((it >> 1) & 1) ^ 1);
+                const int b = buf_of(it);
+                tc5::mbar_wait(bar(TC_EMPTY + b), phase_of(it) ^ 1);
                 tc5::mbar_arrive_expect_tx(bar(TC_FULL + b), TC_BUF);
 #pragma unroll
                 for (int d = 0; d < 3; ++d)
@@ -128,10 +140,10 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
         const uint64_t bwt = tc5::smem_desc(w_u + L.wt, 128, L.sbo_t), bws = tc5::smem_desc(w_u + L.ws, 128, L.sbo_s);
         const uint64_t at0 = tc5::smem_desc(tc_u, 0, 128), as0 = tc5::smem_desc(sk_u, 0, 128);
         for (int g = 0; g < 2 * nmine; ++g) {
-            const int it = g >> 1, h = g & 1, b = it & 1, e = g & 1;
+            const int it = g >> 1, h = g & 1, b = buf_of(it), e = g & 1;
             if (h == 0) {
-                tc5::mbar_wait(bar(TC_FULL + b), (it >> 1) & 1);
-                tc5::mbar_wait(bar(SK_FULL + b), (it >> 1) & 1);
+                tc5::mbar_wait(bar(TC_FULL + b), phase_of(it));
+                tc5::mbar_wait(bar(SK_FULL + b), phase_of(it));
             }
             tc5::mbar_wait(bar(D_EMPTY + e), ((g >> 1) & 1) ^ 1);
             tc5::fence_after_sync();
@@ -182,7 +194,7 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
         };
         if (nmine > 0) fetch(0);
         for (int it = 0; it < nmine; ++it) {
-            const int b = it & 1;
+            const int b = buf_of(it);
 #pragma unroll
             for (int k = 0; k < NIT; ++k) {
                 const int i = bt + 128 * k;
@@ -190,7 +202,7 @@ wdsr_tail_tc5_kernel(const __grid_constant__ CUtensorMap tmap_trunk, const TIN *
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (it + 1 < nmine) fetch(it + 1);       // in flight while this tile's operand is written
-            tc5::mbar_wait(bar(SK_EMPTY + b), ((it >> 1) & 1) ^ 1);
+            tc5::mbar_wait(bar(SK_EMPTY + b), phase_of(it) ^ 1);
             uint8_t *dstb = sk + b * SK_STRIDE;
 #pragma unroll
             for (int k = 0; k < 3 * XH * TW / 128; ++k) {   // 9 entries per thread: copy j, row yy, column xx
