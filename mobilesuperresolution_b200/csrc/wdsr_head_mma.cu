@@ -8,6 +8,9 @@
 // register is a pixel's channel pair), runs 2 x m16n8k16 + 1 x m16n8k8 per 8 output channels and stores its C fragments straight to
 // the trunk -- a warp-wide 4-byte store covers 8 pixels x 16 bytes = 128 contiguous bytes of one channel plane.  At ~600 MAC/clk/SM
 // (tools/hmma_bench.cu) the 960 padded MAC per pixel are ~3 us at cfg2, under the memory time; many small CTAs hide the latencies.
+// (ncu: the top stall is the math-pipe throttle of the HMMA pipe, 13.9 us cold.  A dense K = 32 form -- k = channel * 9 + tap, 6 instead of
+// 9 HMMA per 16 pixels, fragments assembled from 2-byte loads -- was built and measured SLOWER, 12.0 against 11.3 us: the extra LDS / PRMT
+// cost more than the three m16n8k8 saved.)
 // Zero padding happens in the (x - mean) domain, exactly like the reference (pads are 0 after the mean subtraction).
 #include "common.cuh"
 #include "launch.h"
