@@ -277,6 +277,10 @@ B200SR_API int b200sr_spynet_level_input(const float *ref_dev, const float *supp
                                          int out_dtype, float *up_dev, int n, int h, int w, int ph, int pw, int cs, void *stream);
 /* y[n,c,h,w] = a[n,h,w,c] + b[n,c,h,w]  (a NHWC float32 with cs channels, b may be NULL)   (models/spynet_arch.py:72-78) */
 B200SR_API int b200sr_nhwc_plus_nchw(const float *a_dev, const float *b_dev, float *y_dev, int n, int c, int h, int w, int cs, void *stream);
+/* zero-fill `bytes` bytes of device memory on `stream` (cudaMemsetAsync: a memset node under graph capture, no kernel): the
+ * zero features of the first propagation step and the pad channels of the trunk input
+ * (`feat_prop = x.new_zeros(b, self.num_feat, h, w)`, models/basicvsr_arch_origin.py:62,75) */
+B200SR_API int b200sr_zero_async(void *dst_dev, size_t bytes, void *stream);
 /* copy a 3-channel NCHW image (image n at x + n*x_nstride elements) into channels [co,co+3) of an NHWC tensor
  * (torch.cat([x_i, feat_prop], 1), models/basicvsr_arch_origin.py:69,81) */
 B200SR_API int b200sr_nchw3_to_nhwc(const void *x_dev, int x_dtype, int64_t x_nstride, void *y_dev, int y_dtype, int n, int h, int w,

@@ -1071,6 +1071,11 @@ int b200sr_nhwc_plus_nchw(const float *a, const float *b, float *y, int n, int c
     CU(launch_nhwc_plus_nchw(a, b, y, n, c, h, w, cs, (cudaStream_t)stream));
     return 0;
 }
+int b200sr_zero_async(void *dst, size_t bytes, void *stream) {
+    if (!dst && bytes) return fail(B200SR_E_INVAL, "zero_async: null pointer");
+    if (bytes) CU(cudaMemsetAsync(dst, 0, bytes, (cudaStream_t)stream));
+    return 0;
+}
 int b200sr_nchw3_to_nhwc(const void *x, int x_dtype, int64_t x_nstride, void *y, int y_dtype, int n, int h, int w, int cs, int co, void *stream) {
     if (!x || !y || co + 3 > cs) return fail(B200SR_E_INVAL, "nchw3_to_nhwc: bad argument");
     CU(launch_nchw3_to_nhwc(x, x_dtype, x_nstride, y, y_dtype, n, h, w, cs, co, (cudaStream_t)stream));

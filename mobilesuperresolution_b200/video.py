@@ -290,13 +290,18 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
     def get_flow(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """models/basicvsr_arch_origin.py:42-51: both directions of all n-1 frame pairs, batched through SPyNet."""
         b, n, c, h, w = x.size()
-        x_1 = x[:, :-1].reshape(-1, c, h, w)
-        x_2 = x[:, 1:].reshape(-1, c, h, w)
+        x = x.contiguous()
         self.spynet.set_precision(self.precision)
         # the reference's two SPyNet calls (x_1 -> x_2, x_2 -> x_1) as ONE batch of 2 b (n-1) pairs: every op is per sample, so the
         # flows are the same numbers, and the launch-bound coarse pyramid levels run once instead of twice
-        flows = self.spynet(torch.cat([x_1, x_2], 0), torch.cat([x_2, x_1], 0))
+        # (torch.cat([x_1, x_2]) / torch.cat([x_2, x_1]) as per-clip contiguous copies: device-to-device memcpy nodes instead of cat kernels)
         m = b * (n - 1)
+        ref, supp = x.new_empty((2 * m, c, h, w)), x.new_empty((2 * m, c, h, w))
+        for k in range(b):
+            lo, hi = k * (n - 1), (k + 1) * (n - 1)
+            ref[lo:hi].copy_(x[k, :-1]), ref[m + lo:m + hi].copy_(x[k, 1:])
+            supp[lo:hi].copy_(x[k, 1:]), supp[m + lo:m + hi].copy_(x[k, :-1])
+        flows = self.spynet(ref, supp)
         flows_backward = flows[:m].view(b, n - 1, 2, h, w)
         flows_forward = flows[m:].view(b, n - 1, 2, h, w)
         return flows_forward, flows_backward
@@ -363,7 +368,9 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
             st = _lib.current_stream_ptr(dev)   # the stream this direction was forked onto
             # ONE trunk input per direction, zero-filled once: every frame rewrites its x_i channels and (from the second step on) its feature
             # channels; the first step needs zero features, the pad channels stay zero
-            buf = torch.zeros((b, h, w, cs), dtype=adt, device=dev)
+            buf = torch.empty((b, h, w, cs), dtype=adt, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.b200sr_zero_async(_ptr(buf), buf.numel() * buf.element_size(), st))
             for step, i in enumerate(order):
                 xi = x[:, i]
                 with torch.cuda.device(dev):
