@@ -6,7 +6,7 @@
 //
 // What changed against the FFMA kernel (82 us per 360p frame, 7.8 k instructions per pixel for 3.7 k FMAs):
 //   * the three depthwise filters run in ONE pass over the staged tile: a work item (channel, tile row, 8-pixel segment) loads its
-//     7 x 16 window once (28 LDS.128) and feeds all 83 taps of the 3x3 / 5x5 / 7x7 filters (664 FMAs) -- the separate passes loaded
+//     7 x 16 window once (14 LDS.128 of bf16, unpacked in registers) and feeds all 83 taps of the 3x3 / 5x5 / 7x7 filters (664 FMAs) -- the separate passes loaded
 //     the window three times with scalar loads;
 //   * relu(DW_k) is stored as bf16 [k][channel][pixel] and the 1x1 convolutions are mma.sync m16n8k16 / m16n8k8 (bf16 in, fp32
 //     accumulate): the A fragments come straight out of the channel-major image with ldmatrix.trans, the B fragments (the folded
