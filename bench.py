@@ -34,7 +34,7 @@ FLOP_PER_LR_PX_BLOCK = 2 * (24 * 144 + 144 * 20 + 9 * 20 * 24)      # 21,312 (SU
 BYTES_PER_LR_PX_BLOCK = 2 * 24 * 2                                    # read + write the bf16 trunk once = 96
 # measured DRAM bytes of ONE block launch at this workload (ncu --set full, profiles/r01_block_tcgen05_v2_ncu.md):
 # 28,391,936 read + 33,792 written -- the output stays in L2 for the next block
-NCU_DRAM_BYTES_PER_BLOCK_LAUNCH = 28_391_936 + 33_792
+NCU_DRAM_BYTES_PER_BLOCK_LAUNCH = 28480512_391_936 + 33_792
 WORKLOAD = "cfg2: WDSR-B x4 nb16 nru24 (reference seeded init), batch 64 x 3x96x96 LR -> 3x384x384, bf16"
 
 
@@ -372,7 +372,7 @@ def run_b200(args, rank, local_rank, world):
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tflops / peaks["bf16_tflops"],
                 "peak_sustained": peaks["bf16_tflops_sustained"], "frac_sustained": ach_tflops / peaks["bf16_tflops_sustained"],
                 "roof_frac": max(t_tensor, t_hbm) / (blk_ms * 1e-3),
-                "traffic": NCU_DRAM_BYTES_PER_BLOCK_LAUNCH, "traffic_source": "profiles/r01_block_tcgen05_v2_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)",
+                "traffic": NCU_DRAM_BYTES_PER_BLOCK_LAUNCH, "traffic_source": "profiles/r02_block_final_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of the final kernel; r01_block_tcgen05_v2_ncu.md gave the same 28.4 MB)",
                 "peak_source": peaks["source"] + " (burst bf16 GEMM: the kernel is timed alone, 16 launches between two events; the sustained figure is peak_sustained)",
                 "us_per_launch": blk_ms * 1e3, "algorithmic_flop_per_launch": lr_px * FLOP_PER_LR_PX_BLOCK,
                 "algorithmic_bytes_per_launch": lr_px * BYTES_PER_LR_PX_BLOCK,
