@@ -32,8 +32,8 @@ SCALE, NB, NRU = 4, 16, 24
 BATCH, LR = 64, 96
 FLOP_PER_LR_PX_BLOCK = 2 * (24 * 144 + 144 * 20 + 9 * 20 * 24)      # 21,312
 BYTES_PER_LR_PX_BLOCK = 2 * 24 * 2                                    # read + write the bf16 trunk once = 96
-# measured DRAM bytes of ONE block launch at this workload (ncu --set full, profiles/r01_block_tcgen05_v2_ncu.md):
-# 28,391,936 read + 33,792 written -- the output stays in L2 for the next block
+# measured DRAM bytes of ONE block launch at this workload (ncu --set full, profiles/r02_block_final_ncu.md; round 1's capture,
+# profiles/r01_block_tcgen05_v2_ncu.md, gave 28,391,936 + 33,792): the output stays in L2 for the next block
 NCU_DRAM_BYTES_PER_BLOCK_LAUNCH = 28_395_008 + 85_504   # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r02_block_final_ncu.md)
 WORKLOAD = "cfg2: WDSR-B x4 nb16 nru24 (reference seeded init), batch 64 x 3x96x96 LR -> 3x384x384, bf16"
 
