@@ -281,6 +281,11 @@ B200SR_API int b200sr_nhwc_plus_nchw(const float *a_dev, const float *b_dev, flo
  * zero features of the first propagation step and the pad channels of the trunk input
  * (`feat_prop = x.new_zeros(b, self.num_feat, h, w)`, models/basicvsr_arch_origin.py:62,75) */
 B200SR_API int b200sr_zero_async(void *dst_dev, size_t bytes, void *stream);
+/* dst (n, h+1, w+1, px_bytes) = src (n, h, w, px_bytes) with one zero row below and one zero column to the right
+ * (torch.nn.functional.pad(o, (0, 0, 0, 1, 0, 1)) of an NHWC tensor: the domain on which ConvTranspose2d(2 nf, 3, 5, stride=4),
+ * models/mvvsr_arch.py:38,100, is evaluated as a 3x3 convolution).  cudaMemcpy2DAsync + two memsets per image: copy / memset
+ * nodes under graph capture, no kernel */
+B200SR_API int b200sr_pad_bottom_right_async(const void *src_dev, void *dst_dev, int n, int h, int w, int px_bytes, void *stream);
 /* copy a 3-channel NCHW image (image n at x + n*x_nstride elements) into channels [co,co+3) of an NHWC tensor
  * (torch.cat([x_i, feat_prop], 1), models/basicvsr_arch_origin.py:69,81) */
 B200SR_API int b200sr_nchw3_to_nhwc(const void *x_dev, int x_dtype, int64_t x_nstride, void *y_dev, int y_dtype, int n, int h, int w,

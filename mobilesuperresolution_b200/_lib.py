@@ -85,6 +85,7 @@ SYMBOLS = {
                                           c_void_p]),
     "b200sr_nhwc_plus_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_zero_async": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "b200sr_pad_bottom_right_async": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_nchw3_to_nhwc": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200sr_vsr_base_add": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "b200sr_vsr_shuffle4_base_add": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),

@@ -1076,6 +1076,19 @@ int b200sr_zero_async(void *dst, size_t bytes, void *stream) {
     if (bytes) CU(cudaMemsetAsync(dst, 0, bytes, (cudaStream_t)stream));
     return 0;
 }
+int b200sr_pad_bottom_right_async(const void *src, void *dst, int n, int h, int w, int px_bytes, void *stream) {
+    if (!src || !dst || n < 0 || h <= 0 || w <= 0 || px_bytes <= 0) return fail(B200SR_E_INVAL, "pad_bottom_right_async: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t spitch = (size_t)w * px_bytes, dpitch = (size_t)(w + 1) * px_bytes;
+    for (int i = 0; i < n; ++i) {
+        const uint8_t *s = (const uint8_t *)src + (size_t)i * h * spitch;
+        uint8_t *d = (uint8_t *)dst + (size_t)i * (h + 1) * dpitch;
+        CU(cudaMemcpy2DAsync(d, dpitch, s, spitch, spitch, (size_t)h, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemset2DAsync(d + spitch, dpitch, 0, (size_t)px_bytes, (size_t)h, st));   // the zero column
+        CU(cudaMemsetAsync(d + (size_t)h * dpitch, 0, dpitch, st));                       // the zero row
+    }
+    return 0;
+}
 int b200sr_nchw3_to_nhwc(const void *x, int x_dtype, int64_t x_nstride, void *y, int y_dtype, int n, int h, int w, int cs, int co, void *stream) {
     if (!x || !y || co + 3 > cs) return fail(B200SR_E_INVAL, "nchw3_to_nhwc: bad argument");
     CU(launch_nchw3_to_nhwc(x, x_dtype, x_nstride, y, y_dtype, n, h, w, cs, co, (cudaStream_t)stream));

@@ -411,25 +411,52 @@ class _VsrBase(nn.Module, _VideoPlanMixin):
 
     # ---- tail of the fork's BasicVSR and of MotionVectorVSR: lrelu(fusion) -> conv_last = ConvTranspose2d(2nf, 3, 5, stride 4) -> bilinear
     #      resize to (height, weight) + bilinear base (models/basicvsr_arch.py:93-102, models/mvvsr_arch.py:95-104)
-    def _deconv_handle(self, device) -> _ConvHandle:
+    def _deconv_handle(self, device):
+        """(generic 3x3 handle of the transposed conv, [tcgen05 halves] or None).  bf16 with 2 nf = 128 input channels and 3 x 16 <= 64 phase
+        outputs: the 3x3 conv runs as TWO tcgen05 3x3 convs over the two 64-channel windows of the fusion output (outputs padded to 64), the
+        second one adding the first one's result as its residual -- 2 x ~8 us instead of 105 us per 180 x 320 frame on the generic mma.sync
+        kernel (the tcgen05 3x3 kernel takes 64..80 input channels)."""
         sig = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.conv_last.parameters())
         if getattr(self, "_tail_sig", None) != sig:
-            self._tail_handle, self._tail_sig = _ConvHandle(_transposed_s4k5_as_conv3x3(self.conv_last), device), sig
-        return self._tail_handle
+            conv = _transposed_s4k5_as_conv3x3(self.conv_last)
+            halves = None
+            if conv.in_channels == 128 and conv.out_channels <= 64:
+                halves = []
+                for k in range(2):
+                    c = nn.Conv2d(64, 64, 3, 1, 1, bias=True)
+                    with torch.no_grad():
+                        c.weight.zero_(), c.bias.zero_()
+                        c.weight[:conv.out_channels].copy_(conv.weight[:, 64 * k:64 * (k + 1)])
+                        if k == 0:
+                            c.bias[:conv.out_channels].copy_(conv.bias)
+                    halves.append(_ConvHandle(c, device))
+                if not all(hd.tcgen05_ok() for hd in halves):
+                    halves = None
+            self._tail_handle, self._tail_halves, self._tail_sig = _ConvHandle(conv, device), halves, sig
+        return self._tail_handle, self._tail_halves
 
     def _deconv_tail(self, x: torch.Tensor, back, fwd, height: int, weight: int) -> torch.Tensor:
         b, n, _, h, w = x.shape
         dev, p = x.device, self.precision
-        convs, tail = self._convs(dev), self._deconv_handle(dev)
+        convs, (tail, halves) = self._convs(dev), self._deconv_handle(dev)
         L, st = _lib.lib(), _lib.current_stream_ptr(dev)
         out = torch.empty((b, n, 3, height, weight), dtype=torch.float32, device=dev)
         for i in range(n):
             o = convs["fusion"](_cat_feats(back[i], fwd[i]), p, ACT_LRELU)
-            o = torch.nn.functional.pad(o, (0, 0, 0, 1, 0, 1))              # one zero row / column: the fifth tap's outputs
-            t = tail(o, p, ACT_NONE, out_dtype=torch.float32)               # (b, h+1, w+1, 3*16)
+            op = torch.empty((b, h + 1, w + 1, o.shape[-1]), dtype=o.dtype, device=dev)
+            with torch.cuda.device(dev):                                     # F.pad(o, (0, 0, 0, 1, 0, 1)): one zero row / column, the fifth tap's outputs
+                _lib.check(L.b200sr_pad_bottom_right_async(_ptr(o), _ptr(op), b, h, w, o.shape[-1] * o.element_size(), st))
+            o = op
+            if halves is not None and p != "fp32" and o.dtype == torch.bfloat16:
+                ta = halves[0](o, p, ACT_NONE, x_coff=0)                     # (b, h+1, w+1, 64): channels 0..63 of the fusion output
+                t = halves[1](o, p, ACT_NONE, x_coff=64, residual=ta)        # + channels 64..127
+                tdt = _lib.BF16
+            else:
+                t = tail(o, p, ACT_NONE, out_dtype=torch.float32)           # (b, h+1, w+1, 3*16)
+                tdt = _lib.F32
             xi = x[:, i]
             with torch.cuda.device(dev):                                     # shuffle(4) + crop + resize + base + add: one kernel
-                _lib.check(L.b200sr_vsr_deconv_tail(_ptr(t), _lib.F32, t.shape[-1], _ptr(xi), _lib.dtype_code(x.dtype), x.stride(0), _ptr(out[:, i]),
+                _lib.check(L.b200sr_vsr_deconv_tail(_ptr(t), tdt, t.shape[-1], _ptr(xi), _lib.dtype_code(x.dtype), x.stride(0), _ptr(out[:, i]),
                                                     out.stride(0), b, h, w, height, weight, st))
         return out
 
