@@ -365,10 +365,49 @@ __global__ void __launch_bounds__(256) trunk_convert_kernel(const T *__restrict_
         }
     }
 }
+// bf16, planar-8 <-> NCHW with every channel real (the fork NAS_MODEL's two layout changes per forward): a thread moves an 8-channel x
+// 8-pixel block -- eight 16-byte loads (one pixel's 8 channels each, or one channel's 8 pixels), an 8 x 8 transpose of 16-bit values with
+// byte permutes, eight 16-byte stores.  (The generic kernel below moves 2-byte elements: 94 us for 8 x 360p frames, 31 % of the HBM rate.)
+template <bool TO_NCHW>
+__global__ void __launch_bounds__(256) trunk_convert8_bf16_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, long long plane8, int nplanes) {
+    // plane8 = H * W / 8 pixel groups per channel plane; nplanes = N * C / 8 planar-8 planes; item = (planar plane, pixel group)
+    const long long total = plane8 * nplanes;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long g = i % plane8, pl = i / plane8;
+        // planar-8 side: 8 consecutive pixels x 16 bytes; NCHW side: channel 8 pl + c at ((8 pl + c) * plane8 + g) x 16 bytes
+        const uint4 *sp = TO_NCHW ? src + (pl * plane8 + g) * 8 : src + pl * 8 * plane8 + g;
+        const long long ss = TO_NCHW ? 1 : plane8;
+        uint32_t a[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const uint4 v = __ldg(sp + r * ss);
+            a[r][0] = v.x, a[r][1] = v.y, a[r][2] = v.z, a[r][3] = v.w;
+        }
+        uint4 *dp = TO_NCHW ? dst + pl * 8 * plane8 + g : dst + (pl * plane8 + g) * 8;
+        const long long ds = TO_NCHW ? plane8 : 1;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {       // output row c holds element c of every input row: 16-bit transpose
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = __byte_perm(a[2 * k][c >> 1], a[2 * k + 1][c >> 1], (c & 1) ? 0x7632 : 0x5410);
+            dp[c * ds] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 cudaError_t launch_trunk_convert(const void *src, int src_layout, void *dst, int dst_layout, int dtype, int n, int c, int cp, int h, int w, cudaStream_t st) {
     if (cp % 8 != 0 || c > cp || src_layout == dst_layout) return cudaErrorInvalidValue;
     const long long total = (long long)n * h * w * (cp / 8);
     if (total == 0) return cudaSuccess;
+    if (dtype == kBF16 && c == cp && ((long long)h * w) % 8 == 0 && ((src_layout == 1 && dst_layout == 2) || (src_layout == 2 && dst_layout == 1)) &&
+        (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const long long plane8 = (long long)h * w / 8, items = plane8 * n * (cp / 8);
+        long long blocks = (items + 255) / 256;
+        if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+        if (dst_layout == 2) trunk_convert8_bf16_kernel<true><<<(unsigned)blocks, 256, 0, st>>>((const uint4 *)src, (uint4 *)dst, plane8, n * (cp / 8));
+        else trunk_convert8_bf16_kernel<false><<<(unsigned)blocks, 256, 0, st>>>((const uint4 *)src, (uint4 *)dst, plane8, n * (cp / 8));
+        return cudaGetLastError();
+    }
     long long blocks = (total + 255) / 256;
     if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
     if (dtype == kF32) trunk_convert_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float *)src, src_layout, (float *)dst, dst_layout, n, c, cp, h, w);

@@ -86,6 +86,23 @@ def test_fork_nas_model_all_blocks_skipped_and_odd_shapes(sr):
     assert float((out.cpu() - ref).abs().max()) <= FP32_TOL
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 24, 40), (1, 3, 13, 37), (1, 3, 10, 12)])
+def test_fork_nas_model_bf16_layout_and_split_arms(sr, shape):
+    """bf16 forward of the fork NAS_MODEL on shapes that take the vectorised planar-8 <-> NCHW conversion and the tensor-core Split_Block
+    arm (W % 8 == 0), the generic conversion with the FFMA arm (13 x 37), and the vectorised conversion with the FFMA arm (10 x 12:
+    H * W % 8 == 0, W % 8 != 0): >= 50 dB against the oracle port on the bf16-rounded input."""
+    from oracle import port, synth
+    m = sr.NAS_MODEL(_nas_params(4, 3)).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = _t(synth.synth_state_dict(shapes, 35))
+    m.load_state_dict(sd)
+    x = torch.from_numpy(synth.synth_input(shape, 36)).bfloat16()
+    ref, _ = port.nas_fork_forward(sd, x.float(), 4)
+    with torch.no_grad():
+        out, _ = m.cuda().set_precision("bf16")(x.cuda())
+    assert port.psnr_db(out.float().cpu(), ref) >= BF16_PSNR
+
+
 # ------------------------------------------------------------------------------------------------ video
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_fork_basicvsr_forward_nf3_golden(sr, precision):
