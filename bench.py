@@ -257,6 +257,14 @@ def north_star_configs(dev, rank, world, peaks, shard):
         out["cfg4_clip15"] = {"ms_per_clip": us / 1e3, "frames_per_s": world * 15 / us * 1e6, "tflops_per_gpu": 11.23e12 / us / 1e6,
                               "roofline_ms_per_clip": roof_ms, "frac_of_roofline": roof_ms / (us / 1e3)}
         del g
+        # -- the fork's video model: MotionVectorVSR(64, 15), motion vectors in input channels 3:5, same clip size (models/mvvsr_arch.py:10-109)
+        mm = video.MotionVectorVSR(64, 15).to(dev).eval().set_precision("bf16")
+        xm = torch.rand(1, 15, 5, 180, 320, device=dev)
+        xm[:, :, 3:] = (xm[:, :, 3:] - 0.5) * 8
+        us, g = _graph_us(mm, xm, 720, 1280, reps=5, warm=1)
+        us = reduce_us(us)
+        out["mvvsr_clip15"] = {"ms_per_clip": us / 1e3, "frames_per_s": world * 15 / us * 1e6}
+        del g, mm
         # -- sustained leg: the headline forward replayed back to back for >= 3 s (power-limited steady state), clocks sampled
         torch.manual_seed(0)
         mh = sr.BASIC_MODEL(params()).eval().to(dev).set_precision("bf16")
