@@ -801,11 +801,15 @@ int b200sr_conv_create(int cin, int cout, int k, const float *w, const float *bi
         }
     }
     if (cin == 64 && cout == 3 && k == 3) {
-        // "rgb" form of the tcgen05 3x3 kernel (conv_last): 16 output rows (3 used), [2 row groups][72 slices][8 rows][16 B]
+        // "rgb" form of the tcgen05 3x3 kernel (conv_last): [2 row groups][72 slices][8 rows][16 B] with the horizontal taps in N --
+        // accumulator row n = dx * 3 + c (9 of 16 used), slice (dy, 8-channel chunk) (24 of 72 used): conv_tc5.cuh
         std::vector<uint16_t> wi((size_t)2 * 72 * 64, 0);
         for (int o = 0; o < 3; ++o)
             for (int i = 0; i < 64; ++i)
-                for (int t = 0; t < 9; ++t) wi[(((size_t)(o / 8) * 72 + t * 8 + i / 8) * 8 + o % 8) * 8 + i % 8] = f2bf(w[((size_t)o * 64 + i) * 9 + t]);
+                for (int t = 0; t < 9; ++t) {
+                    const int dy = t / 3, dx = t % 3, n = dx * 3 + o;
+                    wi[(((size_t)(n / 8) * 72 + dy * 8 + i / 8) * 8 + n % 8) * 8 + i % 8] = f2bf(w[((size_t)o * 64 + i) * 9 + t]);
+                }
         if ((rc = upload(wi.data(), wi.size() * 2, (void **)&c->d_w_tc5))) {
             b200sr_conv_destroy(c);
             return rc;

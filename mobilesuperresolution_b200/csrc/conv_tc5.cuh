@@ -17,7 +17,8 @@
 //   warps 2-5 / 6-9      epilogue of the tile's first / second M-tile: tcgen05.ld -> + bias -> activation -> (+ residual) -> bf16
 //                        stores: NHWC pixel rows (channel windows of wider tensors allowed), planar-8 planes, or PixelShuffle(2)
 //                        folded into either.  cout = 64 G: a CTA serves one group of 64 output channels (own filter image).
-//                        NOUT = 16 ("rgb" form, 64 -> 3): 3 accumulator columns + bias + x4 bilinear base -> fp32 NCHW frame.
+//                        NOUT = 16 ("rgb" form, 64 -> 3): the horizontal taps ride in N (9 accumulator columns, 12 MMAs per M-tile), the
+//                        epilogue adds them across lanes, + bias + x4 bilinear base -> fp32 NCHW frame.
 // The generic mma.sync kernel (conv.cuh) ran these convolutions at ~110-139 TFLOP/s; they are 90 % of a BasicVSR clip's FLOPs.
 // Measured (profiles/r01_conv_tc5_ncu.md): 925 TFLOP/s at 720 x 1280 = 66 % of the sustained bf16 peak -- an SS MMA with N = 64
 // reads 6 KB of operands from shared memory for 32 clk of tensor work, so ~2/3 of peak is this operand shape's ceiling.
@@ -168,11 +169,23 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
             if (leader) {
                 const uint32_t d = tmem + e * NOUT;
                 const uint64_t abase = a0d + (uint64_t)((b * TILE_BUF + m * 128 * 16) >> 4);
+                if constexpr (NOUT == 16) {
+                    // "rgb" form (64 -> 3): an N = 16 MMA costs what an N = 64 one does (the 4 KB A fetch bounds it), so the three HORIZONTAL
+                    // taps ride in N instead of K: accumulator column dx * 3 + c of box column j = sum over (dy, ci) of x[by + dy][j][ci] *
+                    // w[c][ci][dy][dx] -- 3 * NCH / 2 = 12 MMAs instead of 36 -- and the epilogue adds columns (dx, c) of lanes j + dx
 #pragma unroll
-                for (int i = 0; i < TAPS * (NCH / 2); ++i) {   // (tap t, chunks 2 cp, 2 cp + 1)
-                    const int t = i / (NCH / 2), cp = i % (NCH / 2), dy = t / KS, dx = t % KS;
-                    const int aoff = 2 * cp * PLANE + (dy * BW + dx) * 16;
-                    tc5::mma_ss(d, abase + (uint64_t)(aoff >> 4), bw + (uint64_t)(8 * (t * NCH + 2 * cp)), idesc, i > 0);
+                    for (int i = 0; i < KS * (NCH / 2); ++i) {   // (tap row dy, chunks 2 cp, 2 cp + 1)
+                        const int dy = i / (NCH / 2), cp = i % (NCH / 2);
+                        const int aoff = 2 * cp * PLANE + dy * BW * 16;
+                        tc5::mma_ss(d, abase + (uint64_t)(aoff >> 4), bw + (uint64_t)(8 * (dy * NCH + 2 * cp)), idesc, i > 0);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < TAPS * (NCH / 2); ++i) {   // (tap t, chunks 2 cp, 2 cp + 1)
+                        const int t = i / (NCH / 2), cp = i % (NCH / 2), dy = t / KS, dx = t % KS;
+                        const int aoff = 2 * cp * PLANE + (dy * BW + dx) * 16;
+                        tc5::mma_ss(d, abase + (uint64_t)(aoff >> 4), bw + (uint64_t)(8 * (t * NCH + 2 * cp)), idesc, i > 0);
+                    }
                 }
                 tc5::commit(bar(D_FULL + e));
                 if (m == MT - 1) tc5::commit(bar(TC_EMPTY + b));
@@ -217,13 +230,19 @@ conv3x3_c64_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, c
                 tc5::tmem_wait_ld();
                 tc5::fence_before_sync();
                 tc5::mbar_arrive_relaxed(bar(D_EMPTY + e));
+                // output column o = lane: taps dx = 0, 1, 2 were accumulated at box columns o, o + 1, o + 2 (lanes of this warp = one box row)
+                float s3[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    s3[c] = __uint_as_float(v[c]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[3 + c]), 1) +
+                            __shfl_down_sync(0xffffffffu, __uint_as_float(v[6 + c]), 2);
                 if (ok) {
                     const int lh = H >> 2, lw = W >> 2;
                     const float *bp = a.base + (long long)n * a.base_nstride;
                     float *yp = reinterpret_cast<float *>(a.y) + (long long)n * a.y_nstride + (long long)gy * W + gx;
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
-                        yp[c * hw] = __uint_as_float(v[c]) + bias_s[c] + bilinear_x4(bp + (long long)c * lh * lw, lh, lw, gy, gx);
+                        yp[c * hw] = s3[c] + bias_s[c] + bilinear_x4(bp + (long long)c * lh * lw, lh, lw, gy, gx);
                 }
                 continue;
             }
