@@ -817,14 +817,17 @@ int b200sr_conv_create(int cin, int cout, int k, const float *w, const float *bi
     }
     if (k == 7 && conv7_tc5_shape_ok(cin, cout)) {
         // [7 tap rows ky][cout/8 row groups][7 taps kx x nch chunks][8 rows][16 B]: one contiguous stage per tap row (conv7_tc5.cuh)
-        const int nch = conv7_tc5_nch(cin);
-        std::vector<uint16_t> wi((size_t)7 * (cout / 8) * 7 * nch * 64, 0);
+        // G horizontal taps in N (conv7_tc5.cuh, Cfg): accumulator row n = (kx % G) * cout + o, tap group kx / G
+        const int nch = conv7_tc5_nch(cin), G = cout == 32 ? 2 : cout == 16 ? 4 : 1, NG = (7 + G - 1) / G, ND = G * cout;
+        std::vector<uint16_t> wi((size_t)7 * (ND / 8) * NG * nch * 64, 0);
         for (int o = 0; o < cout; ++o)
             for (int i = 0; i < cin; ++i)
                 for (int ky = 0; ky < 7; ++ky)
-                    for (int kx = 0; kx < 7; ++kx)
-                        wi[(((((size_t)ky * (cout / 8) + o / 8) * 7 + kx) * nch + i / 8) * 8 + o % 8) * 8 + i % 8] =
+                    for (int kx = 0; kx < 7; ++kx) {
+                        const int n = (kx % G) * cout + o, j = kx / G;
+                        wi[(((((size_t)ky * (ND / 8) + n / 8) * NG + j) * nch + i / 8) * 8 + n % 8) * 8 + i % 8] =
                             f2bf(w[((size_t)o * cin + i) * 49 + ky * 7 + kx]);
+                    }
         if ((rc = upload(wi.data(), wi.size() * 2, (void **)&c->d_w_tc5))) {
             b200sr_conv_destroy(c);
             return rc;

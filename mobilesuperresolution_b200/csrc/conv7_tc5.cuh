@@ -10,8 +10,8 @@
 //                        3-pixel halo) into chunk-planar shared memory [chunk][pixel][16 B]; out-of-image pixels and channels past
 //                        cin are zero-filled by the TMA unit.  x is NHWC or planar-8 [n][c/8][h][w][8] (SPyNet's private tensors).
 //   warp 1      weights  one cp.async.bulk (global -> shared, contiguous) per tap row into the ring, free running
-//   warp 2      MMA      per tap row: 4 M-tiles x 7 taps x NCH/2 tcgen05.mma (M = 128, N = cout, K = 16); a tap is a constant pixel
-//                        offset of the A operand, the two chunks of a K step are paired through the LBO stride
+//   warp 2      MMA      per tap row: 4 M-tiles x NG tap groups x NCH/2 tcgen05.mma (M = 128, N = G cout, K = 16; Cfg): a tap group is a
+//                        constant pixel offset of the A operand, the two chunks of a K step are paired through the LBO stride
 //   warps 4-7            epilogue: tcgen05.ld -> + bias -> activation -> bf16 stores (NHWC pixel rows or planar-8 planes)
 #pragma once
 #include <cuda.h>
@@ -27,11 +27,18 @@ constexpr int PLANE_PX = BW * BH + 8;            // + 8 zero pixels: the last ta
 constexpr int PLANE = PLANE_PX * 16;             // 11,392 B
 constexpr int CTRL = 256;
 enum Bar { TILE_FULL = 0, TILE_EMPTY = 1, W_FULL = 2 /*3*/, W_EMPTY = 5 /*3*/, D_FULL = 8 /*2*/, D_EMPTY = 10 /*2*/, NBARS = 12 };
+// G horizontal taps ride in the N dimension (an MMA of N <= 64 costs ~41-48 clk whatever N is: its 4 KB A fetch bounds it): accumulator
+// column b * NOUT + co of box column r = sum over tap groups j and input channels of x[r + G j] * w[co][ci][ky][G j + b], and the epilogue
+// forms out[o] = sum_b D_b[o + b] with G - 1 shuffles per value (a warp = one 32-pixel box row, outputs at its first 26 columns).
+// 64 -> 32: G = 2 (28 -> 16 MMAs per tap row and M-tile); 32 -> 16: G = 4 (14 -> 4); 64 outputs: G = 1 (TMEM is full at 2 x 4 x 64).
 template <int NCH, int NOUT> struct Cfg {
+    static constexpr int G = NOUT == 32 ? 2 : NOUT == 16 ? 4 : 1;
+    static constexpr int NG = (7 + G - 1) / G;                // tap groups per row (the last one padded with zero weights)
+    static constexpr int ND = G * NOUT;                       // accumulator columns per M-tile (64 for every layer)
     static constexpr int TILE_BUF = NCH * PLANE;
-    static constexpr int W_SBO = 7 * NCH * 128;               // stage image [NOUT/8 row groups][7 taps x NCH chunks][8 rows][16 B]
-    static constexpr int STAGE = (NOUT / 8) * W_SBO;          // <= 28,672 B
-    static constexpr int TMEM_COLS = 2 * NMT * NOUT;          // 128 / 256 / 512
+    static constexpr int W_SBO = NG * NCH * 128;              // stage image [ND/8 row groups][NG tap groups x NCH chunks][8 rows][16 B]
+    static constexpr int STAGE = (ND / 8) * W_SBO;            // <= 32,768 B
+    static constexpr int TMEM_COLS = 2 * NMT * ND <= 128 ? 128 : 2 * NMT * ND <= 256 ? 256 : 512;
     static constexpr size_t smem_bytes() { return (size_t)CTRL + TILE_BUF + NSTAGE * STAGE + 256; }
 };
 }  // namespace tc5conv7
@@ -54,7 +61,7 @@ conv7x7_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, const
                    int ntiles) {
     using namespace tc5conv7;
     using C = Cfg<NCH, NOUT>;
-    constexpr int TILE_BUF = C::TILE_BUF, W_SBO = C::W_SBO, STAGE = C::STAGE;
+    constexpr int TILE_BUF = C::TILE_BUF, W_SBO = C::W_SBO, STAGE = C::STAGE, G = C::G, NG = C::NG, ND = C::ND;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *ctrl = smem_raw;
     uint8_t *tc = smem_raw + CTRL;           // TILE_BUF
@@ -132,7 +139,7 @@ conv7x7_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, const
     } else if (warp == 2) {
         // ============================== MMA issuer ==============================
         const bool leader = tc5::elect_one();
-        const uint32_t idesc = tc5::idesc_bf16_f32(128, NOUT);
+        const uint32_t idesc = tc5::idesc_bf16_f32(128, ND);
         const uint64_t a0d = tc5::smem_desc(tc_u, PLANE, 128);   // A: chunk pairs through LBO = plane stride
         for (int it = 0; it < nmine; ++it) {
             const int set = it & 1;
@@ -146,13 +153,13 @@ conv7x7_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, const
                     const uint64_t bw = tc5::smem_desc(w_u + s * STAGE, 128, W_SBO);
 #pragma unroll 1
                     for (int m = 0; m < NMT; ++m) {
-                        const uint32_t d = tmem + (set * NMT + m) * NOUT;
+                        const uint32_t d = tmem + (set * NMT + m) * ND;
                         const uint64_t abase = a0d + (uint64_t)((((4 * m + ky) * BW) * 16) >> 4);
 #pragma unroll
-                        for (int i = 0; i < 7 * (NCH / 2); ++i) {   // (tap kx, chunks 2 cp, 2 cp + 1)
-                            const int kx = i / (NCH / 2), cp = i % (NCH / 2);
-                            const int aoff = 2 * cp * PLANE + kx * 16;
-                            tc5::mma_ss(d, abase + (uint64_t)(aoff >> 4), bw + (uint64_t)(8 * (kx * NCH + 2 * cp)), idesc, (ky | i) != 0);
+                        for (int i = 0; i < NG * (NCH / 2); ++i) {   // (tap group j = taps G j .. G j + G - 1, chunks 2 cp, 2 cp + 1)
+                            const int j = i / (NCH / 2), cp = i % (NCH / 2);
+                            const int aoff = 2 * cp * PLANE + G * j * 16;
+                            tc5::mma_ss(d, abase + (uint64_t)(aoff >> 4), bw + (uint64_t)(8 * (j * NCH + 2 * cp)), idesc, (ky | i) != 0);
                         }
                     }
                     tc5::commit(bar(W_EMPTY + s));
@@ -189,10 +196,19 @@ conv7x7_tc5_kernel(const __grid_constant__ CUtensorMap tmap_x, ConvArgs a, const
 #pragma unroll
                 for (int hh = 0; hh < NOUT / HC; ++hh) {
                     uint32_t v[HC];
-                    const uint32_t taddr = tmem + lane_base + (set * NMT + m) * NOUT + HC * hh;
+                    const uint32_t taddr = tmem + lane_base + (set * NMT + m) * ND + HC * hh;
                     if constexpr (HC == 32) tc5::tmem_ld32(taddr, v);
                     else tc5::tmem_ld16(taddr, v);
                     tc5::tmem_wait_ld();
+#pragma unroll
+                    for (int b = 1; b < G; ++b) {   // + taps G j + b, accumulated b box columns to the right (all 32 lanes shuffle)
+                        uint32_t vb[HC];
+                        if constexpr (HC == 32) tc5::tmem_ld32(taddr + b * NOUT, vb);
+                        else tc5::tmem_ld16(taddr + b * NOUT, vb);
+                        tc5::tmem_wait_ld();
+#pragma unroll
+                        for (int q = 0; q < HC; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __shfl_down_sync(0xffffffffu, __uint_as_float(vb[q]), b));
+                    }
                     if (ok) {
                         uint4 *yp = reinterpret_cast<uint4 *>(a.y_planar ? y + ppix * 8 : y + pix * a.y_cs + a.y_co);
                         const long long ystep = a.y_planar ? hw : 1;
