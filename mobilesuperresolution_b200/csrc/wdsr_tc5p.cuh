@@ -278,6 +278,18 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             const uint32_t d3 = tmem + d3_col(k);
 #ifdef B200SR_EXP_G3SHORT
             constexpr int NG3 = 2;   // (timing experiment: results are wrong)
+#elif defined(B200SR_EXP_DXN)
+            // (timing experiment for DESIGN.md 9-1, results are wrong: the tensor-queue shape of the "horizontal taps in N" mapping -- 5 MMAs of
+            //  N = 80 per M-tile into one of two 80-column accumulators at TMEM columns 352 / 432)
+            constexpr int NG3 = 5;
+            const uint32_t idesc80 = tc5::idesc_bf16_f32(128, 80);
+            const uint32_t d3x = tmem + 352 + (k & 1) * 80;
+#pragma unroll
+            for (int i = 0; i < NG3; ++i)
+                tc5::mma_ss(d3x, abase + (uint64_t)((i % 3) * T2_ROW >> 4) + ((uint64_t)(128 >> 4) << 16), tc5::smem_desc(w_u + L.w3, 128, 1024) + (uint64_t)(16 * i), idesc80, i > 0);
+            tc5::commit(bar(D3_FULL + k));
+            if (k == 3) tc5::commit(bar(T2R_FREE + 3));
+            return;
 #else
             constexpr int NG3 = NM;
 #endif
@@ -406,7 +418,23 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             V3_T0();
             V3_EVT(500 + k);
             uint32_t v[32];
+#if defined(B200SR_EXP_DXN) && !defined(B200SR_EXP_DXN_LIGHTE3)
+            {   // (timing experiment: the heavier E3 of the mapping -- 72 accumulator columns and two shuffles per output value)
+                uint32_t v1[32], v2[16];
+                tc5::tmem_ld32(tmem + lane_base + 352 + (k & 1) * 80, v);
+                tc5::tmem_ld32(tmem + lane_base + 352 + (k & 1) * 80 + 32, v1);
+                tc5::tmem_ld16(tmem + lane_base + 352 + (k & 1) * 80 + 64, v2);
+                tc5::tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 24; ++j)
+                    v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(j < 8 ? v[24 + j] : v1[j - 8]), 1) +
+                                           __shfl_down_sync(0xffffffffu, __uint_as_float(j < 8 ? v1[16 + j] : j < 16 ? v1[24 + j - 8] : v2[j - 16]), 2));
+            }
+#elif defined(B200SR_EXP_DXN)
+            tc5::tmem_ld32(tmem + lane_base + 352 + (k & 1) * 80, v);   // (upper bound of the mapping: E3 as light as the shipped one)
+#else
             tc5::tmem_ld32(tmem + lane_base + d3_col(k), v);
+#endif
             const int ly = 4 * k + (row >> 5), lx = row & 31;
             const int gy = y0 + 1 + ly, gx = x0 + 1 + lx;
             const uint8_t *res = xs + xb * XS_BUF + ((ly + 1) * HW_ + lx + 1) * 16;
@@ -473,7 +501,11 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                     cw[2 * j4 + 1] = ok ? pack_bf16x2(__uint_as_float(v[4 * j4 + 2]) + bb.z, __uint_as_float(v[4 * j4 + 3]) + bb.w) : 0u;
                 }
 #pragma unroll
+#ifdef B200SR_EXP_DXN
+                for (int d = 0; d < 1; ++d) {      // (timing experiment: ONE copy of t2)
+#else
                 for (int d = 0; d < 3; ++d) {
+#endif
                     const int xi = hx - d;
                     if (xi >= 0 && xi < TW) {
                         uint8_t *dst = t2 + d * T2_COPY + r * T2_ROW + (xi >> 3) * T2_GROUP + (xi & 7) * 16;
