@@ -418,7 +418,7 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
             V3_T0();
             V3_EVT(500 + k);
             uint32_t v[32];
-#if defined(B200SR_EXP_DXN) && !defined(B200SR_EXP_DXN_LIGHTE3)
+#if defined(B200SR_EXP_DXN) && !defined(B200SR_EXP_DXN_LIGHTE3) && !defined(B200SR_EXP_DXN_HALFE3)
             {   // (timing experiment: the heavier E3 of the mapping -- 72 accumulator columns and two shuffles per output value)
                 uint32_t v1[32], v2[16];
                 tc5::tmem_ld32(tmem + lane_base + 352 + (k & 1) * 80, v);
@@ -429,6 +429,17 @@ wdsr_block_tc5p_kernel(const __grid_constant__ CUtensorMap tmap_in, const bf16 *
                 for (int j = 0; j < 24; ++j)
                     v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(j < 8 ? v[24 + j] : v1[j - 8]), 1) +
                                            __shfl_down_sync(0xffffffffu, __uint_as_float(j < 8 ? v1[16 + j] : j < 16 ? v1[24 + j - 8] : v2[j - 16]), 2));
+            }
+#elif defined(B200SR_EXP_DXN) && defined(B200SR_EXP_DXN_HALFE3)
+            {   // (proxy for "the combine split over two warpgroups": half of the extra columns and shuffles on this one)
+                uint32_t v1[16];
+                tc5::tmem_ld32(tmem + lane_base + 352 + (k & 1) * 80, v);
+                tc5::tmem_ld16(tmem + lane_base + 352 + (k & 1) * 80 + 32, v1);
+                tc5::tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 12; ++j)
+                    v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v[12 + j]), 1) +
+                                           __shfl_down_sync(0xffffffffu, __uint_as_float(v1[j]), 2));
             }
 #elif defined(B200SR_EXP_DXN)
             tc5::tmem_ld32(tmem + lane_base + 352 + (k & 1) * 80, v);   // (upper bound of the mapping: E3 as light as the shipped one)
